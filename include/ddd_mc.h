@@ -1,0 +1,186 @@
+/*
+ * ddd_mc.h -- C ABI of libddd_mc.so: the B200-native (sm_100a CUDA) Metropolis Monte-Carlo
+ * binding-energy hot path of Simran-Sodhi/drug-design-dynamics (metropolisMethod/).
+ *
+ * The reference has no FFI: its boundary is a set of Go functions in `package main`
+ * (SURVEY.md 8b).  Each entry point below names the Go function(s) whose body it replaces;
+ * the cgo overlay that binds them is go/metropolis_cuda.go and is described in INTEGRATION.md.
+ * All citations are relative to /root/reference/metropolisMethod/.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  Every function returns 0 (DDD_OK) or a negative DDD_E*
+ *    code; ddd_last_error() returns a thread-local message.  The Go shim panics on non-zero,
+ *    which is what the reference's Check() does (main.go:179-183).
+ *  - Atoms travel as `xyzq`: 4 float64 per atom (X, Y, Z, Charge) -- byte-identical to Go's
+ *    `[]Atom` (datatypes.go:18-25), so cgo passes &mol.atoms[0] without repacking.
+ *  - Ligand batches are CSR: offsets[n_lig+1] in atoms, offsets[0] == 0.
+ *  - Chains: chain c = ligand (c / replicas), replica (c % replicas); it draws from the
+ *    Philox4x32-10 stream (seed, first_chain_id + c).  Chain outputs are chain-major: chain c's atoms start at
+ *    atom index replicas*offsets[lig] + replica*nL(lig).
+ *  - No CPU fallback: without a usable CUDA device every compute entry point fails with
+ *    DDD_ENODEVICE.  The caller's buffers are host memory; nothing is retained after return
+ *    except inside the opaque handles.
+ *  - Thread-safe: calls are serialised on an internal mutex and select their device on entry
+ *    (goroutines migrate between OS threads).
+ */
+#ifndef DDD_MC_H
+#define DDD_MC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDD_OK            0
+#define DDD_EINVAL       -1   /* bad argument (NULL pointer, negative size, num_procs <= 0 ...) */
+#define DDD_ENODEVICE    -2   /* no CUDA device / ddd_init not called or failed */
+#define DDD_ECUDA        -3   /* CUDA runtime error (message in ddd_last_error) */
+#define DDD_ELIMIT       -4   /* size beyond a kernel limit (ligand larger than DDD_MAX_LIGAND_ATOMS) */
+
+#define DDD_MAX_LIGAND_ATOMS 2048
+
+/* precision of the pair-energy sum inside the chains / ddd_energy_batch */
+#define DDD_PRECISION_F32  0  /* fp32 pair terms (rsqrt), fp64 accumulation of per-tile partials */
+#define DDD_PRECISION_F64  1  /* fp64 terms with the reference's exact per-term arithmetic */
+
+/* proposal */
+#define DDD_MOVE_REFERENCE 0  /* metropolis.go:154-208: per-atom jitter, Rodrigues about the ORIGIN */
+#define DDD_MOVE_RIGID     1  /* extension: centroid translation + quaternion rotation (no reference row) */
+
+/* chain status bits */
+#define DDD_STATUS_RETRY_LIMIT      1  /* collision retry bound hit (reference would spin, :155,:173) */
+#define DDD_STATUS_STREAM_EXHAUSTED 2  /* recorded uniform stream ran dry */
+
+/* Philox stream-id spaces */
+#define DDD_STREAM_PARENT_BASE    0x4000000000000000ull  /* + ligand index: replica-pick draws (:105) */
+#define DDD_STREAM_RANDOMIZE_BASE 0x2000000000000000ull  /* + ligand index: RandomizeLigandPose draws */
+
+/* datatypes.go:6-12 and the literals in metropolis.go; ddd_params_default() fills the reference values */
+typedef struct ddd_params {
+    double  k_coulomb;          /* K = 9e9            datatypes.go:6  */
+    double  threshold;          /* THRESHOLD = 5      datatypes.go:9  */
+    double  min_distance;       /* MINDISTANCE = 0.5  datatypes.go:10 */
+    double  max_angle;          /* MAXANGLE = 0.79    datatypes.go:11 */
+    double  jitter_width;       /* 0.1                metropolis.go:158-160,176-178 */
+    double  clamp_distance;     /* 1e-6               metropolis.go:255-257 */
+    double  rigid_translation;  /* RIGID only: full width of the per-axis uniform translation (0.5 A) */
+    double  rigid_angle;        /* RIGID only: max |angle| (0.79 rad) */
+    int64_t max_retries;        /* collision-retry bound per step (1024); <= 0: 2^62 */
+    int32_t precision;          /* DDD_PRECISION_*  (default F32) */
+    int32_t move_mode;          /* DDD_MOVE_*       (default REFERENCE) */
+} ddd_params;
+
+/* per-chain counters returned by ddd_run_chains (no reference counterpart; SURVEY 5 "metrics") */
+typedef struct ddd_chain_stats {
+    int64_t steps;         /* iterations of metropolis.go:119-134 executed */
+    int64_t accepted;      /* AcceptMove == true */
+    int64_t downhill;      /* accepted on newE < curE (no draw, :142-144) */
+    int64_t retries;       /* collision-rejected proposal attempts (:162,:180) */
+    int64_t draws;         /* uniforms consumed from the chain's stream */
+    int64_t status;        /* DDD_STATUS_* bits */
+    double  final_energy;  /* CalculateEnergy(protein, final pose) evaluated in fp64 (:61) */
+    double  start_energy;  /* CalculateEnergy(protein, start pose) in fp64 (:96,:118) */
+    double  chain_energy;  /* the chain's own currentEnergy at exit (fp32-summed in F32 mode) */
+} ddd_chain_stats;
+
+typedef struct ddd_receptor ddd_receptor;   /* protein Molecule resident on every initialised device */
+typedef struct ddd_screen   ddd_screen;     /* ligand x replica chain batch resident on the devices */
+
+/* ---- library ---- */
+int         ddd_init(const int *devices, int n_devices);  /* devices == NULL: every visible device */
+int         ddd_shutdown(void);
+int         ddd_num_devices(void);                         /* devices in use (0 before ddd_init) */
+const char *ddd_last_error(void);
+const char *ddd_version(void);
+void        ddd_params_default(ddd_params *p);
+
+/* ---- receptor (protein Molecule, datatypes.go:14-16) ---- */
+int     ddd_receptor_create(const double *xyzq, int64_t n_atoms, ddd_receptor **out);
+int     ddd_receptor_destroy(ddd_receptor *r);
+int64_t ddd_receptor_num_atoms(const ddd_receptor *r);
+
+/* ---- CalculateEnergy (metropolis.go:247-262), batched over ligand poses ----
+ * out_energy[n_lig]; out_abs_sum (nullable) receives sum|term| (fp64) for conditioning reports. */
+int ddd_energy_batch(const ddd_receptor *r, const int64_t *offsets, const double *lig_xyzq,
+                     int64_t n_lig, const ddd_params *p, double *out_energy, double *out_abs_sum);
+
+/* ---- SimulateEnergyMinimizationOneProc (metropolis.go:116-136), batched ----
+ * Runs n_lig*replicas independent chains of steps_per_chain iterations, each from a private
+ * copy of its ligand's start pose, entirely on device (proposal :154-208, collision test
+ * :229-242, energy :247-262, AcceptMove :141-149).
+ * recorded / recorded_offsets (both nullable): per-chain recorded uniform streams replacing
+ *   Philox (chain c reads recorded[recorded_offsets[c] .. recorded_offsets[c+1])).
+ * out_xyzq: (replicas * offsets[n_lig]) atoms x 4 doubles, chain-major final poses.
+ * out_stats[n_chains].  out_accept_trace (nullable): n_chains*steps_per_chain bytes, 1 = accepted. */
+int ddd_run_chains(const ddd_receptor *r, const int64_t *offsets, const double *lig_xyzq,
+                   int64_t n_lig, int32_t replicas, int64_t steps_per_chain, int32_t rotate,
+                   double temperature, const ddd_params *p, uint64_t seed, uint64_t first_chain_id,
+                   const double *recorded, const int64_t *recorded_offsets,
+                   double *out_xyzq, ddd_chain_stats *out_stats, uint8_t *out_accept_trace);
+
+/* ---- SimulateEnergyMinimizationParallel (:94-111) + the final CalculateEnergy (:61, :19, main.go:48),
+ *      batched over ligands = SimulateMultipleLigandsParallel (:27-67) ----
+ * num_procs replica chains of iterations/num_procs steps per ligand, then the sequential
+ * AcceptMove pick over the replicas' end poses in replica-index order (draws from stream
+ * (seed, DDD_STREAM_PARENT_BASE + first_ligand_index + i)); chain (i, r) draws from stream
+ * (seed, (first_ligand_index + i) * num_procs + r), so a ligand list split over calls or ranks
+ * sees the streams of one call.
+ * out_xyzq: offsets[n_lig] atoms x 4 doubles (same CSR as the input); out_energy[n_lig];
+ * out_chain_stats (nullable) [n_lig*num_procs]; out_picked (nullable) [n_lig]: replica kept, -1 = start pose. */
+int ddd_minimize_batch(const ddd_receptor *r, const int64_t *offsets, const double *lig_xyzq,
+                       int64_t n_lig, int64_t iterations, int32_t rotate, double temperature,
+                       int32_t num_procs, const ddd_params *p, uint64_t seed,
+                       uint64_t first_ligand_index,
+                       double *out_xyzq, double *out_energy,
+                       ddd_chain_stats *out_chain_stats, int64_t *out_picked);
+
+/* ---- CalculateRMSD (validateResults.go:50-65), batched over (simulated, reference) pairs ----
+ * atom_stride: doubles per atom in sim/ref (4 = Go []Atom layout, 3 = packed xyz).
+ * out_rmsd[n_pairs]; a pair with zero atoms yields NaN (0/0, as in Go). */
+int ddd_rmsd_batch(const int64_t *offsets, const double *sim, const double *ref,
+                   int32_t atom_stride, int64_t n_pairs, double *out_rmsd);
+
+/* ---- FindClosestAtomDistance (:290-304) / ShiftLigandCloserByThreshold (:267-285), batched ----
+ * out_lig_atom / out_prot_atom: indices of the first minimum in ligand-outer, protein-inner order. */
+int ddd_closest_atom_batch(const ddd_receptor *r, const int64_t *offsets, const double *lig_xyzq,
+                           int64_t n_lig, double *out_distance, int64_t *out_lig_atom,
+                           int64_t *out_prot_atom);
+int ddd_shift_closer_batch(const ddd_receptor *r, const int64_t *offsets, double *lig_xyzq_inout,
+                           int64_t n_lig, double threshold);
+
+/* ---- RandomizeLigandPose (validateResults.go:70-79), batched; ligand i draws from stream
+ *      (seed, DDD_STREAM_RANDOMIZE_BASE + first_ligand_index + i) ---- */
+int ddd_randomize_pose_batch(const int64_t *offsets, double *lig_xyzq_inout, int64_t n_lig,
+                             uint64_t seed, uint64_t first_ligand_index);
+
+/* ---- device-resident screen: the same chains with inputs/outputs kept in HBM ----
+ * create uploads the start poses and shards the chains over the devices (contiguous blocks,
+ * balanced by sum nL); run launches steps_per_chain iterations from the start poses on every
+ * device asynchronously; sync waits; last_kernel_ms = max over devices of the CUDA-event time
+ * of the chain kernel on its launch stream; download copies final poses + stats to the host. */
+int    ddd_screen_create(const ddd_receptor *r, const int64_t *offsets, const double *lig_xyzq,
+                         int64_t n_lig, int32_t replicas, uint64_t first_chain_id, ddd_screen **out);
+int    ddd_screen_run(ddd_screen *s, int64_t steps_per_chain, int32_t rotate, double temperature,
+                      const ddd_params *p, uint64_t seed);
+int    ddd_screen_sync(ddd_screen *s);
+double ddd_screen_last_kernel_ms(const ddd_screen *s);
+int    ddd_screen_download(ddd_screen *s, double *out_xyzq, ddd_chain_stats *out_stats);
+int    ddd_screen_destroy(ddd_screen *s);
+
+/* ---- sharding plan (pure host logic, works without a device): chains
+ *      [out_begin[k], out_begin[k+1]) go to shard k; contiguous blocks (the reference's output order,
+ *      metropolis.go:34-49) balanced by sum(nL + 1).  out_begin has n_shards + 1 entries. ---- */
+int ddd_shard_plan(const int64_t *offsets, int64_t n_lig, int32_t replicas, int32_t n_shards,
+                   int64_t *out_begin);
+
+/* ---- introspection for the roofline report ---- */
+int ddd_device_info(int ordinal, int32_t *sm_count, int32_t *clock_khz, int32_t *cc_major,
+                    int32_t *cc_minor, char *name, int32_t name_cap);
+int ddd_chain_kernel_info(int32_t precision, int32_t *threads, int32_t *regs, int32_t *static_smem,
+                          int32_t *max_blocks_per_sm_at_nl40);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDD_MC_H */
