@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- Metropolis Monte-Carlo hot path: MC steps/s and atom-pair evaluations/s on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config 2|3] [--chain-steps S]
+
+One bench "step" = one pass of the hot path over one batch of synthetic input: every ligand chain of
+the workload runs `chain_steps` (default 10 000) Metropolis iterations (metropolis.go:119-134) against
+the synthetic 5 000-atom receptor (BASELINE.json configs[1]):
+
+  config 2 (default, the N=1 headline): 1024 ligands x 40 atoms x 1 chain per GPU.  With N > 1 every rank
+           runs its own 1024 ligands (ligand indices rank*1024 ...): weak scaling, no data-path collective.
+  config 3: 4096 ligands x 8 replica chains, sharded over the N ranks by contiguous ligand blocks (strong).
+
+`value`  = MC steps/s, whole job, chains resident in HBM (ddd_screen_*), max over ranks of the device time.
+`e2e`    = the same metric through the reference-facing call (ddd_minimize_batch = SimulateMultipleLigands-
+           Parallel, main.go:144) with pinned HOST buffers: H2D of the start poses and D2H of poses/energies
+           inside the timed region.
+`roofline` = 12 flop/pair x pair evaluations / CUDA-event time of the chain kernel (measured on the library's
+           own launch stream) against the FP32 FMA-pipe peak SMs*128*2*f_max (f_max = sm_max_mhz from
+           MEASURED_PEAKS.json); the binding pipe is MUFU.RSQ (16/clk/SM = 75 % of that peak).
+`cpu_baseline` = the C float64 restatement of the reference (oracle/, "port": NOT Go -- there is no Go
+           toolchain) timed on this box's host cores on a bounded sample of the same workload.
+--impl reference times that restatement alone (rank 0 only), same metric/config/units.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+NP, NL, TEMPERATURE = 5000, 40, 310.15
+FLOP_PER_PAIR = 12          # 3 sub, 3 mul + 2 add, rsqrt, clamp, mul + add
+METRIC, UNIT = "mc_steps_per_sec", "MC steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3])
+    ap.add_argument("--chain-steps", type=int, default=10000)
+    ap.add_argument("--ligands", type=int, default=0, help="override ligands per GPU (config 2) / total (config 3)")
+    ap.add_argument("--chain-threads", type=int, default=0, help="force the chain CTA width (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()), "MEASURED_PEAKS.json"
+    return {"sm_max_mhz": 1965.0, "hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def workload(config, rank, world, n_override):
+    """(first global ligand index, ligands of this rank, replicas, description)"""
+    if config == 2:
+        n = n_override or 1024
+        return rank * n, n, 1, f"synthetic {NP}-atom receptor x {n} ligands x {NL} atoms per GPU, 1 chain each"
+    total = n_override or 4096
+    lo, hi = rank * total // world, (rank + 1) * total // world
+    return lo, hi - lo, 8, f"synthetic {NP}-atom receptor x {total} ligands x {NL} atoms x 8 replica chains, sharded"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        mhz, mx, reasons, power = [], None, set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                mhz.append(float(f[1])); mx = float(f[2]); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "power_w_max": max(power) if power else None, "samples": len(mhz)}
+
+
+def cpu_oracle_rate(prot, off, lig, seconds, variant=""):
+    """Time the C restatement of the reference on all host cores; returns (steps/s, cores, sample text, pairs/s)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from _oracle import Oracle            # the one place bench.py executes oracle/: the CPU baseline
+    orc = Oracle(variant)
+    cores = os.cpu_count() or 1
+    n_lig = min(len(off) - 1, max(cores, 8) * 2)
+    o, x = off[:n_lig + 1], lig[:off[n_lig]]
+    sec, st, pr = orc.bench_chains(prot, o, x, 1, 20, True, TEMPERATURE, 1, cores)          # calibration
+    steps = max(20, int(20 * seconds / max(sec, 1e-3)))
+    sec, st, pr = orc.bench_chains(prot, o, x, 1, steps, True, TEMPERATURE, 1, cores)
+    return st / sec, cores, f"{n_lig} ligands x {NL} atoms x {steps} MC steps vs the {NP}-atom receptor ({sec:.1f} s, {orc.build_info()})", pr / sec
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    import ddd_loader
+    ddd = ddd_loader.load()
+    capi, synth = ddd.capi, ddd.synth
+    peaks, peaks_src = measured_peaks()
+
+    first, n_lig, replicas, desc = workload(args.config, rank, world, args.ligands)
+    prot = synth.make_receptor(NP)
+
+    # ------------------------------------------------------------------ reference arm: CPU restatement only
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        off, lig = synth.make_ligands([NL] * 64, prot)
+        per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+        rates = []
+        for i in range(args.warmup + args.steps):
+            r, cores, sample, pr = cpu_oracle_rate(prot, off, lig, per_step)
+            if i >= args.warmup:
+                rates.append((r, pr, sample))
+        v = float(np.mean([r[0] for r in rates]))
+        out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "pair_evals_per_sec": float(np.mean([r[1] for r in rates])),
+               "config": {"workload": desc, "chain_steps": args.chain_steps, "rotate": True, "temperature": TEMPERATURE,
+                          "note": "reference = C float64 restatement of metropolis.go on host cores (no Go toolchain in this image); "
+                                  "each step is a bounded sample of the workload"},
+               "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": rates[-1][2]},
+               "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "gpu_launches": 0}
+        print(json.dumps(out))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU restatement)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    capi.init([local_rank])
+    info = capi.device_info(0)
+
+    sizes = [NL] * n_lig
+    off, lig = synth.make_ligands(sizes, prot, first_index=first)
+    rec = capi.Receptor(prot)
+    prm = capi.default_params()                       # F32 pair sum, REFERENCE move, reference constants
+    first_chain = first * replicas
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident: value + roofline
+    scr = capi.Screen(rec, off, lig, replicas, first_chain_id=first_chain)
+    if args.chain_threads:
+        scr.set_chain_threads(args.chain_threads)
+    for w in range(args.warmup):
+        scr.run(args.chain_steps, True, TEMPERATURE, prm, seed=100 + w)
+        scr.sync()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    kernel_ms = 0.0
+    for k in range(args.steps):
+        scr.run(args.chain_steps, True, TEMPERATURE, prm, seed=200 + k)
+        scr.sync()                                    # device-side completion of the step (cudaStreamSynchronize)
+        kernel_ms += scr.last_kernel_ms()             # CUDA events on the library's launch stream
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    _, st = scr.download()
+    my_steps = float(st["steps"].sum()) * 1.0         # steps of the LAST bench step, all chains of this rank
+    assert my_steps == n_lig * replicas * args.chain_steps, "chains stopped early"
+    assert not np.any(st["status"]), "chain status flags set"
+    width = scr.chain_threads()
+    scr.close()
+    dev_s = max_over_ranks(kernel_ms * 1e-3)          # max over ranks of the device time of K steps
+    wall_s = max_over_ranks(wall)
+    total_steps = sum_over_ranks(my_steps) * args.steps
+    total_pairs = total_steps * NP * NL
+    value = total_steps / dev_s
+
+    # ---- end to end through the reference-facing call with pinned host buffers
+    pin_lig = torch.empty(lig.shape, dtype=torch.float64).pin_memory()
+    pin_lig.numpy()[:] = lig
+    h_lig = pin_lig.numpy()
+    n_e2e = max(1, min(args.steps, 3))
+    if replicas == 1:
+        call = lambda seed: capi.minimize_batch(rec, off, h_lig, args.chain_steps, True, TEMPERATURE, 1, prm,
+                                                seed=seed, first_ligand_index=first)
+    else:
+        call = lambda seed: capi.minimize_batch(rec, off, h_lig, args.chain_steps * replicas, True, TEMPERATURE,
+                                                replicas, prm, seed=seed, first_ligand_index=first)
+    call(300)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(n_e2e):
+        out_pose, out_energy, picked = call(400 + k)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = sum_over_ranks(n_lig * replicas * args.chain_steps) * n_e2e / e2e_s
+    h2d = int(h_lig.nbytes + off.nbytes) * world
+    d2h = int(h_lig.nbytes * replicas + n_lig * replicas * capi.STATS_DTYPE.itemsize) * world
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    fp32_peak = info["sm_count"] * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12          # TFLOP/s per GPU
+    achieved = FLOP_PER_PAIR * total_pairs / dev_s / 1e12 / world                     # per GPU
+    cpu = None
+    if not args.no_cpu_baseline:
+        r, cores, sample, pr = cpu_oracle_rate(prot, off[:min(n_lig, 64) + 1], lig[:off[min(n_lig, 64)]], 12.0)
+        rp, _, sample_p, _ = cpu_oracle_rate(prot, off[:min(n_lig, 64) + 1], lig[:off[min(n_lig, 64)]], 6.0, "pow")
+        cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "pair_evals_per_sec": pr,
+               "pow_variant_value": rp,
+               "note": "C float64 restatement of metropolis.go (x*x squares), NOT Go; pow_variant mimics the cost of Go's out-of-line math.Pow"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_s * 1e3 / args.steps, "higher_is_better": True,
+        "scaling": "weak" if args.config == 2 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "pair_evals_per_sec": total_pairs / dev_s,
+        "config": {"workload": desc, "receptor_atoms": NP, "ligand_atoms": NL, "ligands_per_gpu": n_lig, "replicas": replicas,
+                   "chain_steps": args.chain_steps, "rotate": True, "temperature": TEMPERATURE, "move": "REFERENCE",
+                   "pair_precision": "fp32 terms, fp64 accumulation", "chain_cta_threads": width,
+                   "l2": "receptor (80 KB) and poses are L1/L2-resident by design; the kernel is FP32/MUFU-bound, HBM traffic ~0, so no L2 flush applies",
+                   "parallelism": f"{world} x independent chain shards, no collective"},
+        "wall_ms_per_step": wall_s * 1e3 / args.steps,
+        "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                     "traffic": None, "peak_source": f"SMs*128 lanes*2*sm_max_mhz ({peaks['sm_max_mhz']:.0f} MHz from {peaks_src})",
+                     "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": total_pairs / args.steps / world,
+                     "kernel_ms_per_launch": dev_s * 1e3 / args.steps,
+                     "mufu_bound_frac_of_peak": 0.75, "frac_of_mufu_bound": achieved / fp32_peak / 0.75},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "call": "ddd_minimize_batch (SimulateMultipleLigandsParallel, main.go:144) with pinned host buffers", "steps": n_e2e},
+        "gpu_launches": args.steps * world,
+        "clocks": clocks,
+        "device": info["name"],
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -20,7 +20,8 @@ SYMBOLS = [
     "ddd_energy_batch", "ddd_run_chains", "ddd_minimize_batch", "ddd_rmsd_batch",
     "ddd_closest_atom_batch", "ddd_shift_closer_batch", "ddd_randomize_pose_batch",
     "ddd_screen_create", "ddd_screen_run", "ddd_screen_sync", "ddd_screen_last_kernel_ms",
-    "ddd_screen_download", "ddd_screen_destroy", "ddd_shard_plan", "ddd_device_info",
+    "ddd_screen_download", "ddd_screen_destroy", "ddd_screen_set_chain_threads", "ddd_screen_chain_threads",
+    "ddd_shard_plan", "ddd_device_info",
     "ddd_chain_kernel_info",
 ]
 
@@ -75,7 +76,8 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.build_library()
+    import os
+    path = os.environ.get("DDD_MC_LIB") or _build.build_library()     # DDD_MC_LIB: tuning builds (tools/), never a fallback
     L = C.CDLL(str(path))
     vp, i32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
     sig = {
@@ -100,6 +102,8 @@ def lib() -> C.CDLL:
         "ddd_screen_create": (C.c_int, [vp, vp, vp, i64, i32, u64, C.POINTER(vp)]),
         "ddd_screen_run": (C.c_int, [vp, i64, i32, dbl, C.POINTER(Params), u64]),
         "ddd_screen_sync": (C.c_int, [vp]),
+        "ddd_screen_set_chain_threads": (C.c_int, [vp, i32]),
+        "ddd_screen_chain_threads": (i32, [vp]),
         "ddd_screen_last_kernel_ms": (dbl, [vp]),
         "ddd_screen_download": (C.c_int, [vp, vp, vp]),
         "ddd_screen_destroy": (C.c_int, [vp]),
@@ -329,6 +333,12 @@ class Screen:
     def run(self, steps, rotate, temperature, params: Params | None = None, seed=1):
         p = params or default_params()
         _check(lib().ddd_screen_run(self._h, steps, int(bool(rotate)), float(temperature), C.byref(p), seed))
+
+    def set_chain_threads(self, threads: int):
+        _check(lib().ddd_screen_set_chain_threads(self._h, threads))
+
+    def chain_threads(self) -> int:
+        return int(lib().ddd_screen_chain_threads(self._h))
 
     def sync(self):
         _check(lib().ddd_screen_sync(self._h))

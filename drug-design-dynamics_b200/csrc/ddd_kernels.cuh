@@ -1,6 +1,6 @@
 // ddd_kernels.cuh -- sm_100a device code of the Metropolis Monte-Carlo hot path.
 //
-// One CTA (kThreads = 128) runs one independent ligand chain of
+// One CTA (32..256 threads, chosen from the chain count) runs one independent ligand chain of
 // SimulateEnergyMinimizationOneProc (reference metropolisMethod/metropolis.go:116-136)
 // from start to finish on device: proposal (:154-208), collision test (:229-242),
 // protein x ligand Coulomb sum (:247-262) and AcceptMove (:141-149), with no host round trip.
@@ -16,10 +16,10 @@
 
 namespace ddd {
 
-constexpr int kThreads = 128;   // threads per chain CTA
+constexpr int kThreads = 128;   // threads per CTA of the batched helper kernels (energy / closest / randomize)
 constexpr int kTileA   = 4;     // receptor atoms held in registers per lane per tile (fp32 path)
-constexpr int kTile    = kThreads * kTileA;
-constexpr float kPadCoord = 1.0e4f;   // padding receptor atoms: q = 0, parked 1e4 A away
+constexpr int kRecPad  = 256;   // receptor fp32 array is padded to a multiple of the widest chain CTA
+constexpr float kPadCoord = 1.0e4f;   // padding atoms: q = 0, parked 1e4 A away (receptor +, ligand -)
 
 // receptor atom, fp64 master copy: absolute coordinates, Go Atom layout (datatypes.go:18-25)
 struct __align__(32) Atom64 { double x, y, z, q; };
@@ -33,7 +33,7 @@ struct DevParams {
 };
 
 struct RecView {
-    const float4 *f32;           // (x-cx, y-cy, z-cz, q), padded to a multiple of kThreads
+    const float4 *f32;           // (x-cx, y-cy, z-cz, q), padded to a multiple of kRecPad
     const Atom64 *f64;           // absolute, n atoms
     int n, n_pad;
     double cx, cy, cz;           // receptor centroid: origin of the fp32 frame
@@ -101,6 +101,27 @@ struct Stream {
         const double v0 = u53(a[0], a[1]), v1 = u53(a[2], a[3]), v2 = u53(b[0], b[1]), v3 = u53(b[2], b[3]);
         if (index & 1) { u[0] = v1; u[1] = v2; u[2] = v3; } else { u[0] = v0; u[1] = v1; u[2] = v2; }
     }
+    // four consecutive draws (axis X,Y,Z and theta): two Philox blocks when index is even, three when odd
+    __device__ __forceinline__ void draw4(uint64_t index, double u[4], int &status) const {
+        if (rec) {
+            for (int k = 0; k < 4; ++k) u[k] = draw(index + k, status);
+            return;
+        }
+        const uint64_t blk = index >> 1;
+        uint32_t a[4], b[4];
+        philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)id, (uint32_t)(id >> 32),
+                      (uint32_t)seed, (uint32_t)(seed >> 32), a);
+        philox4x32_10((uint32_t)(blk + 1), (uint32_t)((blk + 1) >> 32), (uint32_t)id, (uint32_t)(id >> 32),
+                      (uint32_t)seed, (uint32_t)(seed >> 32), b);
+        if (index & 1) {
+            uint32_t c[4];
+            philox4x32_10((uint32_t)(blk + 2), (uint32_t)((blk + 2) >> 32), (uint32_t)id, (uint32_t)(id >> 32),
+                          (uint32_t)seed, (uint32_t)(seed >> 32), c);
+            u[0] = u53(a[2], a[3]); u[1] = u53(b[0], b[1]); u[2] = u53(b[2], b[3]); u[3] = u53(c[0], c[1]);
+        } else {
+            u[0] = u53(a[0], a[1]); u[1] = u53(a[2], a[3]); u[2] = u53(b[0], b[1]); u[3] = u53(b[2], b[3]);
+        }
+    }
 };
 
 // ------------------------------------------------------------------ reductions
@@ -110,19 +131,30 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Deterministic block sum returned to every thread.  `red` holds 2 x (kThreads/32) doubles used
+// Deterministic block sum returned to every thread.  `red` holds 2 x kMaxWarps doubles used
 // alternately (parity) so that back-to-back calls need only the one barrier inside.
+constexpr int kMaxWarps = 8;
+template <int THREADS>
 __device__ __forceinline__ double block_sum(double v, double *red, int &parity) {
     v = warp_sum(v);
-    double *buf = red + parity * (kThreads / 32);
+    if (THREADS == 32) return v;
+    double *buf = red + parity * kMaxWarps;
     parity ^= 1;
     if ((threadIdx.x & 31) == 0) buf[threadIdx.x >> 5] = v;
     __syncthreads();
     double s = buf[0];
 #pragma unroll
-    for (int w = 1; w < kThreads / 32; ++w) s += buf[w];
+    for (int w = 1; w < THREADS / 32; ++w) s += buf[w];
     return s;
 }
+
+// packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2): one instruction, two lanes of a register pair
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 __device__ __forceinline__ float rsqrt_approx(float x) {
     float r;
@@ -131,49 +163,99 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
 }
 
 // ------------------------------------------------------------------ pair sums (CalculateEnergy :247-262)
-// fp32 path.  Lane holds A receptor atoms in registers, ligand atoms are broadcast from shared
-// memory as float4 (x, y, z, q) in the receptor-centred frame.  Per pair: 3 FADD, FMUL + 2 FFMA
-// (d^2), MUFU.RSQ, FMNMX (clamp), FFMA (s += q_l * 1/d).  q_p and K are applied per tile / per call.
+// fp32 path.  A lane holds A receptor atoms in registers; the ligand sits in shared memory packed
+// by PAIRS of atoms (2k, 2k+1) in the receptor-centred frame:
+//     lf[2k] = (-x0, -x1, -y0, -y1)     lf[2k+1] = (-z0, -z1, q0, q1)
+// so that every FADD2 / FMUL2 / FFMA2 evaluates two ligand atoms against one receptor atom (the
+// receptor coordinate enters as the broadcast-scalar operand).  Per receptor atom and ligand PAIR:
+// 3 FADD2, FMUL2 + 2 FFMA2 (d^2), 2 MUFU.RSQ, 2 FMNMX (clamp d >= 1e-6 <=> 1/d <= 1e6), FFMA2
+// (s += q_l / d): 11 issue slots per 2 pair terms.  MUFU (16/clk/SM) is the binding pipe.
+// q_p is applied once per tile and K once per call.  An odd ligand is padded with a q = 0 atom.
 template <int A>
-__device__ __forceinline__ double tile_sum_f32(const float4 *__restrict__ rec, int base,
-                                               const float4 *__restrict__ lf, int nl, float rinv_max) {
-    float4 P[A];
-    float s[A];
+__device__ __forceinline__ float warp_tile_sum_f32(const float4 *__restrict__ rec, int base,
+                                                   const ulonglong2 *__restrict__ lf2, int n_pairs, float rinv_max) {
+    f32x2 px[A], py[A], pz[A], s[A];
+    float q[A];
+    const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int a = 0; a < A; ++a) { P[a] = __ldg(rec + base + a * kThreads + threadIdx.x); s[a] = 0.f; }
+    for (int a = 0; a < A; ++a) {
+        const float4 P = __ldg(rec + base + a * 32 + lane);
+        px[a] = pack2(P.x, P.x); py[a] = pack2(P.y, P.y); pz[a] = pack2(P.z, P.z);
+        q[a] = P.w; s[a] = pack2(0.f, 0.f);
+    }
 #pragma unroll 2
-    for (int l = 0; l < nl; ++l) {
-        const float4 L = lf[l];
+    for (int k = 0; k < n_pairs; ++k) {
+        const ulonglong2 Lxy = lf2[2 * k], Lzq = lf2[2 * k + 1];
 #pragma unroll
         for (int a = 0; a < A; ++a) {
-            const float dx = P[a].x - L.x, dy = P[a].y - L.y, dz = P[a].z - L.z;
-            const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            const float r = fminf(rsqrt_approx(d2), rinv_max);
-            s[a] = fmaf(L.w, r, s[a]);
+            const f32x2 dx = add2(px[a], Lxy.x), dy = add2(py[a], Lxy.y), dz = add2(pz[a], Lzq.x);
+            const f32x2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+            float d2a, d2b;
+            unpack2(d2, d2a, d2b);
+            const float ra = fminf(rsqrt_approx(d2a), rinv_max), rb = fminf(rsqrt_approx(d2b), rinv_max);
+            s[a] = fma2(Lzq.y, pack2(ra, rb), s[a]);
         }
     }
-    double e = 0.0;
+    float t = 0.f;                       // fp32 within the lane's A * nl terms, fp64 beyond
 #pragma unroll
-    for (int a = 0; a < A; ++a) e = fma((double)P[a].w, (double)s[a], e);
-    return e;
+    for (int a = 0; a < A; ++a) { float sa, sb; unpack2(s[a], sa, sb); t = fmaf(q[a], sa + sb, t); }
+    return t;
 }
 
-// returns this thread's share of sum_p sum_l q_p q_l / max(d, clamp)   (K applied by the caller)
-__device__ __forceinline__ double pair_sum_f32(const RecView &rv, const float4 *lf, int nl, float rinv_max) {
+// sum_p sum_l q_p q_l / max(d, clamp) for the whole CTA, returned to every thread (K applied by the caller).
+// The receptor is cut into work items of `chunk` warp tiles (32 lanes x kTileA atoms); the warps of the CTA
+// pull items from a shared-memory counter, so a warp that the scheduler favours simply takes more items
+// instead of idling at the barrier.  Each item's sum is stored under its item id and the items are added
+// in id order afterwards: the result does not depend on which warp computed what (bit-reproducible).
+// `ctl[0]` must be 0 on entry (reset by one thread before the barrier that precedes the call).
+constexpr int kMaxItems = 256;
+constexpr int kWarpTile = 32 * kTileA;
+#ifndef DDD_DYNAMIC_TILES
+#define DDD_DYNAMIC_TILES 1
+#endif
+template <int THREADS>
+__device__ __forceinline__ double cta_pair_sum_f32(const RecView &rv, const float4 *lf, int nl, float rinv_max,
+                                                   int *ctl, double *item_out) {
+    const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
+    const int n_pairs = (nl + 1) >> 1;
+    const int lane = threadIdx.x & 31;
+    const int n_wt = (rv.n + kWarpTile - 1) / kWarpTile;                 // n_pad is a multiple of kRecPad >= kWarpTile
+    const int chunk = (n_wt + kMaxItems - 1) / kMaxItems;
+    const int n_items = chunk ? (n_wt + chunk - 1) / chunk : 0;
+    int next_static = threadIdx.x >> 5;
+    for (;;) {
+        int it = 0;
+        if (DDD_DYNAMIC_TILES && THREADS > 32) {
+            if (lane == 0) it = atomicAdd(ctl, 1);
+            it = __shfl_sync(0xffffffffu, it, 0);
+        } else { it = next_static; next_static += THREADS / 32; }
+        if (it >= n_items) break;
+        const int t_end = min((it + 1) * chunk, n_wt);
+        double acc = 0.0;
+        for (int t = it * chunk; t < t_end; ++t)
+            acc += (double)warp_tile_sum_f32<kTileA>(rv.f32, t * kWarpTile, lf2, n_pairs, rinv_max);
+        acc = warp_sum(acc);
+        if (lane == 0) item_out[it] = acc;
+    }
+    __syncthreads();
     double e = 0.0;
-    int base = 0;
-    for (; base + kTile <= rv.n_pad; base += kTile) e += tile_sum_f32<kTileA>(rv.f32, base, lf, nl, rinv_max);
-    for (; base < rv.n_pad; base += kThreads) e += tile_sum_f32<1>(rv.f32, base, lf, nl, rinv_max);
-    return e;
+    for (int it = lane; it < n_items; it += 32) e += item_out[it];
+    return warp_sum(e);
+}
+
+// write atom i of the fp32 pose in the pair-packed layout
+__device__ __forceinline__ void store_lig_f32(float4 *lf, int i, float x, float y, float z, float q) {
+    float *f = reinterpret_cast<float *>(lf + 2 * (i >> 1)) + (i & 1);
+    f[0] = -x; f[2] = -y; f[4] = -z; f[6] = q;
 }
 
 // fp64 path: the reference's per-term arithmetic, term by term (no contraction: -fmad=false).
-template <bool WITH_ABS>
+template <int THREADS, bool WITH_ABS>
 __device__ __forceinline__ double pair_sum_f64(const RecView &rv, const double *lx, const double *ly,
                                                const double *lz, const double *lq, int nl,
                                                double K, double clampd, double *abs_out) {
     double e = 0.0, ab = 0.0;
-    for (int p = threadIdx.x; p < rv.n; p += kThreads) {
+    for (int p = threadIdx.x; p < rv.n; p += THREADS) {
         const Atom64 P = rv.f64[p];
         for (int l = 0; l < nl; ++l) {
             const double ddx = P.x - lx[l], ddy = P.y - ly[l], ddz = P.z - lz[l];
@@ -218,38 +300,102 @@ struct ChainStats {
 };
 
 __host__ __device__ inline size_t chain_smem_bytes(int nl_cap) {
-    // cur xyz, prev xyz, q : 7 double arrays; float4 pose; 2 x 4 reduction doubles
-    return (size_t)nl_cap * (7 * sizeof(double) + sizeof(float4)) + 2 * (kThreads / 32) * sizeof(double);
+    // cur xyz, prev xyz, q : 7 double arrays; packed fp32 pose; 2 x kMaxWarps reduction doubles; work-item sums;
+    // 4 counters; 4 control words (item counter, two alternating "collision possible" flags)
+    return (size_t)nl_cap * (7 * sizeof(double) + sizeof(float4)) + (2 * kMaxWarps + kMaxItems) * sizeof(double) +
+           4 * sizeof(long long) + 4 * sizeof(int);
 }
 
+// Views into the CTA's dynamic shared memory.  Only the capacity is kept in a register; every array address is
+// base + constant * cap, recomputed at the point of use (ten live 64-bit pointers would cost 20 registers of the
+// 64 the chain kernel is allowed and wreck the schedule of the pair loop).
 struct ChainSmem {
-    double *cx, *cy, *cz, *px, *py, *pz, *q;
-    float4 *lf;
-    double *red;
-    __device__ __forceinline__ ChainSmem(unsigned char *base, int cap) {
-        cx = reinterpret_cast<double *>(base);
-        cy = cx + cap; cz = cy + cap; px = cz + cap; py = px + cap; pz = py + cap; q = pz + cap;
-        lf = reinterpret_cast<float4 *>(q + cap);
-        red = reinterpret_cast<double *>(lf + cap);
+    int cap;
+    __device__ __forceinline__ ChainSmem(unsigned char *, int cap_) : cap(cap_) {}
+    __device__ __forceinline__ double *base() const {
+        extern __shared__ __align__(16) unsigned char ddd_smem_raw[];
+        return reinterpret_cast<double *>(ddd_smem_raw);
     }
+    __device__ __forceinline__ double *cx() const { return base(); }
+    __device__ __forceinline__ double *cy() const { return base() + cap; }
+    __device__ __forceinline__ double *cz() const { return base() + 2 * cap; }
+    __device__ __forceinline__ double *px() const { return base() + 3 * cap; }
+    __device__ __forceinline__ double *py() const { return base() + 4 * cap; }
+    __device__ __forceinline__ double *pz() const { return base() + 5 * cap; }
+    __device__ __forceinline__ double *q() const { return base() + 6 * cap; }
+    __device__ __forceinline__ float4 *lf() const { return reinterpret_cast<float4 *>(base() + 7 * cap); }
+    __device__ __forceinline__ double *red() const { return reinterpret_cast<double *>(lf() + cap); }
+    __device__ __forceinline__ double *item_out() const { return red() + 2 * kMaxWarps; }
+    __device__ __forceinline__ long long *cnt() const { return reinterpret_cast<long long *>(item_out() + kMaxItems); }
+    __device__ __forceinline__ int *ctl() const { return reinterpret_cast<int *>(cnt() + 4); }
 };
 
 // IsCollisionFree (:229-242) over all i<j pairs, spread over the CTA; returns "this thread saw
 // a pair closer than min_distance".  Pairs are enumerated as (i, i+m mod nl), m = 1..nl/2.
+// sqrt(d2) < min_distance is decided from d2 alone unless d2 lies within 1e-9 (relative) of
+// min_distance^2, where the reference's own sqrt comparison (:235-236) is evaluated.
+template <int THREADS>
 __device__ __forceinline__ bool collision_partial(const ChainSmem &s, int nl, double min_distance) {
     const int full_rows = (nl - 1) / 2;
     const int n_full = full_rows * nl;
     const int total = n_full + ((nl & 1) ? 0 : nl / 2);
+    const double m2 = min_distance * min_distance, m2_lo = m2 * (1.0 - 1e-9), m2_hi = m2 * (1.0 + 1e-9);
     bool hit = false;
-    for (int w = threadIdx.x; w < total; w += kThreads) {
+    for (int w = threadIdx.x; w < total; w += THREADS) {
         int i, m;
         if (w < n_full) { m = w / nl + 1; i = w - (m - 1) * nl; } else { i = w - n_full; m = nl / 2; }
         int j = i + m; if (j >= nl) j -= nl;
-        const double dx = s.cx[i] - s.cx[j], dy = s.cy[i] - s.cy[j], dz = s.cz[i] - s.cz[j];
-        const double distance = sqrt(dx * dx + dy * dy + dz * dz);       // :235
-        hit |= (distance < min_distance);                                 // :236
+        const double dx = s.cx()[i] - s.cx()[j], dy = s.cy()[i] - s.cy()[j], dz = s.cz()[i] - s.cz()[j];
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 < m2_lo) hit = true;
+        else if (d2 < m2_hi) hit |= (sqrt(d2) < min_distance);              // :235-236
     }
     return hit;
+}
+
+// fp32 screen in front of IsCollisionFree, on the pair-packed fp32 pose (same FADD2/FMUL2/FFMA2 form as
+// the energy loop): atom i against ligand pairs (2k, 2k+1), both orders of every pair, self excluded.
+// Returns true when some pair lies within 2 % (+ the fp32 coordinate rounding bound) of min_distance^2,
+// i.e. "fp32 cannot rule a collision out"; only then does the CTA run the exact fp64 test above.
+struct CollisionPlan { int i0, i_step, k0, k_step; };      // fixed per chain: no division inside the step loop
+
+template <int THREADS>
+__device__ __forceinline__ CollisionPlan collision_plan(int nl) {
+    CollisionPlan p;
+    const int tid = threadIdx.x;
+    if (nl <= 0) { p.i0 = 0; p.i_step = 1; p.k0 = 0; p.k_step = 1; return p; }
+    const int groups = THREADS / nl;
+    if (groups >= 1) {                       // every atom gets `groups` threads, each taking every groups-th pair
+        p.i0 = (tid < groups * nl) ? tid % nl : nl; p.i_step = nl; p.k0 = tid / nl; p.k_step = groups;
+    } else { p.i0 = tid; p.i_step = THREADS; p.k0 = 0; p.k_step = 1; }
+    return p;
+}
+
+// returns bit 1: some pair is certainly closer than min_distance; bit 0: some pair is inside the uncertainty band
+__device__ __forceinline__ int collision_screen_f32(const ChainSmem &s, int nl, const CollisionPlan &cp, float m2) {
+    const int n_pairs = (nl + 1) >> 1;
+    const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(s.lf());
+    const float *lff = reinterpret_cast<const float *>(s.lf());
+    float dmin = 3.0e38f, slack = 0.f;
+    for (int i = cp.i0; i < nl; i += cp.i_step) {
+        const float *mine = lff + 8 * (i >> 1) + (i & 1);
+        const float xi = -mine[0], yi = -mine[2], zi = -mine[4];
+        // |error of the fp32 d2| of a pair near min_distance <= ~4e-7 * (|x|+|y|+|z|); 1e-6 * (...) is a safe bound
+        slack = fmaxf(slack, 1e-6f * (fabsf(xi) + fabsf(yi) + fabsf(zi) + 1.0f));
+        const f32x2 ax = pack2(xi, xi), ay = pack2(yi, yi), az = pack2(zi, zi);
+        for (int k = cp.k0; k < n_pairs; k += cp.k_step) {
+            const ulonglong2 Lxy = lf2[2 * k], Lzq = lf2[2 * k + 1];
+            const f32x2 dx = add2(ax, Lxy.x), dy = add2(ay, Lxy.y), dz = add2(az, Lzq.x);
+            const f32x2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+            float d2a, d2b;
+            unpack2(d2, d2a, d2b);
+            if (k == (i >> 1)) { if (i & 1) d2b = 3.0e38f; else d2a = 3.0e38f; }       // j == i
+            dmin = fminf(dmin, fminf(d2a, d2b));
+        }
+    }
+    const int hit = dmin < m2 * 0.98f - slack;
+    const int near = dmin < m2 * 1.02f + slack;
+    return (hit << 1) | (near & ~hit);
 }
 
 // RotateAtom (:213-224): Rodrigues about an axis through the origin, reference expression order
@@ -265,28 +411,37 @@ __device__ __forceinline__ void rotate_atom(double &x, double &y, double &z, dou
 // axis draws X,Y,Z (U*2-1), Normalize (no-op at zero magnitude, datatypes.go:33-40), theta draw (:192-200)
 __device__ __forceinline__ void draw_axis_angle(const Stream &st, uint64_t pos, double max_angle, int &status,
                                                 double &ax, double &ay, double &az, double &theta) {
-    ax = st.draw(pos, status) * 2 - 1;
-    ay = st.draw(pos + 1, status) * 2 - 1;
-    az = st.draw(pos + 2, status) * 2 - 1;
+    double u[4];
+    st.draw4(pos, u, status);
+    ax = u[0] * 2 - 1;
+    ay = u[1] * 2 - 1;
+    az = u[2] * 2 - 1;
     const double mag = sqrt(ax * ax + ay * ay + az * az);
     if (mag > 0) { ax /= mag; ay /= mag; az /= mag; }
-    theta = (st.draw(pos + 3, status) * 2 - 1) * max_angle;
+    theta = (u[3] * 2 - 1) * max_angle;
 }
 
-template <bool PRECISE>
+template <int THREADS, bool PRECISE>
 __device__ __forceinline__ double chain_energy(const ChainArgs &a, const ChainSmem &s, int nl, int &parity) {
-    double part;
-    if (PRECISE) part = pair_sum_f64<false>(a.rec, s.cx, s.cy, s.cz, s.q, nl, a.prm.k_coulomb, a.prm.clamp_distance, nullptr);
-    else part = pair_sum_f32(a.rec, s.lf, nl, a.prm.rinv_max);
-    double e = block_sum(part, s.red, parity);
-    if (!PRECISE) e *= a.prm.k_coulomb;
-    return e;
+    if (!PRECISE) return a.prm.k_coulomb * cta_pair_sum_f32<THREADS>(a.rec, s.lf(), nl, a.prm.rinv_max, s.ctl(), s.item_out());
+    const double part = pair_sum_f64<THREADS, false>(a.rec, s.cx(), s.cy(), s.cz(), s.q(), nl, a.prm.k_coulomb, a.prm.clamp_distance, nullptr);
+    return block_sum<THREADS>(part, s.red(), parity);
 }
 
-template <bool PRECISE>
-__global__ void __launch_bounds__(kThreads) mc_chain_kernel(const ChainArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const ChainSmem s(smem_raw, a.nl_cap);
+__device__ __forceinline__ void store_pose(const ChainArgs &a, const ChainSmem &s, int i, double x, double y, double z) {
+    s.cx()[i] = x; s.cy()[i] = y; s.cz()[i] = z;
+    store_lig_f32(s.lf(), i, (float)(x - a.rec.cx), (float)(y - a.rec.cy), (float)(z - a.rec.cz), (float)s.q()[i]);
+}
+
+// One CTA of THREADS threads = one chain.  THREADS is chosen by the host from the number of chains
+// (few chains: wide CTAs for latency; many chains: narrow CTAs so the per-step proposal / collision /
+// accept work, which every warp of the CTA repeats, is amortised over more pair terms per warp).
+#ifndef DDD_CHAIN_WARPS_PER_SM
+#define DDD_CHAIN_WARPS_PER_SM 32
+#endif
+template <int THREADS, bool PRECISE>
+__global__ void __launch_bounds__(THREADS, (PRECISE ? 1 : DDD_CHAIN_WARPS_PER_SM * 32 / THREADS)) mc_chain_kernel(const ChainArgs a) {
+    const ChainSmem s(nullptr, a.nl_cap);
     const int tid = threadIdx.x;
     const long long local = a.order ? (long long)a.order[blockIdx.x] : (long long)blockIdx.x;
     const long long chain = a.chain_begin + local;
@@ -295,6 +450,7 @@ __global__ void __launch_bounds__(kThreads) mc_chain_kernel(const ChainArgs a) {
     const long long off = a.offsets[lig];
     const int nl = (int)(a.offsets[lig + 1] - off);
     const DevParams &P = a.prm;
+    const bool warp_has_atoms = (tid & ~31) < nl;
 
     Stream st;
     st.seed = a.seed; st.id = a.chain_id_base + (uint64_t)chain; st.rec = nullptr; st.rec_len = 0;
@@ -305,117 +461,139 @@ __global__ void __launch_bounds__(kThreads) mc_chain_kernel(const ChainArgs a) {
 
     // private copy of the start pose (each chain owns its atoms)
     const double *src = a.lig_xyzq + (off - a.atom_base) * 4;
-    for (int i = tid; i < nl; i += kThreads) {
-        const double x = src[4 * i], y = src[4 * i + 1], z = src[4 * i + 2], q = src[4 * i + 3];
-        s.cx[i] = x; s.cy[i] = y; s.cz[i] = z; s.q[i] = q;
-        s.lf[i] = make_float4((float)(x - a.rec.cx), (float)(y - a.rec.cy), (float)(z - a.rec.cz), (float)q);
+    for (int i = tid; i < nl; i += THREADS) {
+        s.q()[i] = src[4 * i + 3];
+        store_pose(a, s, i, src[4 * i], src[4 * i + 1], src[4 * i + 2]);
+    }
+    if (tid == 0) {
+        if (nl & 1) store_lig_f32(s.lf(), nl, -kPadCoord, -kPadCoord, -kPadCoord, 0.f);   // q = 0 pad atom
+        s.cnt()[0] = 0; s.cnt()[1] = 0; s.cnt()[2] = 0; s.cnt()[3] = 0;
+        s.ctl()[0] = 0; s.ctl()[1] = 0; s.ctl()[2] = 0;
     }
     __syncthreads();
 
     int parity = 0, status = 0;
-    const double start_energy = chain_energy<true>(a, s, nl, parity);            // :118 in fp64
-    double cur_e = PRECISE ? start_energy : chain_energy<false>(a, s, nl, parity);
+    const double start_energy = chain_energy<THREADS, true>(a, s, nl, parity);       // :118 in fp64
+    double cur_e = PRECISE ? start_energy : chain_energy<THREADS, false>(a, s, nl, parity);
 
     uint64_t pos = 0;
-    long long accepted = 0, downhill = 0, retries = 0, steps_done = 0;
     const int draws_per_attempt = (P.move_mode == 1) ? 7 : (P.rotate ? 4 : 0) + 3 * nl;
+    const CollisionPlan cplan = collision_plan<THREADS>(nl);
+    const float m2_f32 = (float)(P.min_distance * P.min_distance);
 
     for (long long step = 0; step < a.steps; ++step) {
-        for (int i = tid; i < nl; i += kThreads) { s.px[i] = s.cx[i]; s.py[i] = s.cy[i]; s.pz[i] = s.cz[i]; }   // :121
+        for (int i = tid; i < nl; i += THREADS) { s.px()[i] = s.cx()[i]; s.py()[i] = s.cy()[i]; s.pz()[i] = s.cz()[i]; }   // :121
         if (P.move_mode == 1) __syncthreads();     // RIGID reads every atom of prev for the centroid
 
         long long rej = 0;
         bool bail = false;
         for (;;) {
             if (P.move_mode == 1) {
-                // EXTENSION: rigid-body move, draws tx,ty,tz,ax,ay,az,theta (oracle: orc_rigid_move)
-                const double tx = (st.draw(pos, status) - 0.5) * P.rigid_translation;
-                const double ty = (st.draw(pos + 1, status) - 0.5) * P.rigid_translation;
-                const double tz = (st.draw(pos + 2, status) - 0.5) * P.rigid_translation;
-                double ax, ay, az, theta;
-                draw_axis_angle(st, pos + 3, P.rigid_angle, status, ax, ay, az, theta);
-                double gx = 0, gy = 0, gz = 0;
-                for (int i = 0; i < nl; ++i) { gx += s.px[i]; gy += s.py[i]; gz += s.pz[i]; }
-                if (nl > 0) { gx /= (double)nl; gy /= (double)nl; gz /= (double)nl; }
-                const double h = 0.5 * theta;
-                double sh, w; sincos(h, &sh, &w);
-                const double qx = sh * ax, qy = sh * ay, qz = sh * az;
-                for (int i = tid; i < nl; i += kThreads) {
-                    const double vx = s.px[i] - gx, vy = s.py[i] - gy, vz = s.pz[i] - gz;
-                    const double c1x = qy * vz - qz * vy, c1y = qz * vx - qx * vz, c1z = qx * vy - qy * vx;
-                    const double c2x = qy * c1z - qz * c1y, c2y = qz * c1x - qx * c1z, c2z = qx * c1y - qy * c1x;
-                    const double x = gx + (vx + 2.0 * (w * c1x + c2x)) + tx;
-                    const double y = gy + (vy + 2.0 * (w * c1y + c2y)) + ty;
-                    const double z = gz + (vz + 2.0 * (w * c1z + c2z)) + tz;
-                    s.cx[i] = x; s.cy[i] = y; s.cz[i] = z;
-                    s.lf[i] = make_float4((float)(x - a.rec.cx), (float)(y - a.rec.cy), (float)(z - a.rec.cz), (float)s.q[i]);
+                // EXTENSION: rigid-body move, draws tx,ty,tz,ax,ay,az,theta (no reference row)
+                if (warp_has_atoms) {
+                    const double tx = (st.draw(pos, status) - 0.5) * P.rigid_translation;
+                    const double ty = (st.draw(pos + 1, status) - 0.5) * P.rigid_translation;
+                    const double tz = (st.draw(pos + 2, status) - 0.5) * P.rigid_translation;
+                    double ax, ay, az, theta;
+                    draw_axis_angle(st, pos + 3, P.rigid_angle, status, ax, ay, az, theta);
+                    double gx = 0, gy = 0, gz = 0;
+                    for (int i = 0; i < nl; ++i) { gx += s.px()[i]; gy += s.py()[i]; gz += s.pz()[i]; }
+                    if (nl > 0) { gx /= (double)nl; gy /= (double)nl; gz /= (double)nl; }
+                    const double h = 0.5 * theta;
+                    double sh, w; sincos(h, &sh, &w);
+                    const double qx = sh * ax, qy = sh * ay, qz = sh * az;
+                    for (int i = tid; i < nl; i += THREADS) {
+                        const double vx = s.px()[i] - gx, vy = s.py()[i] - gy, vz = s.pz()[i] - gz;
+                        const double c1x = qy * vz - qz * vy, c1y = qz * vx - qx * vz, c1z = qx * vy - qy * vx;
+                        const double c2x = qy * c1z - qz * c1y, c2y = qz * c1x - qx * c1z, c2z = qx * c1y - qy * c1x;
+                        store_pose(a, s, i, gx + (vx + 2.0 * (w * c1x + c2x)) + tx,
+                                   gy + (vy + 2.0 * (w * c1y + c2y)) + ty, gz + (vz + 2.0 * (w * c1z + c2z)) + tz);
+                    }
                 }
                 pos += 7;
+                if (tid == 0) s.ctl()[0] = 0;
                 __syncthreads();
                 break;                          // rigid: intra-ligand distances unchanged, no collision test
             }
             // REFERENCE move: JitterAndRotateLigand (:172-184) / JitterLigand (:154-167), in place
-            double ax = 0, ay = 0, az = 0, cos_t = 1, sin_t = 0;
-            uint64_t jpos = pos;
-            if (P.rotate) {                                                   // RotateLigand :189-208
-                double theta;
-                draw_axis_angle(st, pos, P.max_angle, status, ax, ay, az, theta);
-                sincos(theta, &sin_t, &cos_t);                               // :214-215
-                jpos += 4;
-            }
-            for (int i = tid; i < nl; i += kThreads) {
-                double x = s.cx[i], y = s.cy[i], z = s.cz[i];
-                if (P.rotate) rotate_atom(x, y, z, ax, ay, az, cos_t, sin_t);
-                double u[3];
-                st.draw3(jpos + 3ull * (uint64_t)i, u, status);
-                x += (u[0] - 0.5) * P.jitter_width;                          // :176-178 / :158-160
-                y += (u[1] - 0.5) * P.jitter_width;
-                z += (u[2] - 0.5) * P.jitter_width;
-                s.cx[i] = x; s.cy[i] = y; s.cz[i] = z;
-                s.lf[i] = make_float4((float)(x - a.rec.cx), (float)(y - a.rec.cy), (float)(z - a.rec.cz), (float)s.q[i]);
+            if (warp_has_atoms) {               // warps that own no atom skip the draws and the sincos
+                double ax = 0, ay = 0, az = 0, cos_t = 1, sin_t = 0;
+                uint64_t jpos = pos;
+                if (P.rotate) {                                                   // RotateLigand :189-208
+                    double theta;
+                    draw_axis_angle(st, pos, P.max_angle, status, ax, ay, az, theta);
+                    sincos(theta, &sin_t, &cos_t);                               // :214-215
+                    jpos += 4;
+                }
+                for (int i = tid; i < nl; i += THREADS) {
+                    double x = s.cx()[i], y = s.cy()[i], z = s.cz()[i];
+                    if (P.rotate) rotate_atom(x, y, z, ax, ay, az, cos_t, sin_t);
+                    double u[3];
+                    st.draw3(jpos + 3ull * (uint64_t)i, u, status);
+                    x += (u[0] - 0.5) * P.jitter_width;                          // :176-178 / :158-160
+                    y += (u[1] - 0.5) * P.jitter_width;
+                    z += (u[2] - 0.5) * P.jitter_width;
+                    store_pose(a, s, i, x, y, z);
+                }
             }
             pos += (uint64_t)draws_per_attempt;
+            if (tid == 0) s.ctl()[0] = 0;
             __syncthreads();
-            const bool hit = collision_partial(s, nl, P.min_distance);       // :180 / :162
-            if (!__syncthreads_or(hit)) break;
+            // IsCollisionFree (:180 / :162).  Retries are frequent late in a chain (the per-atom jitter lets atoms
+            // pile up until only MINDISTANCE separates them), so the test must be cheap: an fp32 screen decides
+            // "certainly colliding" / "certainly free"; only a pair inside the 2 % band goes to the exact fp64 test.
+            const int code = collision_screen_f32(s, nl, cplan, m2_f32);
+            bool collided = __syncthreads_or(code & 2) != 0;
+            if (!collided && __syncthreads_or(code & 1)) {
+                const bool hit = collision_partial<THREADS>(s, nl, P.min_distance);
+                collided = __syncthreads_or(hit) != 0;
+            }
+            if (!collided) break;
             ++rej;                                  // retry on the already-moved atoms
             if (rej >= P.max_retries) { bail = true; break; }
         }
-        retries += rej;
+        if (tid == 0) s.cnt()[2] += rej;
         if (bail) {                                  // the reference would spin forever here
             status |= 1;
-            for (int i = tid; i < nl; i += kThreads) { s.cx[i] = s.px[i]; s.cy[i] = s.py[i]; s.cz[i] = s.pz[i]; }
+            for (int i = tid; i < nl; i += THREADS) { s.cx()[i] = s.px()[i]; s.cy()[i] = s.py()[i]; s.cz()[i] = s.pz()[i]; }
             break;
         }
 
-        const double new_e = chain_energy<PRECISE>(a, s, nl, parity);         // :127
+        const double new_e = chain_energy<THREADS, PRECISE>(a, s, nl, parity);    // :127
         bool acc;                                                             // AcceptMove :141-149
         const bool dh = new_e < cur_e;
         if (dh) acc = true;
         else {
             const double delta = new_e - cur_e;
-            const double probability = exp(-delta / P.temperature);
-            acc = st.draw(pos, status) < probability;
+            const double x = -delta / P.temperature;
+            // exp(x) is exactly +0 below -746, and no uniform is < 0: reject without evaluating either.  The draw
+            // is still consumed (:148).  (With K = 9e9 this is nearly every uphill move)
+            if (x < -746.0 && !st.rec) acc = false;
+            else acc = st.draw(pos, status) < exp(x);
             pos += 1;
         }
-        if (acc) { cur_e = new_e; ++accepted; downhill += dh ? 1 : 0; }      // :129-130
-        else for (int i = tid; i < nl; i += kThreads) { s.cx[i] = s.px[i]; s.cy[i] = s.py[i]; s.cz[i] = s.pz[i]; }  // :132
-        if (a.out_trace && tid == 0) a.out_trace[local * a.steps + step] = acc ? 1 : 0;
-        ++steps_done;
+        if (acc) cur_e = new_e;                                               // :129-130
+        else for (int i = tid; i < nl; i += THREADS) { s.cx()[i] = s.px()[i]; s.cy()[i] = s.py()[i]; s.cz()[i] = s.pz()[i]; }  // :132
+        if (tid == 0) {
+            s.cnt()[0] += acc ? 1 : 0; s.cnt()[1] += dh ? 1 : 0; s.cnt()[3] += 1;
+            if (a.out_trace) a.out_trace[local * a.steps + step] = acc ? 1 : 0;
+        }
     }
     __syncthreads();
 
     // CalculateEnergy of the returned pose in fp64 (:61 / :104)
-    const double final_energy = (PRECISE && !(status & 1)) ? cur_e : chain_energy<true>(a, s, nl, parity);
+    const double final_energy = PRECISE ? cur_e : chain_energy<THREADS, true>(a, s, nl, parity);
 
     const long long out_atom = (long long)a.replicas * off + (long long)rep * nl - a.out_base;
     double *dst = a.out_xyzq + out_atom * 4;
-    for (int i = tid; i < nl; i += kThreads) {
-        dst[4 * i] = s.cx[i]; dst[4 * i + 1] = s.cy[i]; dst[4 * i + 2] = s.cz[i]; dst[4 * i + 3] = s.q[i];
+    for (int i = tid; i < nl; i += THREADS) {
+        dst[4 * i] = s.cx()[i]; dst[4 * i + 1] = s.cy()[i]; dst[4 * i + 2] = s.cz()[i]; dst[4 * i + 3] = s.q()[i];
     }
+    // status bit 2 (stream exhausted) can be raised by any thread that drew: OR it over the CTA
+    status = __syncthreads_or(status & 2) ? (status | 2) : status;
     if (tid == 0) {
         ChainStats cs;
-        cs.steps = steps_done; cs.accepted = accepted; cs.downhill = downhill; cs.retries = retries;
+        cs.accepted = s.cnt()[0]; cs.downhill = s.cnt()[1]; cs.retries = s.cnt()[2]; cs.steps = s.cnt()[3];
         cs.draws = (long long)pos; cs.status = status;
         cs.final_energy = final_energy; cs.start_energy = start_energy; cs.chain_energy = cur_e;
         reinterpret_cast<ChainStats *>(a.out_stats)[local] = cs;
@@ -435,8 +613,7 @@ struct EnergyArgs {
 
 template <bool PRECISE, bool WITH_ABS>
 __global__ void __launch_bounds__(kThreads) energy_batch_kernel(const EnergyArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const ChainSmem s(smem_raw, a.nl_cap);
+    const ChainSmem s(nullptr, a.nl_cap);
     const int tid = threadIdx.x;
     const long long lig = blockIdx.x;
     const long long off = a.offsets[lig];
@@ -444,19 +621,22 @@ __global__ void __launch_bounds__(kThreads) energy_batch_kernel(const EnergyArgs
     const double *src = a.lig_xyzq + off * 4;
     for (int i = tid; i < nl; i += kThreads) {
         const double x = src[4 * i], y = src[4 * i + 1], z = src[4 * i + 2], q = src[4 * i + 3];
-        s.cx[i] = x; s.cy[i] = y; s.cz[i] = z; s.q[i] = q;
-        s.lf[i] = make_float4((float)(x - a.rec.cx), (float)(y - a.rec.cy), (float)(z - a.rec.cz), (float)q);
+        s.cx()[i] = x; s.cy()[i] = y; s.cz()[i] = z; s.q()[i] = q;
+        store_lig_f32(s.lf(), i, (float)(x - a.rec.cx), (float)(y - a.rec.cy), (float)(z - a.rec.cz), (float)q);
+    }
+    if (tid == 0) {
+        if (nl & 1) store_lig_f32(s.lf(), nl, -kPadCoord, -kPadCoord, -kPadCoord, 0.f);
+        s.ctl()[0] = 0;
     }
     __syncthreads();
     int parity = 0;
-    double part, ab = 0.0;
+    double part = 0.0, ab = 0.0, e;
     if (PRECISE || WITH_ABS) {
-        part = pair_sum_f64<WITH_ABS>(a.rec, s.cx, s.cy, s.cz, s.q, nl, a.prm.k_coulomb, a.prm.clamp_distance, &ab);
+        part = pair_sum_f64<kThreads, WITH_ABS>(a.rec, s.cx(), s.cy(), s.cz(), s.q(), nl, a.prm.k_coulomb, a.prm.clamp_distance, &ab);
     }
-    if (!PRECISE) part = pair_sum_f32(a.rec, s.lf, nl, a.prm.rinv_max);
-    double e = block_sum(part, s.red, parity);
-    if (!PRECISE) e *= a.prm.k_coulomb;
-    if (WITH_ABS) ab = block_sum(ab, s.red, parity);
+    if (PRECISE) e = block_sum<kThreads>(part, s.red(), parity);
+    else e = a.prm.k_coulomb * cta_pair_sum_f32<kThreads>(a.rec, s.lf(), nl, a.prm.rinv_max, s.ctl(), s.item_out());
+    if (WITH_ABS) ab = block_sum<kThreads>(ab, s.red(), parity);
     if (tid == 0) {
         a.out_energy[lig] = e;
         if (WITH_ABS) a.out_abs[lig] = ab;

@@ -137,6 +137,7 @@ struct ScreenDev {
     long long *d_rec_off = nullptr;
     long long rec_base = 0;
     float last_ms = 0.f;
+    int threads = 0;                       // CTA width used by the last launch
 };
 
 struct ddd_screen {
@@ -147,9 +148,18 @@ struct ddd_screen {
     std::vector<int64_t> offsets;
     std::vector<ScreenDev> devs;
     bool launched = false;
+    int threads_override = 0;              // 0: pick from the chain count
 };
 
 namespace {
+
+// CTA width of the chain kernel.  Every warp of a chain's CTA repeats the per-step proposal /
+// collision / accept work, so the narrowest CTA that still gives each SM ~24+ warps wins.
+int pick_chain_threads(int64_t n_chains, int sm_count) {
+    const int64_t want_warps = (int64_t)sm_count * 24;
+    for (int t : {32, 64, 128}) if (n_chains * (t / 32) >= want_warps) return t;
+    return 256;
+}
 
 // chains [begin[k], begin[k+1]) go to shard k; contiguous, balanced by sum(nL + 1)
 void plan_shards(const int64_t *offsets, int64_t n_lig, int replicas, int n_shards, std::vector<int64_t> &begin) {
@@ -298,14 +308,20 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
         a.out_xyzq = d.d_out; a.out_base = d.out_base; a.out_stats = d.d_stats; a.out_trace = d.d_trace;
         a.nl_cap = d.nl_cap;
         const size_t smem = chain_smem_bytes(d.nl_cap);
+        const int threads = s->threads_override > 0 ? s->threads_override : pick_chain_threads(n_local, dev.sm_count);
+        d.threads = threads;
         CUDA_TRY(cudaEventRecord(dev.ev0, dev.stream));
+#define LAUNCH_CHAIN(T, PR)                                                                   \
+        do { if (int rc = set_smem(mc_chain_kernel<T, PR>, smem)) return rc;                   \
+             mc_chain_kernel<T, PR><<<(unsigned)n_local, T, smem, dev.stream>>>(a); } while (0)
         if (p->precision == DDD_PRECISION_F64) {
-            if (int rc = set_smem(mc_chain_kernel<true>, smem)) return rc;
-            mc_chain_kernel<true><<<(unsigned)n_local, kThreads, smem, dev.stream>>>(a);
+            switch (threads) { case 32: LAUNCH_CHAIN(32, true); break; case 64: LAUNCH_CHAIN(64, true); break;
+                               case 256: LAUNCH_CHAIN(256, true); break; default: LAUNCH_CHAIN(128, true); }
         } else {
-            if (int rc = set_smem(mc_chain_kernel<false>, smem)) return rc;
-            mc_chain_kernel<false><<<(unsigned)n_local, kThreads, smem, dev.stream>>>(a);
+            switch (threads) { case 32: LAUNCH_CHAIN(32, false); break; case 64: LAUNCH_CHAIN(64, false); break;
+                               case 256: LAUNCH_CHAIN(256, false); break; default: LAUNCH_CHAIN(128, false); }
         }
+#undef LAUNCH_CHAIN
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(dev.ev1, dev.stream));
     }
@@ -455,7 +471,7 @@ int ddd_receptor_create(const double *xyzq, int64_t n_atoms, ddd_receptor **out)
     if (n_atoms > 0x7fffff00ll) return fail(DDD_ELIMIT, "receptor too large");
     ddd_receptor *r = new ddd_receptor();
     r->n = n_atoms;
-    r->n_pad = (n_atoms + kThreads - 1) / kThreads * kThreads;
+    r->n_pad = (n_atoms + kRecPad - 1) / kRecPad * kRecPad;
     double sx = 0, sy = 0, sz = 0;
     for (int64_t i = 0; i < n_atoms; ++i) { sx += xyzq[4 * i]; sy += xyzq[4 * i + 1]; sz += xyzq[4 * i + 2]; }
     if (n_atoms > 0) { r->cx = sx / (double)n_atoms; r->cy = sy / (double)n_atoms; r->cz = sz / (double)n_atoms; }
@@ -728,6 +744,20 @@ int ddd_screen_run(ddd_screen *s, int64_t steps_per_chain, int32_t rotate, doubl
     return screen_run_impl(s, steps_per_chain, rotate, temperature, p, seed, nullptr, nullptr, false);
 }
 
+int ddd_screen_set_chain_threads(ddd_screen *s, int32_t threads) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!s) return fail(DDD_EINVAL, "screen is NULL");
+    if (threads != 0 && threads != 32 && threads != 64 && threads != 128 && threads != 256)
+        return fail(DDD_EINVAL, "chain CTA width must be 0, 32, 64, 128 or 256 (got %d)", threads);
+    s->threads_override = threads;
+    return DDD_OK;
+}
+
+int32_t ddd_screen_chain_threads(const ddd_screen *s) {
+    if (!s || s->devs.empty()) return 0;
+    return s->devs[0].threads;
+}
+
 int ddd_screen_sync(ddd_screen *s) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     REQUIRE_INIT();
@@ -779,13 +809,13 @@ int ddd_chain_kernel_info(int32_t precision, int32_t *threads, int32_t *regs, in
     int blocks = 0;
     const size_t smem = chain_smem_bytes(40);
     if (precision == DDD_PRECISION_F64) {
-        CUDA_TRY(cudaFuncGetAttributes(&fa, mc_chain_kernel<true>));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, mc_chain_kernel<true>, kThreads, smem));
+        CUDA_TRY(cudaFuncGetAttributes(&fa, mc_chain_kernel<128, true>));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, mc_chain_kernel<128, true>, 128, smem));
     } else {
-        CUDA_TRY(cudaFuncGetAttributes(&fa, mc_chain_kernel<false>));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, mc_chain_kernel<false>, kThreads, smem));
+        CUDA_TRY(cudaFuncGetAttributes(&fa, mc_chain_kernel<128, false>));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, mc_chain_kernel<128, false>, 128, smem));
     }
-    if (threads) *threads = kThreads;
+    if (threads) *threads = 128;
     if (regs) *regs = fa.numRegs;
     if (static_smem) *static_smem = (int32_t)fa.sharedSizeBytes;
     if (max_blocks_per_sm_at_nl40) *max_blocks_per_sm_at_nl40 = blocks;

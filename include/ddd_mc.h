@@ -161,6 +161,9 @@ int ddd_randomize_pose_batch(const int64_t *offsets, double *lig_xyzq_inout, int
  * of the chain kernel on its launch stream; download copies final poses + stats to the host. */
 int    ddd_screen_create(const ddd_receptor *r, const int64_t *offsets, const double *lig_xyzq,
                          int64_t n_lig, int32_t replicas, uint64_t first_chain_id, ddd_screen **out);
+/* threads per chain CTA for subsequent runs: 32, 64, 128 or 256; 0 (default) = chosen from the chain count */
+int    ddd_screen_set_chain_threads(ddd_screen *s, int32_t threads);
+int32_t ddd_screen_chain_threads(const ddd_screen *s);   /* width used by the last run */
 int    ddd_screen_run(ddd_screen *s, int64_t steps_per_chain, int32_t rotate, double temperature,
                       const ddd_params *p, uint64_t seed);
 int    ddd_screen_sync(ddd_screen *s);

@@ -6,9 +6,11 @@
  * float64 throughout; compile with -ffp-contract=off.
  *
  * -DORC_SQUARE_VIA_POW routes the three squares of CalculateEnergy through an
- * out-of-line pow() (build with -fno-builtin-pow) to mimic the cost of Go's
- * out-of-line math.Pow (metropolis.go:253); results are bit-identical (pow(x,2)
- * is correctly rounded x*x in glibc), only the timing differs.
+ * out-of-line pow() (build with -fno-builtin-pow) to mimic the COST of Go's
+ * out-of-line math.Pow (metropolis.go:253).  That build is for timing only:
+ * glibc's pow is not always correctly rounded, so it may differ from x*x in
+ * the last bit, whereas Go's math.Pow(x, 2) is exactly x*x (frexp, one
+ * rounded multiply of the mantissas, ldexp) -- the default build is the oracle.
  */
 #include "ddd_oracle.h"
 

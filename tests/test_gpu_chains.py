@@ -1,0 +1,232 @@
+"""-m gpu: the Metropolis chain (SimulateEnergyMinimizationOneProc, metropolis.go:116-136) on device.
+
+* F64 kernel driven by the same uniform stream as the oracle (Philox or a recorded array): identical accept /
+  reject sequence, draws, retries, and final pose to 1e-9 A (sin/cos differ from libm by <= 1 ulp).
+* F32 production kernel: same per-chain statistics as the oracle (acceptance counts, final-energy distribution).
+* Replica pick (SimulateEnergyMinimizationParallel, :94-111) and the ligand batch (:27-67) vs oracle and goldens.
+"""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, mock_ligand, mock_protein
+
+pytestmark = pytest.mark.gpu
+T = 310.15
+
+
+def _p64(gpu, **kw):
+    return gpu.default_params(precision=gpu.PRECISION_F64, **kw)
+
+
+@pytest.mark.parametrize("rotate", [False, True])
+@pytest.mark.parametrize("width", [32, 64, 128, 256])
+def test_replay_matches_oracle_every_cta_width(gpu, orc, synth_small, rotate, width):
+    prot, off, lig = synth_small
+    with gpu.Receptor(prot) as rec:
+        scr = gpu.Screen(rec, off, lig, 2)
+        scr.set_chain_threads(width)
+        scr.run(120, rotate, T, _p64(gpu), seed=9)
+        poses, stats = scr.download()
+        assert scr.chain_threads() == width
+        scr.close()
+    for c in range(2 * (len(off) - 1)):
+        li, r = divmod(c, 2)
+        pose_o, st_o = orc.chain(prot, lig[off[li]:off[li + 1]], 120, rotate, T, orc.philox_stream(9, c))
+        for k in ("steps", "accepted", "downhill", "retries", "draws", "status"):
+            assert stats[c][k] == st_o[k], (c, k)
+        assert np.allclose(gpu.chain_pose(off, 2, poses, li, r), pose_o, rtol=0, atol=1e-9)
+        assert stats[c]["final_energy"] == pytest.approx(st_o["final_energy"], rel=1e-11)
+        assert stats[c]["start_energy"] == pytest.approx(st_o["start_energy"], rel=1e-12)
+
+
+def test_replay_golden_chains_on_shipped_data(gpu, sample):
+    g = json.loads((GOLDEN / "oracle_golden.json").read_text())["chains"]
+    with gpu.Receptor(sample["223l_protein"]) as rec:
+        for c in g:
+            lig = sample[c["ligand"] + "_ligand"]
+            off = np.array([0, len(lig)])
+            poses, stats, trace = gpu.run_chains(rec, off, lig, 1, c["steps"], c["rotate"], T, _p64(gpu), seed=c["seed"],
+                                                 first_chain_id=c["chain_id"], want_trace=True)
+            assert "".join(map(str, trace[0].tolist())) == c["accept_trace"]
+            assert stats[0]["accepted"] == c["accepted"] and stats[0]["draws"] == c["draws"] and stats[0]["retries"] == c["retries"]
+            assert stats[0]["final_energy"] == pytest.approx(c["final_energy"], rel=1e-11)
+            assert np.allclose(poses[:, :3], np.array(c["pose"]), rtol=0, atol=1e-9)
+
+
+def test_recorded_stream_replay(gpu, orc, synth_small):
+    # the Go harness records rand.Float64() draws; the device must consume them in metropolis.go order
+    prot, off, lig = synth_small
+    sel = [0, 2, 4]
+    ligs = [lig[off[i]:off[i + 1]] for i in sel]
+    o2, l2 = gpu.pack_ligands(ligs)
+    rng = np.random.default_rng(42)
+    streams = [rng.random(60 * (4 + 3 * len(l) + 1) * 2) for l in ligs]
+    roff = np.concatenate([[0], np.cumsum([len(s) for s in streams])]).astype(np.int64)
+    with gpu.Receptor(prot) as rec:
+        poses, stats, trace = gpu.run_chains(rec, o2, l2, 1, 60, True, T, _p64(gpu), seed=0, recorded=np.concatenate(streams),
+                                             recorded_offsets=roff, want_trace=True)
+        for c, l in enumerate(ligs):
+            pose_o, st_o, tr_o, _ = orc.chain(prot, l, 60, True, T, orc.recorded_stream(streams[c]), want_trace=True)
+            assert np.array_equal(trace[c], tr_o) and stats[c]["draws"] == st_o["draws"] and stats[c]["status"] == 0
+            assert np.allclose(gpu.chain_pose(o2, 1, poses, c, 0), pose_o, rtol=0, atol=1e-9)
+        # a stream that is too short is flagged, not silently replaced
+        short = [s[:50] for s in streams]
+        roff2 = np.concatenate([[0], np.cumsum([len(s) for s in short])]).astype(np.int64)
+        _, stats, _ = gpu.run_chains(rec, o2, l2, 1, 60, True, T, _p64(gpu), seed=0, recorded=np.concatenate(short), recorded_offsets=roff2)
+        assert np.all(stats["status"] & gpu.STATUS_STREAM_EXHAUSTED)
+
+
+def test_collision_retry_is_cumulative_and_bounded(gpu, orc):
+    prot = np.array([[5.0, 5, 5, 1.0], [-3.0, 2, 1, -0.5]])
+    lig = np.array([[0.0, 0, 0, 0.1], [0.52, 0, 0, -0.1], [0.0, 0.53, 0, 0.2]])      # pairs hover around MINDISTANCE
+    off = np.array([0, 3])
+    with gpu.Receptor(prot) as rec:
+        poses, stats, trace = gpu.run_chains(rec, off, lig, 8, 200, False, T, _p64(gpu), seed=4, want_trace=True)
+        tot = 0
+        for c in range(8):
+            pose_o, st_o, tr_o, _ = orc.chain(prot, lig, 200, False, T, orc.philox_stream(4, c), want_trace=True)
+            assert np.array_equal(trace[c], tr_o) and stats[c]["retries"] == st_o["retries"] and stats[c]["draws"] == st_o["draws"]
+            assert np.allclose(gpu.chain_pose(off, 8, poses, 0, c), pose_o, atol=1e-10)
+            tot += st_o["retries"]
+        assert tot > 0
+        # impossible ligand: the reference would spin forever (metropolis.go:155); we stop, flag and restore the pose
+        bad = np.array([[0.0, 0, 0, 0.1], [0.01, 0, 0, -0.1]])
+        poses, stats, _ = gpu.run_chains(rec, np.array([0, 2]), bad, 1, 10, False, T, _p64(gpu, max_retries=5), seed=1)
+        assert stats[0]["status"] & gpu.STATUS_RETRY_LIMIT and stats[0]["steps"] == 0 and stats[0]["retries"] == 5
+        assert np.array_equal(poses, bad)
+
+
+def test_zero_steps_and_tiny_ligands(gpu, orc, synth_small):
+    prot, off, lig = synth_small
+    with gpu.Receptor(prot) as rec:
+        poses, stats, _ = gpu.run_chains(rec, off, lig, 3, 0, True, T, gpu.default_params(), seed=1)
+        for c in range(3 * (len(off) - 1)):
+            li, r = divmod(c, 3)
+            assert np.array_equal(gpu.chain_pose(off, 3, poses, li, r), lig[off[li]:off[li + 1]])
+            assert stats[c]["steps"] == 0 and stats[c]["final_energy"] == stats[c]["start_energy"]
+        # an empty ligand in the batch: nothing to move, zero energy
+        o2 = np.array([0, 0, 2]); l2 = mock_ligand()
+        poses, stats, _ = gpu.run_chains(rec, o2, l2, 1, 20, True, T, _p64(gpu), seed=1)
+        assert stats[0]["steps"] == 20 and stats[0]["final_energy"] == 0.0 and poses.shape == (2, 4)
+        assert gpu.run_chains(rec, np.array([0]), np.zeros((0, 4)), 2, 10, True, T)[0].shape == (0, 4)
+
+
+def test_f32_chains_match_oracle_statistics(gpu, orc, ddd):
+    # production precision: trajectories may differ after an fp32 near-tie, statistics must not
+    prot = ddd.synth.make_receptor(1500, seed=2)
+    off, lig = ddd.synth.make_ligands([24] * 48, prot)
+    for rotate in (False, True):
+        with gpu.Receptor(prot) as rec:
+            poses, stats, _ = gpu.run_chains(rec, off, lig, 1, 250, rotate, T, gpu.default_params(), seed=17)
+        acc_o, fin_o = [], []
+        for c in range(48):
+            _, st_o = orc.chain(prot, lig[off[c]:off[c + 1]], 250, rotate, T, orc.philox_stream(17, c))
+            acc_o.append(st_o["accepted"]); fin_o.append(st_o["final_energy"])
+        acc_o, fin_o = np.array(acc_o), np.array(fin_o)
+        assert abs(stats["accepted"].mean() - acc_o.mean()) <= 0.02 * max(1.0, acc_o.mean())
+        same = stats["accepted"] == acc_o
+        assert same.mean() >= 0.9                                    # most chains never hit an fp32 near-tie
+        assert np.allclose(stats["final_energy"][same], fin_o[same], rtol=1e-9)
+        # the chain's own fp32-summed energy agrees with the fp64 energy of the same pose (conditioning-aware)
+        e, ab = gpu.energy_batch(gpu.Receptor(prot), off, poses, gpu.default_params(precision=gpu.PRECISION_F64), with_abs=True)
+        assert np.allclose(e, stats["final_energy"], rtol=1e-12)
+        assert np.all(np.abs(stats["chain_energy"] - stats["final_energy"]) <= 1e-6 * ab)
+        assert np.all(stats["status"] == 0)
+
+
+def test_chain_energy_never_increases_at_this_temperature(gpu, ddd):
+    # with K = 9e9 the sampler is greedy descent; accepted == downhill and E_final <= E_start
+    prot = ddd.synth.make_receptor(1500, seed=2)
+    off, lig = ddd.synth.make_ligands([24] * 64, prot)
+    with gpu.Receptor(prot) as rec:
+        _, stats, _ = gpu.run_chains(rec, off, lig, 2, 300, True, T, gpu.default_params(), seed=3)
+    assert np.all(stats["final_energy"] <= stats["start_energy"])
+    assert np.all(stats["accepted"] == stats["downhill"])
+    assert np.all(stats["draws"] == 300 * (4 + 3 * 24) + (300 - stats["downhill"]) + stats["retries"] * (4 + 3 * 24))
+
+
+def test_minimize_batch_matches_oracle(gpu, orc, synth_small):
+    prot, off, lig = synth_small
+    g = json.loads((GOLDEN / "oracle_golden.json").read_text())["synth600"]
+    with gpu.Receptor(prot) as rec:
+        for rotate, key in ((True, "minimize_rotate"), (False, "minimize_jitter")):
+            out, en, picked, st = gpu.minimize_batch(rec, off, lig, 1000, rotate, T, 4, _p64(gpu), seed=21, want_stats=True)
+            assert np.allclose(en, np.array(g[key]["energy"]), rtol=1e-10)
+            assert st["accepted"].tolist() == g[key]["accepted"]
+            assert np.all(st["steps"] == 250)                              # iterations / numProcs (:97)
+            rc, xo, eno, sto = orc.simulate_multiple_ligands(prot, off, lig, 1000, rotate, T, 4, 21)
+            assert np.allclose(out, xo, rtol=0, atol=1e-9)
+            e64 = gpu.energy_batch(rec, off, out, _p64(gpu))
+            assert np.allclose(en, e64, rtol=1e-12)                        # energy[i] = CalculateEnergy(final pose) (:61)
+        # splitting the ligand list over two calls (or ranks) reproduces the single call
+        a = gpu.minimize_batch(rec, off[:4], lig[:off[3]], 600, True, T, 3, _p64(gpu), seed=8)
+        o_b = off[3:] - off[3]
+        b = gpu.minimize_batch(rec, o_b, lig[off[3]:], 600, True, T, 3, _p64(gpu), seed=8, first_ligand_index=3)
+        full = gpu.minimize_batch(rec, off, lig, 600, True, T, 3, _p64(gpu), seed=8)
+        assert np.array_equal(np.concatenate([a[0], b[0]]), full[0]) and np.array_equal(np.concatenate([a[1], b[1]]), full[1])
+        # numProcs > iterations: width 0, every chain returns the start pose (:97 truncating division)
+        out, en, picked = gpu.minimize_batch(rec, off, lig, 3, True, T, 8, _p64(gpu), seed=1)
+        assert np.array_equal(out, lig)
+        with pytest.raises(gpu.DddError):
+            gpu.minimize_batch(rec, off, lig, 100, True, T, 0)             # Go: integer divide by zero
+
+
+def test_config1_shipped_data_golden(gpu, sample):
+    # RunMultipleLigands (main.go:125-158): 223l protein x first 5 ligands, 3000 it, rotate, numProcs = 8
+    g = json.loads((GOLDEN / "oracle_golden.json").read_text())["config1"]
+    first5 = ["1a0i", "223l", "227l", "421p", "6tol"]
+    off, lig = gpu.pack_ligands([sample[n + "_ligand"] for n in first5])
+    with gpu.Receptor(sample["223l_protein"]) as rec:
+        for seed in ("1", "2"):
+            out, en, picked, st = gpu.minimize_batch(rec, off, lig, 3000, True, T, 8, _p64(gpu), seed=int(seed), want_stats=True)
+            assert st["accepted"].tolist() == g[seed]["accepted"] and st["retries"].tolist() == g[seed]["retries"]
+            assert st["draws"].tolist() == g[seed]["draws"]
+            assert np.allclose(en, g[seed]["energy"], rtol=1e-10)
+            cs = [float(out[off[i]:off[i + 1], :3].sum()) for i in range(5)]
+            assert np.allclose(cs, g[seed]["pose_checksum"], rtol=0, atol=1e-7)
+            # production precision on the same run: same statistics
+            out32, en32, _, st32 = gpu.minimize_batch(rec, off, lig, 3000, True, T, 8, gpu.default_params(), seed=int(seed), want_stats=True)
+            assert abs(st32["accepted"].sum() - st["accepted"].sum()) <= 0.05 * st["accepted"].sum() + 2
+
+
+def test_rigid_extension_matches_its_oracle(gpu, orc, synth_small):
+    # north_star's rigid-body move has no reference row; parity is against the builder's own restatement only
+    prot, off, lig = synth_small
+    with gpu.Receptor(prot) as rec:
+        poses, stats, trace = gpu.run_chains(rec, off, lig, 1, 150, True, T, _p64(gpu, move_mode=gpu.MOVE_RIGID), seed=6, want_trace=True)
+    po = orc.params(move_mode=1)
+    for c in range(len(off) - 1):
+        l = lig[off[c]:off[c + 1]]
+        pose_o, st_o, tr_o, _ = orc.chain(prot, l, 150, True, T, orc.philox_stream(6, c), po, want_trace=True)
+        assert np.array_equal(trace[c], tr_o) and stats[c]["draws"] == st_o["draws"]
+        g = gpu.chain_pose(off, 1, poses, c, 0)
+        assert np.allclose(g, pose_o, atol=1e-9)
+        if len(l) > 1:                                                      # rigid: intra-ligand distances preserved
+            d0 = np.linalg.norm(l[:, None, :3] - l[None, :, :3], axis=-1)
+            d1 = np.linalg.norm(g[:, None, :3] - g[None, :, :3], axis=-1)
+            assert np.allclose(d0, d1, atol=1e-9)
+
+
+def test_full_size_config2_properties(gpu, ddd):
+    # BASELINE config 2 shape (5k receptor x 1024 x 40), shortened chains: size-independent invariants
+    prot = ddd.synth.make_receptor(5000)
+    off, lig = ddd.synth.make_ligands([40] * 1024, prot)
+    with gpu.Receptor(prot) as rec:
+        scr = gpu.Screen(rec, off, lig, 1)
+        scr.run(200, True, T, gpu.default_params(), seed=1)
+        poses, stats = scr.download()
+        ms = scr.last_kernel_ms()
+        scr.run(200, True, T, gpu.default_params(), seed=1)                 # idempotent: same seed -> same bits
+        poses2, stats2 = scr.download()
+        scr.close()
+        e64, ab = gpu.energy_batch(rec, off, poses, gpu.default_params(precision=gpu.PRECISION_F64), with_abs=True)
+    assert ms > 0 and np.array_equal(poses, poses2) and np.array_equal(stats, stats2)
+    assert np.all(stats["steps"] == 200) and np.all(stats["status"] == 0)
+    assert np.all(stats["final_energy"] <= stats["start_energy"])
+    assert np.allclose(e64, stats["final_energy"], rtol=1e-12)
+    assert np.all(np.abs(stats["chain_energy"] - e64) <= 1e-6 * ab)
+    assert np.array_equal(poses[:, 3], lig[:, 3])                           # charges untouched
+    moved = np.abs(poses[:, :3] - lig[:, :3]).reshape(1024, -1).max(1) > 0
+    assert np.array_equal(moved, stats["accepted"] > 0)

@@ -30,10 +30,10 @@ def main():
     eo, ao = orc.energy_batch(prot, off, lig, with_abs=True)
     e64, a64 = capi.energy_batch(rec, off, lig, capi.default_params(precision=capi.PRECISION_F64), with_abs=True)
     e32 = capi.energy_batch(rec, off, lig, capi.default_params(precision=capi.PRECISION_F32))
-    print("energy f64: max |d|/abs_sum", np.max(np.abs(e64 - eo) / ao), " max rel", np.max(np.abs(e64 - eo) / np.abs(eo)),
-          " abs_sum rel", np.max(np.abs(a64 - ao) / ao))
-    print("energy f32: max |d|/abs_sum", np.max(np.abs(e32 - eo) / ao), " max rel", np.max(np.abs(e32 - eo) / np.abs(eo)),
-          " cond max", np.max(ao / np.abs(eo)))
+    print("energy f64: max |d|/abs_sum", np.nanmax(np.abs(e64 - eo) / ao), " max rel", np.nanmax(np.abs(e64 - eo) / np.abs(eo)),
+          " abs_sum rel", np.nanmax(np.abs(a64 - ao) / ao))
+    print("energy f32: max |d|/abs_sum", np.nanmax(np.abs(e32 - eo) / ao), " max rel", np.nanmax(np.abs(e32 - eo) / np.abs(eo)),
+          " cond max", np.nanmax(ao / np.abs(eo)))
 
     # ---- replay parity, F64
     for rotate in (False, True):
@@ -51,7 +51,7 @@ def main():
                 nbad += 1
                 print("  chain", c, "trace differs at", int(np.argmax(tr_o != trace[c])))
             else:
-                maxpose = max(maxpose, float(np.max(np.abs(g - pose_o))) if len(g) else 0.0)
+                maxpose = max(maxpose, float(np.nanmax(np.abs(g - pose_o))) if len(g) else 0.0)
                 maxe = max(maxe, abs(stats[c]["final_energy"] - st_o["final_energy"]) / max(1.0, abs(st_o["final_energy"])))
             assert stats[c]["steps"] == st_o["steps"], (stats[c], st_o)
             if same:
@@ -68,7 +68,7 @@ def main():
             _, st_o = orc.chain(prot, lig[off[li]:off[li + 1]], steps, rotate, 310.15, orc.philox_stream(7, c))
             acc_o.append(st_o["accepted"])
         print(f"F32 rotate={rotate}: mean acc gpu {stats['accepted'].mean():.2f} oracle {np.mean(acc_o):.2f}; status {set(stats['status'].tolist())}; "
-              f"|chain_energy-final_energy|/|E| max {np.max(np.abs(stats['chain_energy'] - stats['final_energy']) / np.abs(stats['final_energy'])):.2e}")
+              f"|chain_energy-final_energy|/|E| max {np.nanmax(np.abs(stats['chain_energy'] - stats['final_energy']) / np.abs(stats['final_energy'])):.2e}")
 
     # ---- rigid extension
     prm = capi.default_params(precision=capi.PRECISION_F64, move_mode=capi.MOVE_RIGID)
@@ -83,7 +83,7 @@ def main():
     # ---- minimize
     out, en, picked, st = capi.minimize_batch(rec, off, lig, 800, True, 310.15, 4, capi.default_params(precision=capi.PRECISION_F64), seed=11, want_stats=True)
     rc, xo, eno, sto = orc.simulate_multiple_ligands(prot, off, lig, 800, True, 310.15, 4, 11)
-    print("minimize F64: max rel energy diff", np.max(np.abs(en - eno) / np.abs(eno)), "max pose diff", np.max(np.abs(out - xo)), "picked", picked[:8])
+    print("minimize F64: max rel energy diff", np.nanmax(np.abs(en - eno) / np.abs(eno)), "max pose diff", np.nanmax(np.abs(out - xo)), "picked", picked[:8])
 
     # ---- helpers
     d, li, pj = capi.closest_atom_batch(rec, off, lig)
@@ -92,39 +92,40 @@ def main():
     far = lig.copy(); far[:, :3] += 40.0
     sh = capi.shift_closer_batch(rec, off, far, 5.0)
     sho = np.concatenate([orc.shift_closer(far[off[i]:off[i + 1]], prot, 5.0) for i in range(len(off) - 1)])
-    print("shift max diff", np.max(np.abs(sh - sho)))
+    print("shift max diff", np.nanmax(np.abs(sh - sho)))
     rz = capi.randomize_pose_batch(off, lig, seed=5)
     rzo = np.concatenate([orc.randomize_pose(lig[off[i]:off[i + 1]], orc.philox_stream(5, capi.STREAM_RANDOMIZE_BASE + i)) for i in range(len(off) - 1)])
-    print("randomize max diff", np.max(np.abs(rz - rzo)))
+    print("randomize max diff", np.nanmax(np.abs(rz - rzo)))
     r4 = capi.rmsd_batch(off, rz, lig, 4)
     r3 = capi.rmsd_batch(off, np.ascontiguousarray(rz[:, :3]), np.ascontiguousarray(lig[:, :3]), 3)
     ro = np.array([orc.rmsd(rz[off[i]:off[i + 1]], lig[off[i]:off[i + 1]]) for i in range(len(off) - 1)])
-    print("rmsd max rel diff", np.max(np.abs(r4 - ro) / ro), np.max(np.abs(r3 - ro) / ro))
+    print("rmsd max rel diff", np.nanmax(np.abs(r4 - ro) / ro), np.nanmax(np.abs(r3 - ro) / ro))
 
     # ---- timing, config-2 shape
     off2, lig2 = synth.make_ligands([40] * 1024, prot)
-    for prec, steps_list in ((capi.PRECISION_F32, (100, 1000)), (capi.PRECISION_F64, (20,))):
-        scr = capi.Screen(rec, off2, lig2, 1)
-        for steps in steps_list:
+    scr = capi.Screen(rec, off2, lig2, 1)
+    for prec, steps, widths in ((capi.PRECISION_F32, 1000, (0, 64, 128, 256)), (capi.PRECISION_F64, 20, (0,))):
+        for w in widths:
+            scr.set_chain_threads(w)
             prm = capi.default_params(precision=prec)
+            scr.run(steps // 4, True, 310.15, prm, seed=1); scr.sync()
             scr.run(steps, True, 310.15, prm, seed=1); scr.sync()
-            t0 = time.time()
-            scr.run(steps, True, 310.15, prm, seed=1); scr.sync()
-            wall = time.time() - t0
             ms = scr.last_kernel_ms()
             _, st = scr.download()
             total_steps = int(st["steps"].sum())
             pairs = total_steps * 5000 * 40
-            print(f"timing prec={prec} steps={steps}: kernel {ms:.2f} ms (wall {wall * 1e3:.1f}) -> {total_steps / ms * 1e3:.3e} steps/s, "
+            print(f"timing 1024 chains prec={prec} steps={steps} width={scr.chain_threads()}: kernel {ms:.2f} ms -> {total_steps / ms * 1e3:.3e} steps/s, "
                   f"{pairs / ms * 1e3:.3e} pairs/s, {12 * pairs / ms * 1e3 / 74.4e12 * 100:.1f}% of 74.4 TF; acc {st['accepted'].mean() / steps:.3f} retries {st['retries'].sum()}")
-        scr.close()
+    scr.close()
     # 32768 chains (config 3 on 1 GPU), short
     off3, lig3 = synth.make_ligands([40] * 4096, prot)
     scr = capi.Screen(rec, off3, lig3, 8)
-    scr.run(50, True, 310.15, capi.default_params(), seed=1); scr.sync()
-    scr.run(100, True, 310.15, capi.default_params(), seed=1); scr.sync()
-    ms = scr.last_kernel_ms()
-    print(f"timing 4096x8 chains x100 steps: kernel {ms:.2f} ms -> {32768 * 100 / ms * 1e3:.3e} steps/s, {32768 * 100 * 2e5 / ms * 1e3:.3e} pairs/s, {12 * 32768 * 100 * 2e5 / ms * 1e3 / 74.4e12 * 100:.1f}% of 74.4 TF")
+    for w in (0, 64, 128):
+        scr.set_chain_threads(w)
+        scr.run(50, True, 310.15, capi.default_params(), seed=1); scr.sync()
+        scr.run(200, True, 310.15, capi.default_params(), seed=1); scr.sync()
+        ms = scr.last_kernel_ms()
+        print(f"timing 4096x8 chains x200 steps width={scr.chain_threads()}: kernel {ms:.2f} ms -> {32768 * 200 / ms * 1e3:.3e} steps/s, {32768 * 200 * 2e5 / ms * 1e3:.3e} pairs/s, {12 * 32768 * 200 * 2e5 / ms * 1e3 / 74.4e12 * 100:.1f}% of 74.4 TF")
     scr.close()
 
 

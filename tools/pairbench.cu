@@ -11,6 +11,7 @@
 #include <vector>
 #include <cstdint>
 #include <cmath>
+#include <cstring>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
@@ -148,8 +149,8 @@ __global__ void __launch_bounds__(THREADS) k_expanded(const float4 *__restrict__
 // ---------------------------------------------------------------- V3: packed, ligand-pair packing: lane holds A atoms, each f32x2 op
 // covers TWO LIGAND atoms (l, l+1) against one receptor atom.  Receptor operand (px,px) is built once per tile.
 // ligand smem: per ligand pair two float4: (-x0,-x1,-y0,-y1), (-z0,-z1,q0,q1)
-template <int THREADS, int A, int UNROLL>
-__global__ void __launch_bounds__(THREADS) k_packed_lig(const float4 *__restrict__ rec, int n_pad, const float4 *__restrict__ lig,
+template <int THREADS, int A, int UNROLL, int MODE = 0, int MINB = 1>
+__global__ void __launch_bounds__(THREADS, MINB) k_packed_lig(const float4 *__restrict__ rec, int n_pad, const float4 *__restrict__ lig,
                                                         int nl, int reps, float rinv_max, double *out, Timing *tm) {
     extern __shared__ float4 lf[];
     const int nl2 = nl / 2;      // nl even in this benchmark
@@ -178,7 +179,10 @@ __global__ void __launch_bounds__(THREADS) k_packed_lig(const float4 *__restrict
                     const u64 dx = add2(px[a], Lxy.x), dy = add2(py[a], Lxy.y), dz = add2(pz[a], Lzq.x);
                     const u64 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
                     float d2a, d2b; unpack2(d2, d2a, d2b);
-                    const float ra = fminf(rsq(d2a), rinv_max), rb = fminf(rsq(d2b), rinv_max);
+                    float ra, rb;
+                    if (MODE == 1) { ra = d2a; rb = d2b; }
+                    else if (MODE == 2) { ra = rsq(d2a); rb = rsq(d2b); }
+                    else { ra = fminf(rsq(d2a), rinv_max); rb = fminf(rsq(d2b), rinv_max); }
                     s[a] = fma2(Lzq.y, pack2(ra, rb), s[a]);
                 }
             }
@@ -191,12 +195,29 @@ __global__ void __launch_bounds__(THREADS) k_packed_lig(const float4 *__restrict
     out[(size_t)blockIdx.x * THREADS + threadIdx.x] = e;
 }
 
+// pure MUFU.RSQ issue rate: 8 independent chains per thread
+__global__ void __launch_bounds__(128) k_mufu(int iters, float *out, Timing *tm) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 1.0f + threadIdx.x * 0.01f + i;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { tm->clk0 = clock64(); tm->ns0 = gtime(); }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = rsq(v[i]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { tm->clk1 = clock64(); tm->ns1 = gtime(); }
+    float s = 0; for (int i = 0; i < 8; ++i) s += v[i];
+    out[blockIdx.x * 128 + threadIdx.x] = s;
+}
+
 struct Ctx {
     float4 *rec; float *pp; float4 *lig; double *out; Timing *tm; int n_pad, nl, sms; double max_mhz;
 };
 
+static const char *g_filter = "";
 template <typename F>
 void run(const char *name, F launch, const Ctx &c, int threads, int ctas_per_sm, int reps, size_t smem) {
+    if (g_filter[0] && !strstr(name, g_filter)) return;
     const int grid = c.sms * ctas_per_sm;
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     launch(grid, threads, smem, reps / 4 + 1);          // warm-up
@@ -227,6 +248,7 @@ int main(int argc, char **argv) {
     const int n_atoms = argc > 1 ? atoi(argv[1]) : 5000;
     const int nl = argc > 2 ? atoi(argv[2]) : 40;
     const int reps = argc > 3 ? atoi(argv[3]) : 200;
+    const char *filter = argc > 4 ? argv[4] : "";
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     int khz = 0; CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0));
     Ctx c; c.sms = prop.multiProcessorCount; c.max_mhz = khz / 1000.0; c.nl = nl;
@@ -245,6 +267,7 @@ int main(int argc, char **argv) {
     CK(cudaMemcpy(c.rec, hrec.data(), sizeof(float4) * c.n_pad, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c.pp, hpp.data(), sizeof(float) * c.n_pad, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c.lig, hlig.data(), sizeof(float4) * 64 * nl, cudaMemcpyHostToDevice));
+    g_filter = filter;
     const float rmax = 1e6f;
     const size_t sm1 = sizeof(float4) * nl, sm2 = sizeof(float4) * 2 * nl, sm3 = sizeof(float4) * nl + sizeof(float) * nl;
 
@@ -259,5 +282,21 @@ int main(int argc, char **argv) {
     RUN_PACKED(128, 2, 2, 4); RUN_PACKED(128, 2, 2, 7); RUN_PACKED(128, 4, 1, 4); RUN_PACKED(128, 4, 1, 7); RUN_PACKED(128, 2, 4, 7);
     RUN_PLIG(128, 4, 2, 4); RUN_PLIG(128, 4, 2, 7); RUN_PLIG(128, 8, 1, 4); RUN_PLIG(128, 2, 2, 8);
     RUN_EXP(128, 4, 2, 4); RUN_EXP(128, 4, 2, 7); RUN_EXP(128, 8, 1, 4);
+#define RUN_PLIGM(T, A, U_, M, MB, OCC) run("plig-mode" #M " T" #T " A" #A " U" #U_ " minb" #MB, [&](int g, int t, size_t s, int r) { k_packed_lig<T, A, U_, M, MB><<<g, t, s>>>(c.rec, c.n_pad, c.lig, nl, r, rmax, c.out, c.tm); }, c, T, OCC, reps, sm2)
+    RUN_PLIGM(128, 4, 2, 1, 1, 7); RUN_PLIGM(128, 4, 2, 2, 1, 7);
+    RUN_PLIGM(128, 4, 2, 0, 1, 8); RUN_PLIGM(128, 4, 2, 0, 1, 9); RUN_PLIGM(128, 4, 4, 0, 1, 8);
+    RUN_PLIGM(128, 2, 4, 0, 1, 12); RUN_PLIGM(128, 2, 2, 0, 1, 12); RUN_PLIGM(128, 2, 2, 0, 1, 16);
+    RUN_PLIGM(256, 4, 2, 0, 1, 4); RUN_PLIGM(64, 4, 2, 0, 1, 16); RUN_PLIGM(64, 8, 1, 0, 1, 12); RUN_PLIGM(32, 8, 1, 0, 1, 28); RUN_PLIGM(32, 4, 2, 0, 1, 32);
+    if (!filter[0] || strstr("mufu-only", filter)) {
+        cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        float *o; CK(cudaMalloc(&o, sizeof(float) * c.sms * 16 * 128));
+        k_mufu<<<c.sms * 16, 128>>>(1000, o, c.tm); CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0)); k_mufu<<<c.sms * 16, 128>>>(20000, o, c.tm); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        Timing tm; CK(cudaMemcpy(&tm, c.tm, sizeof tm, cudaMemcpyDeviceToHost));
+        const double mhz = (double)(tm.clk1 - tm.clk0) / (double)(tm.ns1 - tm.ns0) * 1e3;
+        const double n = (double)c.sms * 16 * 128 * 8 * 20000;
+        printf("mufu-only: %.3f ms, clk %.0f MHz, %.2f MUFU.RSQ/clk/SM\n", ms, mhz, n / (ms * 1e-3) / (mhz * 1e6) / c.sms);
+    }
     return 0;
 }
