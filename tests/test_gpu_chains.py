@@ -119,16 +119,19 @@ def test_f32_chains_match_oracle_statistics(gpu, orc, ddd):
     off, lig = ddd.synth.make_ligands([24] * 48, prot)
     for rotate in (False, True):
         with gpu.Receptor(prot) as rec:
-            poses, stats, _ = gpu.run_chains(rec, off, lig, 1, 250, rotate, T, gpu.default_params(), seed=17)
-        acc_o, fin_o = [], []
+            poses, stats, trace = gpu.run_chains(rec, off, lig, 1, 250, rotate, T, gpu.default_params(), seed=17, want_trace=True)
+        acc_o, same = [], []
         for c in range(48):
-            _, st_o = orc.chain(prot, lig[off[c]:off[c + 1]], 250, rotate, T, orc.philox_stream(17, c))
-            acc_o.append(st_o["accepted"]); fin_o.append(st_o["final_energy"])
-        acc_o, fin_o = np.array(acc_o), np.array(fin_o)
+            pose_o, st_o, tr_o, _ = orc.chain(prot, lig[off[c]:off[c + 1]], 250, rotate, T, orc.philox_stream(17, c), want_trace=True)
+            acc_o.append(st_o["accepted"])
+            if np.array_equal(tr_o, trace[c]):                       # same decisions -> same trajectory
+                same.append(c)
+                assert np.allclose(gpu.chain_pose(off, 1, poses, c, 0), pose_o, rtol=0, atol=1e-9)
+                assert stats[c]["final_energy"] == pytest.approx(st_o["final_energy"], rel=1e-9)
+                assert stats[c]["draws"] == st_o["draws"] and stats[c]["retries"] == st_o["retries"]
+        acc_o = np.array(acc_o)
         assert abs(stats["accepted"].mean() - acc_o.mean()) <= 0.02 * max(1.0, acc_o.mean())
-        same = stats["accepted"] == acc_o
-        assert same.mean() >= 0.9                                    # most chains never hit an fp32 near-tie
-        assert np.allclose(stats["final_energy"][same], fin_o[same], rtol=1e-9)
+        assert len(same) >= 0.85 * 48                                # most chains never meet an fp32 near-tie
         # the chain's own fp32-summed energy agrees with the fp64 energy of the same pose (conditioning-aware)
         e, ab = gpu.energy_batch(gpu.Receptor(prot), off, poses, gpu.default_params(precision=gpu.PRECISION_F64), with_abs=True)
         assert np.allclose(e, stats["final_energy"], rtol=1e-12)
