@@ -52,6 +52,24 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+HOST = HERE / "host"
+
+
+def build_host() -> list[Path]:
+    """C++ mirror of the reference's Go API (host/): the drop-in binary and its metropolis_test.go restatement."""
+    build_library()
+    outs = []
+    common = ["g++", "-O2", "-std=c++17", "-Wall", "-Wextra", str(HOST / "metropolis.cpp")]
+    link = [f"-L{CSRC}", "-lddd_mc", f"-Wl,-rpath,{CSRC}", "-Wl,-rpath,$ORIGIN/../csrc", "-lpthread"]
+    for name, src in (("ddd_metropolis", "main.cpp"), ("ddd_metropolis_test", "metropolis_test.cpp")):
+        out = HOST / name
+        res = subprocess.run(common + [str(HOST / src), "-o", str(out)] + link, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("host build failed:\n" + res.stdout + res.stderr)
+        outs.append(out)
+    return outs
+
+
 def build_oracle() -> Path:
     """Compile the CPU oracle (test infrastructure; building the checker is not using it)."""
     res = subprocess.run(["make", "-C", str(ROOT / "oracle")], capture_output=True, text=True)
