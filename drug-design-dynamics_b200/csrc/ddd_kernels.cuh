@@ -208,24 +208,31 @@ __device__ __forceinline__ float warp_tile_sum_f32(const float4 *__restrict__ re
 // instead of idling at the barrier.  Each item's sum is stored under its item id and the items are added
 // in id order afterwards: the result does not depend on which warp computed what (bit-reproducible).
 // `ctl[0]` must be 0 on entry (reset by one thread before the barrier that precedes the call).
-constexpr int kMaxItems = 256;
 constexpr int kWarpTile = 32 * kTileA;
+// work items a CTA of `threads` threads stages in shared memory (12 per warp; a single-warp CTA needs none)
+__host__ __device__ constexpr int max_items(int threads) { return threads > 32 ? 12 * (threads / 32) : 0; }
 #ifndef DDD_DYNAMIC_TILES
 #define DDD_DYNAMIC_TILES 1
 #endif
 template <int THREADS>
 __device__ __forceinline__ double cta_pair_sum_f32(const RecView &rv, const float4 *lf, int nl, float rinv_max,
-                                                   int *ctl, double *item_out) {
+                                                   int *ctl, double *item_out, double *red, int &parity) {
     const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
     const int n_pairs = (nl + 1) >> 1;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_wt = (rv.n + kWarpTile - 1) / kWarpTile;                 // n_pad is a multiple of kRecPad >= kWarpTile
+    if (THREADS == 32) {                                                  // one warp: tiles in order, no staging
+        double e1 = 0.0;
+        for (int t = 0; t < n_wt; ++t) e1 += (double)warp_tile_sum_f32<kTileA>(rv.f32, t * kWarpTile, lf2, n_pairs, rinv_max);
+        return warp_sum(e1);
+    }
+    constexpr int kMaxItems = max_items(THREADS) > 0 ? max_items(THREADS) : 1;
     const int chunk = (n_wt + kMaxItems - 1) / kMaxItems;
     const int n_items = chunk ? (n_wt + chunk - 1) / chunk : 0;
-    int next_static = threadIdx.x >> 5;
+    int next_static = warp;
     for (;;) {
         int it = 0;
-        if (DDD_DYNAMIC_TILES && THREADS > 32) {
+        if (DDD_DYNAMIC_TILES) {
             if (lane == 0) it = atomicAdd(ctl, 1);
             it = __shfl_sync(0xffffffffu, it, 0);
         } else { it = next_static; next_static += THREADS / 32; }
@@ -234,13 +241,14 @@ __device__ __forceinline__ double cta_pair_sum_f32(const RecView &rv, const floa
         double acc = 0.0;
         for (int t = it * chunk; t < t_end; ++t)
             acc += (double)warp_tile_sum_f32<kTileA>(rv.f32, t * kWarpTile, lf2, n_pairs, rinv_max);
-        acc = warp_sum(acc);
-        if (lane == 0) item_out[it] = acc;
+        item_out[it * 32 + lane] = acc;                                   // per item AND per lane: no reduction here
     }
     __syncthreads();
+    // fixed summation order, independent of which warp computed which item: thread (warp, lane) adds lane `lane`
+    // of items warp, warp + W, ... ; then the deterministic block sum
     double e = 0.0;
-    for (int it = lane; it < n_items; it += 32) e += item_out[it];
-    return warp_sum(e);
+    for (int it = warp; it < n_items; it += THREADS / 32) e += item_out[it * 32 + lane];
+    return block_sum<THREADS>(e, red, parity);
 }
 
 // write atom i of the fp32 pose in the pair-packed layout
@@ -299,23 +307,32 @@ struct ChainStats {
     double final_energy, start_energy, chain_energy;
 };
 
-__host__ __device__ inline size_t chain_smem_bytes(int nl_cap) {
-    // cur xyz, prev xyz, q : 7 double arrays; packed fp32 pose; 2 x kMaxWarps reduction doubles; work-item sums;
-    // 4 counters; 4 control words (item counter, two alternating "collision possible" flags)
-    return (size_t)nl_cap * (7 * sizeof(double) + sizeof(float4)) + (2 * kMaxWarps + kMaxItems) * sizeof(double) +
-           4 * sizeof(long long) + 4 * sizeof(int);
+__host__ __device__ inline size_t chain_smem_bytes(int nl_cap, int threads) {
+    // control words + counters + reduction scratch + per-lane work-item sums, then the packed fp32 pose and the
+    // 7 fp64 arrays (cur xyz, prev xyz, q); see ChainSmem
+    return 48 + (2 * kMaxWarps + max_items(threads) * 32) * sizeof(double) + (size_t)nl_cap * (7 * sizeof(double) + sizeof(float4));
 }
 
-// Views into the CTA's dynamic shared memory.  Only the capacity is kept in a register; every array address is
-// base + constant * cap, recomputed at the point of use (ten live 64-bit pointers would cost 20 registers of the
-// 64 the chain kernel is allowed and wreck the schedule of the pair loop).
+// Views into the CTA's dynamic shared memory.  Layout (bytes): [ctl 16][cnt 32][red 2*kMaxWarps*8][item_out
+// max_items(THREADS)*32*8][lf 16*cap][cx cy cz px py pz q: 7*8*cap].  Everything the pair loop touches sits at a
+// compile-time constant offset; only `cap` is kept in a register (ten live 64-bit pointers would cost 20 of the 64
+// registers the chain kernel is allowed).
+template <int THREADS>
 struct ChainSmem {
     int cap;
+    static constexpr int kCtlOff = 0, kCntOff = 16, kRedOff = 48, kItemOff = kRedOff + 2 * kMaxWarps * 8,
+                         kLfOff = kItemOff + max_items(THREADS) * 32 * 8;
     __device__ __forceinline__ ChainSmem(unsigned char *, int cap_) : cap(cap_) {}
-    __device__ __forceinline__ double *base() const {
+    __device__ __forceinline__ unsigned char *raw() const {
         extern __shared__ __align__(16) unsigned char ddd_smem_raw[];
-        return reinterpret_cast<double *>(ddd_smem_raw);
+        return ddd_smem_raw;
     }
+    __device__ __forceinline__ int *ctl() const { return reinterpret_cast<int *>(raw() + kCtlOff); }
+    __device__ __forceinline__ long long *cnt() const { return reinterpret_cast<long long *>(raw() + kCntOff); }
+    __device__ __forceinline__ double *red() const { return reinterpret_cast<double *>(raw() + kRedOff); }
+    __device__ __forceinline__ double *item_out() const { return reinterpret_cast<double *>(raw() + kItemOff); }
+    __device__ __forceinline__ float4 *lf() const { return reinterpret_cast<float4 *>(raw() + kLfOff); }
+    __device__ __forceinline__ double *base() const { return reinterpret_cast<double *>(raw() + kLfOff) + 2 * cap; }
     __device__ __forceinline__ double *cx() const { return base(); }
     __device__ __forceinline__ double *cy() const { return base() + cap; }
     __device__ __forceinline__ double *cz() const { return base() + 2 * cap; }
@@ -323,11 +340,6 @@ struct ChainSmem {
     __device__ __forceinline__ double *py() const { return base() + 4 * cap; }
     __device__ __forceinline__ double *pz() const { return base() + 5 * cap; }
     __device__ __forceinline__ double *q() const { return base() + 6 * cap; }
-    __device__ __forceinline__ float4 *lf() const { return reinterpret_cast<float4 *>(base() + 7 * cap); }
-    __device__ __forceinline__ double *red() const { return reinterpret_cast<double *>(lf() + cap); }
-    __device__ __forceinline__ double *item_out() const { return red() + 2 * kMaxWarps; }
-    __device__ __forceinline__ long long *cnt() const { return reinterpret_cast<long long *>(item_out() + kMaxItems); }
-    __device__ __forceinline__ int *ctl() const { return reinterpret_cast<int *>(cnt() + 4); }
 };
 
 // IsCollisionFree (:229-242) over all i<j pairs, spread over the CTA; returns "this thread saw
@@ -335,7 +347,7 @@ struct ChainSmem {
 // sqrt(d2) < min_distance is decided from d2 alone unless d2 lies within 1e-9 (relative) of
 // min_distance^2, where the reference's own sqrt comparison (:235-236) is evaluated.
 template <int THREADS>
-__device__ __forceinline__ bool collision_partial(const ChainSmem &s, int nl, double min_distance) {
+__device__ __forceinline__ bool collision_partial(const ChainSmem<THREADS> &s, int nl, double min_distance) {
     const int full_rows = (nl - 1) / 2;
     const int n_full = full_rows * nl;
     const int total = n_full + ((nl & 1) ? 0 : nl / 2);
@@ -372,7 +384,8 @@ __device__ __forceinline__ CollisionPlan collision_plan(int nl) {
 }
 
 // returns bit 1: some pair is certainly closer than min_distance; bit 0: some pair is inside the uncertainty band
-__device__ __forceinline__ int collision_screen_f32(const ChainSmem &s, int nl, const CollisionPlan &cp, float m2) {
+template <class SM>
+__device__ __forceinline__ int collision_screen_f32(const SM &s, int nl, const CollisionPlan &cp, float m2) {
     const int n_pairs = (nl + 1) >> 1;
     const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(s.lf());
     const float *lff = reinterpret_cast<const float *>(s.lf());
@@ -383,6 +396,7 @@ __device__ __forceinline__ int collision_screen_f32(const ChainSmem &s, int nl, 
         // |error of the fp32 d2| of a pair near min_distance <= ~4e-7 * (|x|+|y|+|z|); 1e-6 * (...) is a safe bound
         slack = fmaxf(slack, 1e-6f * (fabsf(xi) + fabsf(yi) + fabsf(zi) + 1.0f));
         const f32x2 ax = pack2(xi, xi), ay = pack2(yi, yi), az = pack2(zi, zi);
+#pragma unroll 4
         for (int k = cp.k0; k < n_pairs; k += cp.k_step) {
             const ulonglong2 Lxy = lf2[2 * k], Lzq = lf2[2 * k + 1];
             const f32x2 dx = add2(ax, Lxy.x), dy = add2(ay, Lxy.y), dz = add2(az, Lzq.x);
@@ -422,13 +436,14 @@ __device__ __forceinline__ void draw_axis_angle(const Stream &st, uint64_t pos, 
 }
 
 template <int THREADS, bool PRECISE>
-__device__ __forceinline__ double chain_energy(const ChainArgs &a, const ChainSmem &s, int nl, int &parity) {
-    if (!PRECISE) return a.prm.k_coulomb * cta_pair_sum_f32<THREADS>(a.rec, s.lf(), nl, a.prm.rinv_max, s.ctl(), s.item_out());
+__device__ __forceinline__ double chain_energy(const ChainArgs &a, const ChainSmem<THREADS> &s, int nl, int &parity) {
+    if (!PRECISE) return a.prm.k_coulomb * cta_pair_sum_f32<THREADS>(a.rec, s.lf(), nl, a.prm.rinv_max, s.ctl(), s.item_out(), s.red(), parity);
     const double part = pair_sum_f64<THREADS, false>(a.rec, s.cx(), s.cy(), s.cz(), s.q(), nl, a.prm.k_coulomb, a.prm.clamp_distance, nullptr);
     return block_sum<THREADS>(part, s.red(), parity);
 }
 
-__device__ __forceinline__ void store_pose(const ChainArgs &a, const ChainSmem &s, int i, double x, double y, double z) {
+template <class SM>
+__device__ __forceinline__ void store_pose(const ChainArgs &a, const SM &s, int i, double x, double y, double z) {
     s.cx()[i] = x; s.cy()[i] = y; s.cz()[i] = z;
     store_lig_f32(s.lf(), i, (float)(x - a.rec.cx), (float)(y - a.rec.cy), (float)(z - a.rec.cz), (float)s.q()[i]);
 }
@@ -441,7 +456,7 @@ __device__ __forceinline__ void store_pose(const ChainArgs &a, const ChainSmem &
 #endif
 template <int THREADS, bool PRECISE>
 __global__ void __launch_bounds__(THREADS, (PRECISE ? 1 : DDD_CHAIN_WARPS_PER_SM * 32 / THREADS)) mc_chain_kernel(const ChainArgs a) {
-    const ChainSmem s(nullptr, a.nl_cap);
+    const ChainSmem<THREADS> s(nullptr, a.nl_cap);
     const int tid = threadIdx.x;
     const long long local = a.order ? (long long)a.order[blockIdx.x] : (long long)blockIdx.x;
     const long long chain = a.chain_begin + local;
@@ -613,7 +628,7 @@ struct EnergyArgs {
 
 template <bool PRECISE, bool WITH_ABS>
 __global__ void __launch_bounds__(kThreads) energy_batch_kernel(const EnergyArgs a) {
-    const ChainSmem s(nullptr, a.nl_cap);
+    const ChainSmem<kThreads> s(nullptr, a.nl_cap);
     const int tid = threadIdx.x;
     const long long lig = blockIdx.x;
     const long long off = a.offsets[lig];
@@ -635,7 +650,7 @@ __global__ void __launch_bounds__(kThreads) energy_batch_kernel(const EnergyArgs
         part = pair_sum_f64<kThreads, WITH_ABS>(a.rec, s.cx(), s.cy(), s.cz(), s.q(), nl, a.prm.k_coulomb, a.prm.clamp_distance, &ab);
     }
     if (PRECISE) e = block_sum<kThreads>(part, s.red(), parity);
-    else e = a.prm.k_coulomb * cta_pair_sum_f32<kThreads>(a.rec, s.lf(), nl, a.prm.rinv_max, s.ctl(), s.item_out());
+    else e = a.prm.k_coulomb * cta_pair_sum_f32<kThreads>(a.rec, s.lf(), nl, a.prm.rinv_max, s.ctl(), s.item_out(), s.red(), parity);
     if (WITH_ABS) ab = block_sum<kThreads>(ab, s.red(), parity);
     if (tid == 0) {
         a.out_energy[lig] = e;
