@@ -21,6 +21,7 @@ SYMBOLS = [
     "ddd_closest_atom_batch", "ddd_shift_closer_batch", "ddd_randomize_pose_batch",
     "ddd_screen_create", "ddd_screen_run", "ddd_screen_sync", "ddd_screen_last_kernel_ms",
     "ddd_screen_download", "ddd_screen_destroy", "ddd_screen_set_chain_threads", "ddd_screen_chain_threads",
+    "ddd_screen_set_chain_slots", "ddd_screen_chain_slots",
     "ddd_shard_plan", "ddd_device_info",
     "ddd_chain_kernel_info",
 ]
@@ -104,6 +105,8 @@ def lib() -> C.CDLL:
         "ddd_screen_sync": (C.c_int, [vp]),
         "ddd_screen_set_chain_threads": (C.c_int, [vp, i32]),
         "ddd_screen_chain_threads": (i32, [vp]),
+        "ddd_screen_set_chain_slots": (C.c_int, [vp, i32]),
+        "ddd_screen_chain_slots": (i32, [vp]),
         "ddd_screen_last_kernel_ms": (dbl, [vp]),
         "ddd_screen_download": (C.c_int, [vp, vp, vp]),
         "ddd_screen_destroy": (C.c_int, [vp]),
@@ -339,6 +342,13 @@ class Screen:
 
     def chain_threads(self) -> int:
         return int(lib().ddd_screen_chain_threads(self._h))
+
+    def set_chain_slots(self, slots: int):
+        """chains resident per SM in the SM-persistent engine (0 = automatic)"""
+        _check(lib().ddd_screen_set_chain_slots(self._h, slots))
+
+    def chain_slots(self) -> int:
+        return int(lib().ddd_screen_chain_slots(self._h))
 
     def sync(self):
         _check(lib().ddd_screen_sync(self._h))

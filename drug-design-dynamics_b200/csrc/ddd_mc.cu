@@ -6,6 +6,7 @@
 // and the replica pick of SimulateEnergyMinimizationParallel (:102-109).
 // There is deliberately no CPU implementation of any compute entry point in this file.
 #include "ddd_kernels.cuh"
+#include "ddd_sm_chain.cuh"
 #include "../../include/ddd_mc.h"
 
 #include <algorithm>
@@ -33,6 +34,7 @@ struct Dev {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
+    size_t max_smem = 0;                   // opt-in dynamic shared memory per CTA
 };
 std::vector<Dev> g_devs;
 
@@ -138,6 +140,8 @@ struct ScreenDev {
     long long rec_base = 0;
     float last_ms = 0.f;
     int threads = 0;                       // CTA width used by the last launch
+    int slots = 0;                         // chains resident per SM in the last launch (0: one-CTA-per-chain engine)
+    int *d_queue = nullptr;                // SM-persistent engine: dynamic chain counter
 };
 
 struct ddd_screen {
@@ -148,7 +152,8 @@ struct ddd_screen {
     std::vector<int64_t> offsets;
     std::vector<ScreenDev> devs;
     bool launched = false;
-    int threads_override = 0;              // 0: pick from the chain count
+    int threads_override = 0;              // > 0: one-CTA-per-chain engine with this CTA width
+    int slots_override = 0;                // > 0: SM-persistent engine with this many chains per SM; both 0: automatic
 };
 
 namespace {
@@ -161,6 +166,14 @@ int pick_chain_threads(int64_t n_chains, int sm_count) {
     if (n_chains >= (int64_t)sm_count * 48) return 64;
     if (n_chains >= (int64_t)sm_count * 4) return 128;
     return 256;
+}
+
+// Chains resident per SM in the SM-persistent engine.  A launch whose chains all fit (<= grid * kSlotsAuto) is
+// dealt statically, ceil(n/grid) per SM; beyond that slots refill from the launch's queue as chains finish.
+constexpr int kSlotsAuto = 8;
+int pick_chain_slots(int64_t n_chains, int grid) {
+    const int64_t per_sm = (n_chains + grid - 1) / std::max(grid, 1);
+    return (int)std::max<int64_t>(1, std::min<int64_t>(kSlotsAuto, per_sm));
 }
 
 // chains [begin[k], begin[k+1]) go to shard k; contiguous, balanced by sum(nL + 1)
@@ -189,7 +202,7 @@ void plan_shards(const int64_t *offsets, int64_t n_lig, int replicas, int n_shar
 void free_screen_dev(ScreenDev &sd) {
     cudaSetDevice(g_devs[sd.di].id);
     cudaFree(sd.d_offsets); cudaFree(sd.d_lig); cudaFree(sd.d_order); cudaFree(sd.d_out);
-    cudaFree(sd.d_stats); cudaFree(sd.d_trace); cudaFree(sd.d_rec); cudaFree(sd.d_rec_off);
+    cudaFree(sd.d_stats); cudaFree(sd.d_trace); cudaFree(sd.d_rec); cudaFree(sd.d_rec_off); cudaFree(sd.d_queue);
     sd = ScreenDev();
 }
 
@@ -236,6 +249,7 @@ int screen_create_impl(const ddd_receptor *r, const int64_t *offsets, const doub
         if (!rc) guard(dev_alloc(&d.d_lig, (size_t)d.n_atoms_in * 4));
         if (!rc) guard(dev_alloc(&d.d_out, (size_t)d.out_atoms * 4));
         if (!rc) guard(dev_alloc(&d.d_stats, (size_t)n_local));
+        if (!rc) guard(dev_alloc(&d.d_queue, 1));
         if (!rc) {
             static_assert(sizeof(long long) == sizeof(int64_t), "");
             ce = cudaMemcpyAsync(d.d_offsets, s->offsets.data(), sizeof(int64_t) * ((size_t)n_lig + 1), cudaMemcpyHostToDevice, g_devs[di].stream);
@@ -309,14 +323,45 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
         a.recorded = d.d_rec; a.rec_offsets = d.d_rec_off; a.rec_base = d.rec_base;
         a.out_xyzq = d.d_out; a.out_base = d.out_base; a.out_stats = d.d_stats; a.out_trace = d.d_trace;
         a.nl_cap = d.nl_cap;
+        const bool precise = p->precision == DDD_PRECISION_F64;
+        if (s->threads_override <= 0 && n_local > 0) {
+            // SM-persistent engine: one 32-warp CTA per SM, K resident chains each (ddd_sm_chain.cuh)
+            SmArgs A;
+            A.c = a;
+            const int grid = (int)std::min<int64_t>(dev.sm_count, n_local);
+            const int k_fit = (int)std::min<size_t>(kSmMaxSlots, (dev.max_smem - 16) / (sm_smem_bytes(d.nl_cap, 1) - 16));
+            if (k_fit < 1) return fail(DDD_ELIMIT, "ligand of %d atoms does not fit one SM's shared memory", d.nl_cap);
+            const int k_want = s->slots_override > 0 ? s->slots_override : pick_chain_slots(n_local, grid);
+            A.slots = std::max(1, std::min(k_want, k_fit));
+            A.queue = d.d_queue; A.n_local = n_local; A.first_dynamic = (long long)grid * A.slots;
+            const int n = (int)s->rec->n;
+            A.tile_a = (n + 127) / 128 >= 24 ? 4 : 1;
+            A.n_wt = (n + 32 * A.tile_a - 1) / (32 * A.tile_a);
+            A.chunk = (A.n_wt + kSmMaxItems - 1) / kSmMaxItems;
+            A.n_items = A.chunk ? (A.n_wt + A.chunk - 1) / A.chunk : 0;
+            const size_t smem = sm_smem_bytes(d.nl_cap, A.slots);
+            d.threads = kSmThreads; d.slots = A.slots;
+            CUDA_TRY(cudaMemsetAsync(d.d_queue, 0, sizeof(int), dev.stream));
+            CUDA_TRY(cudaEventRecord(dev.ev0, dev.stream));
+            if (precise) {
+                if (int rc = set_smem(mc_sm_kernel<true>, smem)) return rc;
+                mc_sm_kernel<true><<<(unsigned)grid, kSmThreads, smem, dev.stream>>>(A);
+            } else {
+                if (int rc = set_smem(mc_sm_kernel<false>, smem)) return rc;
+                mc_sm_kernel<false><<<(unsigned)grid, kSmThreads, smem, dev.stream>>>(A);
+            }
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaEventRecord(dev.ev1, dev.stream));
+            continue;
+        }
         const int threads = s->threads_override > 0 ? s->threads_override : pick_chain_threads(n_local, dev.sm_count);
         const size_t smem = chain_smem_bytes(d.nl_cap, threads);
-        d.threads = threads;
+        d.threads = threads; d.slots = 0;
         CUDA_TRY(cudaEventRecord(dev.ev0, dev.stream));
 #define LAUNCH_CHAIN(T, PR)                                                                   \
         do { if (int rc = set_smem(mc_chain_kernel<T, PR>, smem)) return rc;                   \
              mc_chain_kernel<T, PR><<<(unsigned)n_local, T, smem, dev.stream>>>(a); } while (0)
-        if (p->precision == DDD_PRECISION_F64) {
+        if (precise) {
             switch (threads) { case 32: LAUNCH_CHAIN(32, true); break; case 64: LAUNCH_CHAIN(64, true); break;
                                case 256: LAUNCH_CHAIN(256, true); break; default: LAUNCH_CHAIN(128, true); }
         } else {
@@ -408,6 +453,7 @@ int ddd_init(const int *devices, int n_devices) {
         CUDA_TRY(cudaGetDeviceProperties(&prop, id));
         if (prop.major < 10) { g_devs.clear(); return fail(DDD_ENODEVICE, "device %d (%s, sm_%d%d) is not Blackwell: this library ships sm_100a code only", id, prop.name, prop.major, prop.minor); }
         d.sm_count = prop.multiProcessorCount;
+        d.max_smem = prop.sharedMemPerBlockOptin;
         CUDA_TRY(cudaSetDevice(id));
         CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreate(&d.ev0));
@@ -758,6 +804,20 @@ int ddd_screen_set_chain_threads(ddd_screen *s, int32_t threads) {
 int32_t ddd_screen_chain_threads(const ddd_screen *s) {
     if (!s || s->devs.empty()) return 0;
     return s->devs[0].threads;
+}
+
+int ddd_screen_set_chain_slots(ddd_screen *s, int32_t slots) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!s) return fail(DDD_EINVAL, "screen is NULL");
+    if (slots < 0 || slots > kSmMaxSlots) return fail(DDD_EINVAL, "chains per SM must be 0..%d (got %d)", kSmMaxSlots, slots);
+    s->slots_override = slots;
+    if (slots > 0) s->threads_override = 0;
+    return DDD_OK;
+}
+
+int32_t ddd_screen_chain_slots(const ddd_screen *s) {
+    if (!s || s->devs.empty()) return 0;
+    return s->devs[0].slots;
 }
 
 int ddd_screen_sync(ddd_screen *s) {

@@ -1,0 +1,467 @@
+// ddd_sm_chain.cuh -- SM-persistent engine of the Metropolis chain kernel (sm_100a).
+//
+// One CTA of 32 warps owns one SM and keeps up to K chains ("slots") of
+// SimulateEnergyMinimizationOneProc (reference metropolisMethod/metropolis.go:116-136) resident in
+// shared memory.  A chain alternates between
+//   * an ENERGY phase: CalculateEnergy (:247-262) cut into work items (runs of receptor warp tiles)
+//     that ANY warp of the CTA may take from the slot's counter, and
+//   * a SERIAL phase run by the one warp that finished the last item: item sums added in item order,
+//     AcceptMove (:141-149), the next proposal (:154-208) with its collision retries (:229-242).
+// There is no CTA-wide barrier inside the step loop: a chain that is proposing (latency-bound fp64 +
+// Philox work of one warp) overlaps with the pair sums of the other chains, and when chains finish the
+// remaining ones inherit all 32 warps -- the SM stays busy until its last chain ends, which the
+// one-CTA-per-chain engine (ddd_kernels.cuh) cannot do when a launch has only ~7 chains per SM.
+// Chains beyond grid*K are pulled from a global counter as slots free up.
+//
+// Results do not depend on which warp computed which item or on K: item sums are stored under their
+// item id and added in id order, and a chain's uniform stream is indexed by (chain id, draw index).
+#pragma once
+
+#include "ddd_kernels.cuh"
+
+namespace ddd {
+
+constexpr int kSmThreads  = 1024;
+constexpr int kSmWarps    = kSmThreads / 32;
+constexpr int kSmMaxSlots = 16;
+constexpr int kSmMaxItems = 128;            // work items per energy evaluation (item sums kept per slot)
+constexpr int kSlotIdle   = 0x3fffffff;     // next_item of a slot that has nothing to hand out
+
+enum : int { ST_START64 = 0, ST_START32 = 1, ST_STEP = 2, ST_FINAL64 = 3, ST_PROPOSE = 4, ST_LOAD = 5 };
+
+struct __align__(16) SmSlotCtl {
+    int next_item, done_items, mode, stage;           // mode: 0 = fp32 items, 1 = fp64 items
+    int nl, status, rep, bailed;
+    long long local, step;
+    unsigned long long pos;                           // uniforms consumed so far
+    long long accepted, downhill, retries;
+    double cur_e, start_e;
+    long long off;                                    // first atom of the ligand in the global CSR
+    unsigned long long stream_id;
+    const double *rec_ptr;                            // recorded stream (nullable)
+    long long rec_len;
+};
+static_assert(sizeof(SmSlotCtl) == 128, "SmSlotCtl is laid out as one 128-byte block");
+
+struct SmArgs {
+    ChainArgs c;
+    int *queue;              // device counter, zero before the launch: next dynamic chain = first_dynamic + atomicAdd
+    long long n_local;       // chains of this launch
+    long long first_dynamic; // gridDim.x * slots: chains below are assigned statically (slot s of CTA b: s*grid + b)
+    int slots;               // K
+    int tile_a;              // receptor atoms per lane per warp tile: 4 (production) or 1 (small receptors)
+    int n_wt;                // warp tiles of 32*tile_a atoms
+    int chunk, n_items;      // warp tiles per item; items per energy evaluation (<= kSmMaxItems)
+};
+
+__host__ __device__ inline size_t sm_smem_bytes(int nl_cap, int slots) {
+    return 16 + (size_t)slots * (sizeof(SmSlotCtl) + kSmMaxItems * sizeof(double) + (size_t)nl_cap * (7 * sizeof(double) + sizeof(float4)));
+}
+
+// Views into the CTA's shared memory: [live 16][ctl K*128][items K*kSmMaxItems*8][slot poses K * cap * 72]
+struct SlotView {
+    unsigned char *pose;     // this slot's pose block: lf (16*cap) then cx cy cz px py pz q (8*cap each)
+    int cap;
+    __device__ __forceinline__ float4 *lf() const { return reinterpret_cast<float4 *>(pose); }
+    __device__ __forceinline__ double *base() const { return reinterpret_cast<double *>(pose) + 2 * cap; }
+    __device__ __forceinline__ double *cx() const { return base(); }
+    __device__ __forceinline__ double *cy() const { return base() + cap; }
+    __device__ __forceinline__ double *cz() const { return base() + 2 * cap; }
+    __device__ __forceinline__ double *px() const { return base() + 3 * cap; }
+    __device__ __forceinline__ double *py() const { return base() + 4 * cap; }
+    __device__ __forceinline__ double *pz() const { return base() + 5 * cap; }
+    __device__ __forceinline__ double *q() const { return base() + 6 * cap; }
+};
+
+struct SmView {
+    unsigned char *raw;
+    int slots, cap;
+    __device__ __forceinline__ int *live() const { return reinterpret_cast<int *>(raw); }
+    __device__ __forceinline__ SmSlotCtl *ctl(int s) const { return reinterpret_cast<SmSlotCtl *>(raw + 16) + s; }
+    __device__ __forceinline__ double *items(int s) const {
+        return reinterpret_cast<double *>(raw + 16 + (size_t)slots * sizeof(SmSlotCtl)) + s * kSmMaxItems;
+    }
+    __device__ __forceinline__ SlotView slot(int s) const {
+        SlotView v;
+        v.cap = cap;
+        v.pose = raw + 16 + (size_t)slots * (sizeof(SmSlotCtl) + kSmMaxItems * sizeof(double)) + (size_t)s * cap * 72;
+        return v;
+    }
+};
+
+__device__ __forceinline__ int ld_volatile(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+__device__ __forceinline__ void st_volatile(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
+
+// ------------------------------------------------------------------ energy work items
+__device__ __forceinline__ double sm_item_f32(const SmArgs &A, const float4 *lf, int nl, int it) {
+    const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
+    const int n_pairs = (nl + 1) >> 1;
+    const int t0 = it * A.chunk, t1 = min(t0 + A.chunk, A.n_wt);
+    double acc = 0.0;
+    if (A.tile_a == 4) {
+        for (int t = t0; t < t1; ++t) acc += (double)warp_tile_sum_f32<4>(A.c.rec.f32, t * 128, lf2, n_pairs, A.c.prm.rinv_max);
+    } else {
+        for (int t = t0; t < t1; ++t) acc += (double)warp_tile_sum_f32<1>(A.c.rec.f32, t * 32, lf2, n_pairs, A.c.prm.rinv_max);
+    }
+    return warp_sum(acc);
+}
+
+// the reference's per-term fp64 arithmetic (:253-258) for the receptor atoms of one item
+__device__ __forceinline__ double sm_item_f64(const SmArgs &A, const SlotView &s, int nl, int it) {
+    const int atoms_per_tile = 32 * A.tile_a;
+    const int p0 = it * A.chunk * atoms_per_tile, p1 = min((it + 1) * A.chunk * atoms_per_tile, A.c.rec.n);
+    const double K = A.c.prm.k_coulomb, clampd = A.c.prm.clamp_distance;
+    const double *lx = s.cx(), *ly = s.cy(), *lz = s.cz(), *lq = s.q();
+    double e = 0.0;
+    for (int p = p0 + (int)(threadIdx.x & 31); p < p1; p += 32) {
+        const Atom64 P = A.c.rec.f64[p];
+        for (int l = 0; l < nl; ++l) {
+            const double ddx = P.x - lx[l], ddy = P.y - ly[l], ddz = P.z - lz[l];
+            double d = sqrt(ddx * ddx + ddy * ddy + ddz * ddz);          // :253 (Pow(x,2) == x*x)
+            if (d < clampd) d = clampd;                                   // :255-257
+            e += K * (P.q * lq[l]) / d;                                   // :258
+        }
+    }
+    return warp_sum(e);
+}
+
+// ------------------------------------------------------------------ one-warp proposal helpers
+__device__ __forceinline__ void sm_store_pose(const SmArgs &A, const SlotView &s, int i, double x, double y, double z) {
+    s.cx()[i] = x; s.cy()[i] = y; s.cz()[i] = z;
+    store_lig_f32(s.lf(), i, (float)(x - A.c.rec.cx), (float)(y - A.c.rec.cy), (float)(z - A.c.rec.cz), (float)s.q()[i]);
+}
+
+// fp32 screen in front of IsCollisionFree, one warp: atoms in rows of 32 lanes; a short last row gives every atom
+// 32/rem lanes that split the ligand pairs.  Same classification as collision_screen_f32 (ddd_kernels.cuh).
+__device__ __forceinline__ int warp_collision_screen(const SlotView &s, int nl, float m2) {
+    const int lane = threadIdx.x & 31;
+    const int n_pairs = (nl + 1) >> 1;
+    const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(s.lf());
+    const float *lff = reinterpret_cast<const float *>(s.lf());
+    float dmin = 3.0e38f, slack = 0.f;
+    for (int b = 0; b < nl; b += 32) {
+        const int rem = nl - b;
+        int i, k0, ks;
+        if (rem >= 32) { i = b + lane; k0 = 0; ks = 1; }
+        else { const int g = 32 / rem; const int grp = lane / rem; i = grp < g ? b + (lane - grp * rem) : nl; k0 = grp; ks = g; }
+        if (i >= nl) continue;
+        const float *mine = lff + 8 * (i >> 1) + (i & 1);
+        const float xi = -mine[0], yi = -mine[2], zi = -mine[4];
+        slack = fmaxf(slack, 1e-6f * (fabsf(xi) + fabsf(yi) + fabsf(zi) + 1.0f));
+        const f32x2 ax = pack2(xi, xi), ay = pack2(yi, yi), az = pack2(zi, zi);
+#pragma unroll 4
+        for (int k = k0; k < n_pairs; k += ks) {
+            const ulonglong2 Lxy = lf2[2 * k], Lzq = lf2[2 * k + 1];
+            const f32x2 dx = add2(ax, Lxy.x), dy = add2(ay, Lxy.y), dz = add2(az, Lzq.x);
+            const f32x2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+            float d2a, d2b;
+            unpack2(d2, d2a, d2b);
+            if (k == (i >> 1)) { if (i & 1) d2b = 3.0e38f; else d2a = 3.0e38f; }       // j == i
+            dmin = fminf(dmin, fminf(d2a, d2b));
+        }
+    }
+    const int hit = dmin < m2 * 0.98f - slack;
+    const int near = dmin < m2 * 1.02f + slack;
+    return (hit << 1) | (near & ~hit);
+}
+
+// exact IsCollisionFree (:229-242) by one warp: pairs (i, i+m mod nl), m = 1..nl/2, as in collision_partial
+__device__ __forceinline__ bool warp_collision_exact(const SlotView &s, int nl, double min_distance) {
+    const int full_rows = (nl - 1) / 2;
+    const int n_full = full_rows * nl;
+    const int total = n_full + ((nl & 1) ? 0 : nl / 2);
+    const double m2 = min_distance * min_distance, m2_lo = m2 * (1.0 - 1e-9), m2_hi = m2 * (1.0 + 1e-9);
+    bool hit = false;
+    for (int w = threadIdx.x & 31; w < total; w += 32) {
+        int i, m;
+        if (w < n_full) { m = w / nl + 1; i = w - (m - 1) * nl; } else { i = w - n_full; m = nl / 2; }
+        int j = i + m; if (j >= nl) j -= nl;
+        const double dx = s.cx()[i] - s.cx()[j], dy = s.cy()[i] - s.cy()[j], dz = s.cz()[i] - s.cz()[j];
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 < m2_lo) hit = true;
+        else if (d2 < m2_hi) hit |= (sqrt(d2) < min_distance);              // :235-236
+    }
+    return hit;
+}
+
+// hand the slot's pose out for an energy evaluation; false when the receptor has no atoms (nothing to hand out)
+__device__ __forceinline__ bool sm_publish(const SmArgs &A, SmSlotCtl *c, int mode, int stage) {
+    if ((threadIdx.x & 31) == 0) { c->mode = mode; c->stage = stage; c->done_items = 0; }
+    if (A.n_items == 0) return false;
+    __threadfence_block();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) st_volatile(&c->next_item, 0);
+    return true;
+}
+
+// ------------------------------------------------------------------ serial phase (one warp)
+// `load_pos` >= 0: (re)start the slot with the chain at launch position load_pos; -1: the slot's items are complete.
+template <bool PRECISE>
+__device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, int slot_id, long long load_pos) {
+    const int lane = threadIdx.x & 31;
+    SmSlotCtl *c = V.ctl(slot_id);
+    const SlotView s = V.slot(slot_id);
+    const ChainArgs &a = A.c;
+    const DevParams &P = a.prm;
+    int stage;
+    double e = 0.0;
+    if (load_pos >= 0) stage = ST_LOAD;
+    else {
+        stage = c->stage;
+        const double *items = V.items(slot_id);
+        for (int it = lane; it < A.n_items; it += 32) e += items[it];       // fixed order: independent of who computed what
+        e = warp_sum(e);
+    }
+    int status = 0;
+    // fold this invocation's status bits into the slot (bit 2 can be raised by any lane that drew)
+    auto flush_status = [&]() {
+        const int st_or = __any_sync(0xffffffffu, status & 2) ? 2 : 0;
+        if (lane == 0) c->status |= (status & 1) | st_or;
+        status = 0;
+        __syncwarp();
+    };
+    for (;;) {
+        if (stage == ST_LOAD) {
+            if (load_pos < 0) {                                                 // pull the next chain of the launch
+                int t = 0;
+                if (lane == 0) t = atomicAdd(A.queue, 1);
+                t = __shfl_sync(0xffffffffu, t, 0);
+                load_pos = A.first_dynamic + (long long)t;
+            }
+            if (load_pos >= A.n_local) {                                        // nothing left: the slot dies
+                if (lane == 0) { st_volatile(&c->next_item, kSlotIdle); atomicSub(V.live(), 1); }
+                return;
+            }
+            const long long local = a.order ? (long long)a.order[load_pos] : load_pos;
+            const long long chain = a.chain_begin + local;
+            const long long lig = chain / a.replicas;
+            const long long off = a.offsets[lig];
+            const int nl = (int)(a.offsets[lig + 1] - off);
+            const double *src = a.lig_xyzq + (off - a.atom_base) * 4;           // private copy of the start pose
+            for (int i = lane; i < nl; i += 32) {
+                s.q()[i] = src[4 * i + 3];
+                sm_store_pose(A, s, i, src[4 * i], src[4 * i + 1], src[4 * i + 2]);
+            }
+            if (lane == 0) {
+                if (nl & 1) store_lig_f32(s.lf(), nl, -kPadCoord, -kPadCoord, -kPadCoord, 0.f);   // q = 0 pad atom
+                c->nl = nl; c->status = 0; c->rep = (int)(chain - lig * a.replicas); c->bailed = 0;
+                c->local = local; c->step = 0; c->pos = 0; c->accepted = 0; c->downhill = 0; c->retries = 0;
+                c->cur_e = 0.0; c->start_e = 0.0; c->off = off;
+                c->stream_id = a.chain_id_base + (uint64_t)chain;
+                c->rec_ptr = nullptr; c->rec_len = 0;
+                if (a.recorded) {
+                    c->rec_ptr = a.recorded + (a.rec_offsets[chain] - a.rec_base);
+                    c->rec_len = a.rec_offsets[chain + 1] - a.rec_offsets[chain];
+                }
+            }
+            __syncwarp();
+            load_pos = -1;
+            status = 0;
+            stage = ST_START64;
+            if (sm_publish(A, c, 1, ST_START64)) return;                        // :118 in fp64
+            e = 0.0;
+        }
+        const int nl = c->nl;
+        if (stage == ST_START64) {
+            if (lane == 0) { c->start_e = e; c->cur_e = e; }
+            __syncwarp();
+            if (PRECISE) stage = ST_PROPOSE;
+            else {
+                stage = ST_START32;                                             // the chain's own currentEnergy, fp32-summed
+                flush_status();
+                if (sm_publish(A, c, 0, ST_START32)) return;
+                e = 0.0;
+            }
+        }
+        if (stage == ST_START32) {
+            if (lane == 0) c->cur_e = P.k_coulomb * e;
+            __syncwarp();
+            stage = ST_PROPOSE;
+        }
+        if (stage == ST_STEP) {                                                 // AcceptMove :141-149
+            const double new_e = PRECISE ? e : P.k_coulomb * e;
+            const double cur_e = c->cur_e;
+            uint64_t pos = c->pos;
+            bool acc;
+            const bool dh = new_e < cur_e;
+            if (dh) acc = true;
+            else {
+                const double x = -(new_e - cur_e) / P.temperature;
+                // exp(x) is exactly +0 below -746 and no uniform is < 0: reject without evaluating either; the draw
+                // is still consumed (:148).  (With K = 9e9 this is nearly every uphill move)
+                if (x < -746.0 && !c->rec_ptr) acc = false;
+                else {
+                    Stream st; st.seed = a.seed; st.id = c->stream_id; st.rec = c->rec_ptr; st.rec_len = c->rec_len;
+                    acc = st.draw(pos, status) < exp(x);
+                }
+                pos += 1;
+            }
+            if (!acc) for (int i = lane; i < nl; i += 32) { s.cx()[i] = s.px()[i]; s.cy()[i] = s.py()[i]; s.cz()[i] = s.pz()[i]; }  // :132
+            __syncwarp();
+            if (lane == 0) {
+                if (acc) c->cur_e = new_e;                                      // :129-130
+                c->pos = pos;
+                c->accepted += acc ? 1 : 0; c->downhill += dh ? 1 : 0;
+                if (a.out_trace) a.out_trace[c->local * a.steps + c->step] = acc ? 1 : 0;
+                c->step += 1;
+            }
+            __syncwarp();
+            stage = ST_PROPOSE;
+        }
+        if (stage == ST_PROPOSE) {
+            if (c->step >= a.steps || c->bailed) {
+                if (PRECISE) { e = c->cur_e; stage = ST_FINAL64; }
+                else {
+                    stage = ST_FINAL64;                                         // CalculateEnergy of the returned pose in fp64 (:61 / :104)
+                    flush_status();
+                    if (sm_publish(A, c, 1, ST_FINAL64)) return;
+                    e = 0.0;
+                }
+            } else {
+                Stream st; st.seed = a.seed; st.id = c->stream_id; st.rec = c->rec_ptr; st.rec_len = c->rec_len;
+                uint64_t pos = c->pos;
+                for (int i = lane; i < nl; i += 32) { s.px()[i] = s.cx()[i]; s.py()[i] = s.cy()[i]; s.pz()[i] = s.cz()[i]; }   // :121
+                __syncwarp();
+                long long rej = 0;
+                bool bail = false;
+                if (P.move_mode == 1) {
+                    // EXTENSION: rigid-body move, draws tx,ty,tz,ax,ay,az,theta (no reference row); no collision test
+                    const double tx = (st.draw(pos, status) - 0.5) * P.rigid_translation;
+                    const double ty = (st.draw(pos + 1, status) - 0.5) * P.rigid_translation;
+                    const double tz = (st.draw(pos + 2, status) - 0.5) * P.rigid_translation;
+                    double ax, ay, az, theta;
+                    draw_axis_angle(st, pos + 3, P.rigid_angle, status, ax, ay, az, theta);
+                    double gx = 0, gy = 0, gz = 0;
+                    for (int i = 0; i < nl; ++i) { gx += s.px()[i]; gy += s.py()[i]; gz += s.pz()[i]; }
+                    if (nl > 0) { gx /= (double)nl; gy /= (double)nl; gz /= (double)nl; }
+                    const double h = 0.5 * theta;
+                    double sh, w; sincos(h, &sh, &w);
+                    const double qx = sh * ax, qy = sh * ay, qz = sh * az;
+                    for (int i = lane; i < nl; i += 32) {
+                        const double vx = s.px()[i] - gx, vy = s.py()[i] - gy, vz = s.pz()[i] - gz;
+                        const double c1x = qy * vz - qz * vy, c1y = qz * vx - qx * vz, c1z = qx * vy - qy * vx;
+                        const double c2x = qy * c1z - qz * c1y, c2y = qz * c1x - qx * c1z, c2z = qx * c1y - qy * c1x;
+                        sm_store_pose(A, s, i, gx + (vx + 2.0 * (w * c1x + c2x)) + tx,
+                                      gy + (vy + 2.0 * (w * c1y + c2y)) + ty, gz + (vz + 2.0 * (w * c1z + c2z)) + tz);
+                    }
+                    pos += 7;
+                } else {
+                    const int draws_per_attempt = (P.rotate ? 4 : 0) + 3 * nl;
+                    const float m2_f32 = (float)(P.min_distance * P.min_distance);
+                    for (;;) {
+                        // REFERENCE move: JitterAndRotateLigand (:172-184) / JitterLigand (:154-167), in place
+                        double ax = 0, ay = 0, az = 0, cos_t = 1, sin_t = 0;
+                        uint64_t jpos = pos;
+                        if (P.rotate) {                                                   // RotateLigand :189-208
+                            double theta;
+                            draw_axis_angle(st, pos, P.max_angle, status, ax, ay, az, theta);
+                            sincos(theta, &sin_t, &cos_t);                               // :214-215
+                            jpos += 4;
+                        }
+                        for (int i = lane; i < nl; i += 32) {
+                            double x = s.cx()[i], y = s.cy()[i], z = s.cz()[i];
+                            if (P.rotate) rotate_atom(x, y, z, ax, ay, az, cos_t, sin_t);
+                            double u[3];
+                            st.draw3(jpos + 3ull * (uint64_t)i, u, status);
+                            x += (u[0] - 0.5) * P.jitter_width;                          // :176-178 / :158-160
+                            y += (u[1] - 0.5) * P.jitter_width;
+                            z += (u[2] - 0.5) * P.jitter_width;
+                            sm_store_pose(A, s, i, x, y, z);
+                        }
+                        pos += (uint64_t)draws_per_attempt;
+                        __syncwarp();
+                        // IsCollisionFree (:180 / :162): fp32 screen, exact fp64 test only inside the 2 % band
+                        const int code = warp_collision_screen(s, nl, m2_f32);
+                        bool collided = __any_sync(0xffffffffu, code & 2) != 0;
+                        if (!collided && __any_sync(0xffffffffu, code & 1))
+                            collided = __any_sync(0xffffffffu, warp_collision_exact(s, nl, P.min_distance)) != 0;
+                        if (!collided) break;
+                        ++rej;                              // retry on the already-moved atoms
+                        if (rej >= P.max_retries) { bail = true; break; }
+                    }
+                }
+                if (bail) {                                  // the reference would spin forever here
+                    status |= 1;
+                    for (int i = lane; i < nl; i += 32) { s.cx()[i] = s.px()[i]; s.cy()[i] = s.py()[i]; s.cz()[i] = s.pz()[i]; }
+                }
+                __syncwarp();
+                if (lane == 0) { c->pos = pos; c->retries += rej; c->bailed = bail ? 1 : 0; }
+                __syncwarp();
+                if (bail) continue;                         // -> ST_PROPOSE sees `bailed` and finalises
+                stage = ST_STEP;
+                flush_status();
+                if (sm_publish(A, c, PRECISE ? 1 : 0, ST_STEP)) return;         // :127
+                e = 0.0;
+                continue;
+            }
+        }
+        if (stage == ST_FINAL64) {
+            const double final_energy = e;
+            const long long out_atom = (long long)a.replicas * c->off + (long long)c->rep * nl - a.out_base;
+            double *dst = a.out_xyzq + out_atom * 4;
+            for (int i = lane; i < nl; i += 32) {
+                dst[4 * i] = s.cx()[i]; dst[4 * i + 1] = s.cy()[i]; dst[4 * i + 2] = s.cz()[i]; dst[4 * i + 3] = s.q()[i];
+            }
+            flush_status();
+            if (lane == 0) {
+                ChainStats cs;
+                cs.accepted = c->accepted; cs.downhill = c->downhill; cs.retries = c->retries; cs.steps = c->step;
+                cs.draws = (long long)c->pos; cs.status = c->status;
+                cs.final_energy = final_energy; cs.start_energy = c->start_e; cs.chain_energy = c->cur_e;
+                reinterpret_cast<ChainStats *>(a.out_stats)[c->local] = cs;
+            }
+            __syncwarp();
+            status = 0;
+            stage = ST_LOAD;                                // load_pos == -1: pull from the queue
+        }
+    }
+}
+
+template <bool PRECISE>
+__global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_constant__ SmArgs A) {
+    extern __shared__ __align__(16) unsigned char ddd_sm_smem[];
+    SmView V;
+    V.raw = ddd_sm_smem; V.slots = A.slots; V.cap = A.c.nl_cap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int K = A.slots;
+    if (threadIdx.x == 0) *V.live() = K;
+    if (threadIdx.x < K) V.ctl(threadIdx.x)->next_item = kSlotIdle;
+    __syncthreads();
+    if (warp < K) sm_serial_phase<PRECISE>(A, V, warp, (long long)warp * gridDim.x + blockIdx.x);
+
+    int rot = warp % K;
+    for (;;) {
+        bool did = false;
+        for (int j = 0; j < K; ++j) {
+            int sid = rot + j; if (sid >= K) sid -= K;
+            SmSlotCtl *c = V.ctl(sid);
+            if (ld_volatile(&c->next_item) >= A.n_items) continue;
+            int it = 0;
+            if (lane == 0) it = atomicAdd(&c->next_item, 1);
+            it = __shfl_sync(0xffffffffu, it, 0);
+            if (it >= A.n_items) continue;
+            __threadfence_block();
+            const SlotView s = V.slot(sid);
+            const int nl = c->nl;
+            const double sum = c->mode ? sm_item_f64(A, s, nl, it) : sm_item_f32(A, s.lf(), nl, it);
+            if (lane == 0) V.items(sid)[it] = sum;
+            __threadfence_block();
+            int d = 0;
+            if (lane == 0) d = atomicAdd(&c->done_items, 1);
+            d = __shfl_sync(0xffffffffu, d, 0);
+            if (d == A.n_items - 1) {                       // this warp completed the evaluation: it runs the serial phase
+                __threadfence_block();
+                sm_serial_phase<PRECISE>(A, V, sid, -1);
+            }
+            did = true;
+            rot = sid + 1; if (rot >= K) rot = 0;
+            break;
+        }
+        if (!did) {
+            if (ld_volatile(V.live()) == 0) break;
+            __nanosleep(100);
+        }
+    }
+}
+
+}  // namespace ddd

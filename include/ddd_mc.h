@@ -161,9 +161,15 @@ int ddd_randomize_pose_batch(const int64_t *offsets, double *lig_xyzq_inout, int
  * of the chain kernel on its launch stream; download copies final poses + stats to the host. */
 int    ddd_screen_create(const ddd_receptor *r, const int64_t *offsets, const double *lig_xyzq,
                          int64_t n_lig, int32_t replicas, uint64_t first_chain_id, ddd_screen **out);
-/* threads per chain CTA for subsequent runs: 32, 64, 128 or 256; 0 (default) = chosen from the chain count */
+/* Engine of the chain kernel for subsequent runs.  Default (both 0): the SM-persistent engine -- one 32-warp
+ * CTA per SM keeps `slots` chains resident and every warp takes pair-sum work items of any of them -- with the
+ * chains per SM chosen from the chain count.  set_chain_slots(k > 0) fixes k (1..16; clipped to what fits in
+ * shared memory).  set_chain_threads(32|64|128|256) selects the one-CTA-per-chain engine with that CTA width;
+ * set_chain_threads(0) returns to the default.  Results do not depend on the engine in F64 precision. */
 int    ddd_screen_set_chain_threads(ddd_screen *s, int32_t threads);
-int32_t ddd_screen_chain_threads(const ddd_screen *s);   /* width used by the last run */
+int32_t ddd_screen_chain_threads(const ddd_screen *s);   /* CTA width used by the last run (1024: SM-persistent) */
+int    ddd_screen_set_chain_slots(ddd_screen *s, int32_t slots);
+int32_t ddd_screen_chain_slots(const ddd_screen *s);     /* chains per SM of the last run (0: one CTA per chain) */
 int    ddd_screen_run(ddd_screen *s, int64_t steps_per_chain, int32_t rotate, double temperature,
                       const ddd_params *p, uint64_t seed);
 int    ddd_screen_sync(ddd_screen *s);
