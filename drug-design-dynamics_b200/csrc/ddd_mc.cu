@@ -335,10 +335,12 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
             A.slots = std::max(1, std::min(k_want, k_fit));
             A.queue = d.d_queue; A.n_local = n_local; A.first_dynamic = (long long)grid * A.slots;
             const int n = (int)s->rec->n;
-            A.tile_a = (n + 127) / 128 >= 24 ? 4 : 1;
-            A.n_wt = (n + 32 * A.tile_a - 1) / (32 * A.tile_a);
-            A.chunk = (A.n_wt + kSmMaxItems - 1) / kSmMaxItems;
-            A.n_items = A.chunk ? (A.n_wt + A.chunk - 1) / A.chunk : 0;
+            A.n_units = (n + 31) / 32;
+            // items per evaluation: a multiple of the warp count, each item <= 16 units (512 receptor atoms) when possible
+            int rounds = std::max(1, (A.n_units + kSmWarps * 16 - 1) / (kSmWarps * 16));
+            rounds = std::min(rounds, kSmMaxItems / kSmWarps);
+            A.upi = std::max(1, (A.n_units + kSmWarps * rounds - 1) / (kSmWarps * rounds));
+            A.n_items = (A.n_units + A.upi - 1) / A.upi;
             const size_t smem = sm_smem_bytes(d.nl_cap, A.slots);
             d.threads = kSmThreads; d.slots = A.slots;
             CUDA_TRY(cudaMemsetAsync(d.d_queue, 0, sizeof(int), dev.stream));

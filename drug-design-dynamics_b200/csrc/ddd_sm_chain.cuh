@@ -21,11 +21,30 @@
 
 namespace ddd {
 
-constexpr int kSmThreads  = 1024;
+#ifndef DDD_SM_THREADS
+#define DDD_SM_THREADS 512
+#endif
+constexpr int kSmThreads  = DDD_SM_THREADS;
 constexpr int kSmWarps    = kSmThreads / 32;
 constexpr int kSmMaxSlots = 16;
 constexpr int kSmMaxItems = 128;            // work items per energy evaluation (item sums kept per slot)
 constexpr int kSlotIdle   = 0x3fffffff;     // next_item of a slot that has nothing to hand out
+constexpr int kUbufDraws  = 256;            // jitter uniforms staged per proposal attempt (ligands up to 84 atoms)
+constexpr int kNearCap    = 128;            // near-pair list entries per slot
+#ifndef DDD_NEAR_MARGIN
+#define DDD_NEAR_MARGIN 0.9
+#endif
+#ifndef DDD_SM_SPIN
+#define DDD_SM_SPIN 1
+#endif
+#ifndef DDD_SM_PRIO
+#define DDD_SM_PRIO 1
+#endif
+#ifndef DDD_SM_UNROLL
+#define DDD_SM_UNROLL 1
+#endif
+constexpr int kSmUnroll = DDD_SM_UNROLL;
+constexpr double kNearMargin = DDD_NEAR_MARGIN;         // a near-pair list holds every ligand pair closer than MINDISTANCE + this
 
 enum : int { ST_START64 = 0, ST_START32 = 1, ST_STEP = 2, ST_FINAL64 = 3, ST_PROPOSE = 4, ST_LOAD = 5 };
 
@@ -40,8 +59,12 @@ struct __align__(16) SmSlotCtl {
     unsigned long long stream_id;
     const double *rec_ptr;                            // recorded stream (nullable)
     long long rec_len;
+    int base_n;                                       // near-pair list of the current pose: -1 = not built, > kNearCap = overflow
+    int list_cnt;                                     // append counter while a list is being built
+    int pad0, pad1;
 };
-static_assert(sizeof(SmSlotCtl) == 128, "SmSlotCtl is laid out as one 128-byte block");
+static_assert(sizeof(SmSlotCtl) == 144, "SmSlotCtl is laid out as nine 16-byte words");
+constexpr int kSlotFixedBytes = (int)sizeof(SmSlotCtl) + kSmMaxItems * 8 + kUbufDraws * 8 + 2 * kNearCap * 4;
 
 struct SmArgs {
     ChainArgs c;
@@ -49,45 +72,72 @@ struct SmArgs {
     long long n_local;       // chains of this launch
     long long first_dynamic; // gridDim.x * slots: chains below are assigned statically (slot s of CTA b: s*grid + b)
     int slots;               // K
-    int tile_a;              // receptor atoms per lane per warp tile: 4 (production) or 1 (small receptors)
-    int n_wt;                // warp tiles of 32*tile_a atoms
-    int chunk, n_items;      // warp tiles per item; items per energy evaluation (<= kSmMaxItems)
+    int n_units;             // receptor units of 32 atoms (one per lane)
+    int upi, n_items;        // units per item; items per energy evaluation (<= kSmMaxItems).  An item is a run of
+                             // consecutive units, cut so that the item count is a multiple of the CTA's warp count:
+                             // a chain that has the SM to itself finishes an evaluation in whole rounds
 };
 
 __host__ __device__ inline size_t sm_smem_bytes(int nl_cap, int slots) {
-    return 16 + (size_t)slots * (sizeof(SmSlotCtl) + kSmMaxItems * sizeof(double) + (size_t)nl_cap * (7 * sizeof(double) + sizeof(float4)));
+    return 16 + (size_t)slots * (kSlotFixedBytes + (size_t)nl_cap * (7 * sizeof(double) + sizeof(float4)));
 }
 
-// Views into the CTA's shared memory: [live 16][ctl K*128][items K*kSmMaxItems*8][slot poses K * cap * 72]
+// Views into the CTA's shared memory: [live 16] then per slot [ctl 144][item sums][uniform staging][base list][dyn list]
+// [pose: 56-byte fp64 atom records (cap), then lf (16*cap)]
 struct SlotView {
-    unsigned char *pose;     // this slot's pose block: lf (16*cap) then cx cy cz px py pz q (8*cap each)
+    unsigned char *blk;      // this slot's block
+    unsigned char *pose;     // its pose part
     int cap;
-    __device__ __forceinline__ float4 *lf() const { return reinterpret_cast<float4 *>(pose); }
-    __device__ __forceinline__ double *base() const { return reinterpret_cast<double *>(pose) + 2 * cap; }
-    __device__ __forceinline__ double *cx() const { return base(); }
-    __device__ __forceinline__ double *cy() const { return base() + cap; }
-    __device__ __forceinline__ double *cz() const { return base() + 2 * cap; }
-    __device__ __forceinline__ double *px() const { return base() + 3 * cap; }
-    __device__ __forceinline__ double *py() const { return base() + 4 * cap; }
-    __device__ __forceinline__ double *pz() const { return base() + 5 * cap; }
-    __device__ __forceinline__ double *q() const { return base() + 6 * cap; }
+    __device__ __forceinline__ double *ubuf() const { return reinterpret_cast<double *>(blk + sizeof(SmSlotCtl) + kSmMaxItems * 8); }
+    __device__ __forceinline__ ushort2 *base_list() const { return reinterpret_cast<ushort2 *>(blk + sizeof(SmSlotCtl) + kSmMaxItems * 8 + kUbufDraws * 8); }
+    __device__ __forceinline__ ushort2 *dyn_list() const { return base_list() + kNearCap; }
+    // fp64 pose, one 56-byte record per atom {cx cy cz px py pz q}: every field sits at a compile-time offset from
+    // pose + 56 * i whatever the capacity (half-warp accesses of stride 56 B are bank-conflict free); the pair-packed
+    // fp32 pose follows at pose + 56 * cap.
+    __device__ __forceinline__ double &f64(int i, int field) const { return *reinterpret_cast<double *>(pose + (size_t)i * 56 + field * 8); }
+    __device__ __forceinline__ double &cx(int i) const { return f64(i, 0); }
+    __device__ __forceinline__ double &cy(int i) const { return f64(i, 1); }
+    __device__ __forceinline__ double &cz(int i) const { return f64(i, 2); }
+    __device__ __forceinline__ double &px(int i) const { return f64(i, 3); }
+    __device__ __forceinline__ double &py(int i) const { return f64(i, 4); }
+    __device__ __forceinline__ double &pz(int i) const { return f64(i, 5); }
+    __device__ __forceinline__ double &q(int i) const { return f64(i, 6); }
+    __device__ __forceinline__ float4 *lf() const { return reinterpret_cast<float4 *>(pose + (size_t)cap * 56); }
 };
 
 struct SmView {
     unsigned char *raw;
     int slots, cap;
     __device__ __forceinline__ int *live() const { return reinterpret_cast<int *>(raw); }
-    __device__ __forceinline__ SmSlotCtl *ctl(int s) const { return reinterpret_cast<SmSlotCtl *>(raw + 16) + s; }
-    __device__ __forceinline__ double *items(int s) const {
-        return reinterpret_cast<double *>(raw + 16 + (size_t)slots * sizeof(SmSlotCtl)) + s * kSmMaxItems;
-    }
+    __device__ __forceinline__ int *epoch() const { return reinterpret_cast<int *>(raw) + 1; }
+    __device__ __forceinline__ unsigned long long *mbar() const { return reinterpret_cast<unsigned long long *>(raw + 8); }
+    __device__ __forceinline__ unsigned char *block(int s) const { return raw + 16 + (size_t)s * (kSlotFixedBytes + cap * 72); }
+    __device__ __forceinline__ SmSlotCtl *ctl(int s) const { return reinterpret_cast<SmSlotCtl *>(block(s)); }
+    __device__ __forceinline__ double *items(int s) const { return reinterpret_cast<double *>(block(s) + sizeof(SmSlotCtl)); }
     __device__ __forceinline__ SlotView slot(int s) const {
         SlotView v;
         v.cap = cap;
-        v.pose = raw + 16 + (size_t)slots * (sizeof(SmSlotCtl) + kSmMaxItems * sizeof(double)) + (size_t)s * cap * 72;
+        v.blk = block(s);
+        v.pose = v.blk + kSlotFixedBytes;
         return v;
     }
 };
+
+// Idle warps do not spin (31 polling warps slow the one warp that is in a serial phase): they block on an mbarrier
+// whose phase flips whenever work is published or the last slot dies.  `epoch` counts the flips; a warp reads it BEFORE
+// it looks for work and then waits for the phase of that parity, so a publish in between wakes it at once; the rare
+// double flip inside that window is bounded by the wait's time limit.
+__device__ __forceinline__ void wake_init(unsigned long long *mbar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((unsigned)__cvta_generic_to_shared(mbar)) : "memory");
+}
+__device__ __forceinline__ void wake_all(int *epoch, unsigned long long *mbar) {     // one lane
+    atomicAdd(epoch, 1);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"((unsigned)__cvta_generic_to_shared(mbar)) : "memory");
+}
+__device__ __forceinline__ void wake_wait(unsigned long long *mbar, int parity, unsigned ns) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t}"
+                 :: "r"((unsigned)__cvta_generic_to_shared(mbar)), "r"(parity), "r"(ns) : "memory");
+}
 
 __device__ __forceinline__ int ld_volatile(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 __device__ __forceinline__ void st_volatile(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
@@ -96,30 +146,28 @@ __device__ __forceinline__ void st_volatile(int *p, int v) { *reinterpret_cast<v
 __device__ __forceinline__ double sm_item_f32(const SmArgs &A, const float4 *lf, int nl, int it) {
     const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
     const int n_pairs = (nl + 1) >> 1;
-    const int t0 = it * A.chunk, t1 = min(t0 + A.chunk, A.n_wt);
+    int u = it * A.upi;
+    const int u1 = min(u + A.upi, A.n_units);
+    const float rmax = A.c.prm.rinv_max;
     double acc = 0.0;
-    if (A.tile_a == 4) {
-        for (int t = t0; t < t1; ++t) acc += (double)warp_tile_sum_f32<4>(A.c.rec.f32, t * 128, lf2, n_pairs, A.c.prm.rinv_max);
-    } else {
-        for (int t = t0; t < t1; ++t) acc += (double)warp_tile_sum_f32<1>(A.c.rec.f32, t * 32, lf2, n_pairs, A.c.prm.rinv_max);
-    }
+    for (; u + 4 <= u1; u += 4) acc += (double)warp_tile_sum_f32<4>(A.c.rec.f32, u * 32, lf2, n_pairs, rmax);
+    if (u + 2 <= u1) { acc += (double)warp_tile_sum_f32<2>(A.c.rec.f32, u * 32, lf2, n_pairs, rmax); u += 2; }
+    if (u < u1) acc += (double)warp_tile_sum_f32<1>(A.c.rec.f32, u * 32, lf2, n_pairs, rmax);
     return warp_sum(acc);
 }
 
 // the reference's per-term fp64 arithmetic (:253-258) for the receptor atoms of one item
 __device__ __forceinline__ double sm_item_f64(const SmArgs &A, const SlotView &s, int nl, int it) {
-    const int atoms_per_tile = 32 * A.tile_a;
-    const int p0 = it * A.chunk * atoms_per_tile, p1 = min((it + 1) * A.chunk * atoms_per_tile, A.c.rec.n);
+    const int p0 = it * A.upi * 32, p1 = min((it + 1) * A.upi * 32, A.c.rec.n);
     const double K = A.c.prm.k_coulomb, clampd = A.c.prm.clamp_distance;
-    const double *lx = s.cx(), *ly = s.cy(), *lz = s.cz(), *lq = s.q();
     double e = 0.0;
     for (int p = p0 + (int)(threadIdx.x & 31); p < p1; p += 32) {
         const Atom64 P = A.c.rec.f64[p];
         for (int l = 0; l < nl; ++l) {
-            const double ddx = P.x - lx[l], ddy = P.y - ly[l], ddz = P.z - lz[l];
+            const double ddx = P.x - s.cx(l), ddy = P.y - s.cy(l), ddz = P.z - s.cz(l);
             double d = sqrt(ddx * ddx + ddy * ddy + ddz * ddz);          // :253 (Pow(x,2) == x*x)
             if (d < clampd) d = clampd;                                   // :255-257
-            e += K * (P.q * lq[l]) / d;                                   // :258
+            e += K * (P.q * s.q(l)) / d;                                  // :258
         }
     }
     return warp_sum(e);
@@ -127,8 +175,8 @@ __device__ __forceinline__ double sm_item_f64(const SmArgs &A, const SlotView &s
 
 // ------------------------------------------------------------------ one-warp proposal helpers
 __device__ __forceinline__ void sm_store_pose(const SmArgs &A, const SlotView &s, int i, double x, double y, double z) {
-    s.cx()[i] = x; s.cy()[i] = y; s.cz()[i] = z;
-    store_lig_f32(s.lf(), i, (float)(x - A.c.rec.cx), (float)(y - A.c.rec.cy), (float)(z - A.c.rec.cz), (float)s.q()[i]);
+    s.cx(i) = x; s.cy(i) = y; s.cz(i) = z;
+    store_lig_f32(s.lf(), i, (float)(x - A.c.rec.cx), (float)(y - A.c.rec.cy), (float)(z - A.c.rec.cz), (float)s.q(i));
 }
 
 // fp32 screen in front of IsCollisionFree, one warp: atoms in rows of 32 lanes; a short last row gives every atom
@@ -176,7 +224,7 @@ __device__ __forceinline__ bool warp_collision_exact(const SlotView &s, int nl, 
         int i, m;
         if (w < n_full) { m = w / nl + 1; i = w - (m - 1) * nl; } else { i = w - n_full; m = nl / 2; }
         int j = i + m; if (j >= nl) j -= nl;
-        const double dx = s.cx()[i] - s.cx()[j], dy = s.cy()[i] - s.cy()[j], dz = s.cz()[i] - s.cz()[j];
+        const double dx = s.cx(i) - s.cx(j), dy = s.cy(i) - s.cy(j), dz = s.cz(i) - s.cz(j);
         const double d2 = dx * dx + dy * dy + dz * dz;
         if (d2 < m2_lo) hit = true;
         else if (d2 < m2_hi) hit |= (sqrt(d2) < min_distance);              // :235-236
@@ -184,13 +232,72 @@ __device__ __forceinline__ bool warp_collision_exact(const SlotView &s, int nl, 
     return hit;
 }
 
+// fp32 pose of every atom from the fp64 master copy (the pair-packed layout the pair loop and the list scan read)
+__device__ __forceinline__ void warp_write_lf(const SmArgs &A, const SlotView &s, int nl) {
+    for (int i = threadIdx.x & 31; i < nl; i += 32)
+        store_lig_f32(s.lf(), i, (float)(s.cx(i) - A.c.rec.cx), (float)(s.cy(i) - A.c.rec.cy), (float)(s.cz(i) - A.c.rec.cz), (float)s.q(i));
+    __syncwarp();
+}
+
+// Near-pair list of the pose in lf: every pair (i < j) that is closer than sqrt(r2) -- conservatively: the fp32 test
+// carries the coordinate-rounding slack, so a listed pair may be slightly farther, never the reverse.  A pair that is
+// NOT listed cannot come within MINDISTANCE during the next k_max attempts (each attempt moves a pair distance by at
+// most jitter_width * sqrt(3); RotateLigand is rigid), so IsCollisionFree (:229-242) for those attempts only has to
+// look at the listed pairs -- with the reference's own fp64 test.  Returns the pair count (> kNearCap: overflow).
+__device__ __forceinline__ int warp_build_near_list(const SlotView &s, SmSlotCtl *c, ushort2 *list, int nl, float r2) {
+    const int lane = threadIdx.x & 31;
+    const int n_pairs = (nl + 1) >> 1;
+    const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(s.lf());
+    const float *lff = reinterpret_cast<const float *>(s.lf());
+    if (lane == 0) c->list_cnt = 0;
+    __syncwarp();
+    for (int b = 0; b < nl; b += 32) {
+        const int rem = nl - b;
+        int i, k0, ks;
+        if (rem >= 32) { i = b + lane; k0 = 0; ks = 1; }
+        else { const int g = 32 / rem; const int grp = lane / rem; i = grp < g ? b + (lane - grp * rem) : nl; k0 = grp; ks = g; }
+        if (i >= nl) continue;
+        const float *mine = lff + 8 * (i >> 1) + (i & 1);
+        const float xi = -mine[0], yi = -mine[2], zi = -mine[4];
+        const float lim = r2 * 1.001f + 4e-6f * (fabsf(xi) + fabsf(yi) + fabsf(zi) + 1.0f);
+        const f32x2 ax = pack2(xi, xi), ay = pack2(yi, yi), az = pack2(zi, zi);
+#pragma unroll 2
+        for (int k = k0; k < n_pairs; k += ks) {
+            const ulonglong2 Lxy = lf2[2 * k], Lzq = lf2[2 * k + 1];
+            const f32x2 dx = add2(ax, Lxy.x), dy = add2(ay, Lxy.y), dz = add2(az, Lzq.x);
+            const f32x2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+            float d2a, d2b;
+            unpack2(d2, d2a, d2b);
+            const int j0 = 2 * k, j1 = 2 * k + 1;
+            if (d2a < lim && j0 > i) { const int idx = atomicAdd(&c->list_cnt, 1); if (idx < kNearCap) list[idx] = make_ushort2((unsigned short)i, (unsigned short)j0); }
+            if (d2b < lim && j1 > i && j1 < nl) { const int idx = atomicAdd(&c->list_cnt, 1); if (idx < kNearCap) list[idx] = make_ushort2((unsigned short)i, (unsigned short)j1); }
+        }
+    }
+    __syncwarp();
+    return c->list_cnt;
+}
+
+// IsCollisionFree (:229-242) restricted to the listed pairs, in the reference's fp64 arithmetic; true = some pair collides
+__device__ __forceinline__ bool warp_check_near_list(const SlotView &s, const ushort2 *list, int n, double min_distance) {
+    const double m2 = min_distance * min_distance, m2_lo = m2 * (1.0 - 1e-9), m2_hi = m2 * (1.0 + 1e-9);
+    bool hit = false;
+    for (int e = threadIdx.x & 31; e < n; e += 32) {
+        const ushort2 pr = list[e];
+        const double dx = s.cx(pr.x) - s.cx(pr.y), dy = s.cy(pr.x) - s.cy(pr.y), dz = s.cz(pr.x) - s.cz(pr.y);
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 < m2_lo) hit = true;
+        else if (d2 < m2_hi) hit |= (sqrt(d2) < min_distance);              // :235-236
+    }
+    return __any_sync(0xffffffffu, hit) != 0;
+}
+
 // hand the slot's pose out for an energy evaluation; false when the receptor has no atoms (nothing to hand out)
-__device__ __forceinline__ bool sm_publish(const SmArgs &A, SmSlotCtl *c, int mode, int stage) {
+__device__ __forceinline__ bool sm_publish(const SmArgs &A, const SmView &V, SmSlotCtl *c, int mode, int stage) {
     if ((threadIdx.x & 31) == 0) { c->mode = mode; c->stage = stage; c->done_items = 0; }
     if (A.n_items == 0) return false;
     __threadfence_block();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) st_volatile(&c->next_item, 0);
+    if ((threadIdx.x & 31) == 0) { st_volatile(&c->next_item, 0); __threadfence_block(); wake_all(V.epoch(), V.mbar()); }
     return true;
 }
 
@@ -229,7 +336,7 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 load_pos = A.first_dynamic + (long long)t;
             }
             if (load_pos >= A.n_local) {                                        // nothing left: the slot dies
-                if (lane == 0) { st_volatile(&c->next_item, kSlotIdle); atomicSub(V.live(), 1); }
+                if (lane == 0) { st_volatile(&c->next_item, kSlotIdle); atomicSub(V.live(), 1); __threadfence_block(); wake_all(V.epoch(), V.mbar()); }
                 return;
             }
             const long long local = a.order ? (long long)a.order[load_pos] : load_pos;
@@ -239,14 +346,14 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
             const int nl = (int)(a.offsets[lig + 1] - off);
             const double *src = a.lig_xyzq + (off - a.atom_base) * 4;           // private copy of the start pose
             for (int i = lane; i < nl; i += 32) {
-                s.q()[i] = src[4 * i + 3];
+                s.q(i) = src[4 * i + 3];
                 sm_store_pose(A, s, i, src[4 * i], src[4 * i + 1], src[4 * i + 2]);
             }
             if (lane == 0) {
                 if (nl & 1) store_lig_f32(s.lf(), nl, -kPadCoord, -kPadCoord, -kPadCoord, 0.f);   // q = 0 pad atom
                 c->nl = nl; c->status = 0; c->rep = (int)(chain - lig * a.replicas); c->bailed = 0;
                 c->local = local; c->step = 0; c->pos = 0; c->accepted = 0; c->downhill = 0; c->retries = 0;
-                c->cur_e = 0.0; c->start_e = 0.0; c->off = off;
+                c->cur_e = 0.0; c->start_e = 0.0; c->off = off; c->base_n = -1; c->list_cnt = 0;
                 c->stream_id = a.chain_id_base + (uint64_t)chain;
                 c->rec_ptr = nullptr; c->rec_len = 0;
                 if (a.recorded) {
@@ -258,7 +365,7 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
             load_pos = -1;
             status = 0;
             stage = ST_START64;
-            if (sm_publish(A, c, 1, ST_START64)) return;                        // :118 in fp64
+            if (sm_publish(A, V, c, 1, ST_START64)) return;                        // :118 in fp64
             e = 0.0;
         }
         const int nl = c->nl;
@@ -269,7 +376,7 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
             else {
                 stage = ST_START32;                                             // the chain's own currentEnergy, fp32-summed
                 flush_status();
-                if (sm_publish(A, c, 0, ST_START32)) return;
+                if (sm_publish(A, V, c, 0, ST_START32)) return;
                 e = 0.0;
             }
         }
@@ -296,10 +403,10 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 }
                 pos += 1;
             }
-            if (!acc) for (int i = lane; i < nl; i += 32) { s.cx()[i] = s.px()[i]; s.cy()[i] = s.py()[i]; s.cz()[i] = s.pz()[i]; }  // :132
+            if (!acc) for (int i = lane; i < nl; i += 32) { s.cx(i) = s.px(i); s.cy(i) = s.py(i); s.cz(i) = s.pz(i); }  // :132
             __syncwarp();
             if (lane == 0) {
-                if (acc) c->cur_e = new_e;                                      // :129-130
+                if (acc) { c->cur_e = new_e; c->base_n = -1; }                  // :129-130; the near-pair list described the old pose
                 c->pos = pos;
                 c->accepted += acc ? 1 : 0; c->downhill += dh ? 1 : 0;
                 if (a.out_trace) a.out_trace[c->local * a.steps + c->step] = acc ? 1 : 0;
@@ -314,13 +421,13 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 else {
                     stage = ST_FINAL64;                                         // CalculateEnergy of the returned pose in fp64 (:61 / :104)
                     flush_status();
-                    if (sm_publish(A, c, 1, ST_FINAL64)) return;
+                    if (sm_publish(A, V, c, 1, ST_FINAL64)) return;
                     e = 0.0;
                 }
             } else {
                 Stream st; st.seed = a.seed; st.id = c->stream_id; st.rec = c->rec_ptr; st.rec_len = c->rec_len;
                 uint64_t pos = c->pos;
-                for (int i = lane; i < nl; i += 32) { s.px()[i] = s.cx()[i]; s.py()[i] = s.cy()[i]; s.pz()[i] = s.cz()[i]; }   // :121
+                for (int i = lane; i < nl; i += 32) { s.px(i) = s.cx(i); s.py(i) = s.cy(i); s.pz(i) = s.cz(i); }   // :121
                 __syncwarp();
                 long long rej = 0;
                 bool bail = false;
@@ -332,13 +439,13 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                     double ax, ay, az, theta;
                     draw_axis_angle(st, pos + 3, P.rigid_angle, status, ax, ay, az, theta);
                     double gx = 0, gy = 0, gz = 0;
-                    for (int i = 0; i < nl; ++i) { gx += s.px()[i]; gy += s.py()[i]; gz += s.pz()[i]; }
+                    for (int i = 0; i < nl; ++i) { gx += s.px(i); gy += s.py(i); gz += s.pz(i); }
                     if (nl > 0) { gx /= (double)nl; gy /= (double)nl; gz /= (double)nl; }
                     const double h = 0.5 * theta;
                     double sh, w; sincos(h, &sh, &w);
                     const double qx = sh * ax, qy = sh * ay, qz = sh * az;
                     for (int i = lane; i < nl; i += 32) {
-                        const double vx = s.px()[i] - gx, vy = s.py()[i] - gy, vz = s.pz()[i] - gz;
+                        const double vx = s.px(i) - gx, vy = s.py(i) - gy, vz = s.pz(i) - gz;
                         const double c1x = qy * vz - qz * vy, c1y = qz * vx - qx * vz, c1z = qx * vy - qy * vx;
                         const double c2x = qy * c1z - qz * c1y, c2y = qz * c1x - qx * c1z, c2z = qx * c1y - qy * c1x;
                         sm_store_pose(A, s, i, gx + (vx + 2.0 * (w * c1x + c2x)) + tx,
@@ -346,43 +453,103 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                     }
                     pos += 7;
                 } else {
-                    const int draws_per_attempt = (P.rotate ? 4 : 0) + 3 * nl;
-                    const float m2_f32 = (float)(P.min_distance * P.min_distance);
+                    // REFERENCE move: JitterAndRotateLigand (:172-184) / JitterLigand (:154-167), in place, retried
+                    // cumulatively until IsCollisionFree (:180 / :162).  Latency is what matters here (late in a chain the
+                    // jitter piles atoms up at MINDISTANCE and a step needs tens of attempts), so:
+                    //  * axis / angle / sincos of up to 32 FUTURE attempts are computed at once, one attempt per lane
+                    //    (their stream positions are known in advance); an attempt fetches its own by shuffle;
+                    //  * the jitter uniforms of an attempt are produced one Philox block per lane and staged in shared memory;
+                    //  * the collision test looks only at the near-pair list of the step's start pose (or of a later
+                    //    attempt's pose once the list's distance budget is spent); the fp32 pose is written only for
+                    //    the attempt that passes.
+                    const int dpa = (P.rotate ? 4 : 0) + 3 * nl;                         // draws per attempt
+                    const uint64_t pos0 = pos;
+                    const double pair_step = fabs(P.jitter_width) * 1.7320508075688774;   // max change of a pair distance per attempt
+                    const int k_max = pair_step > 0.0 ? (int)fmin((kNearMargin - 1e-6) / (pair_step * (1.0 + 1e-9)), 1.0e6) : 1000000;
+                    const float r_near = (float)(P.min_distance + kNearMargin), r2_near = r_near * r_near;
+                    const bool use_ubuf = !st.rec && 3 * nl + 2 <= kUbufDraws;
+                    int base_n = c->base_n;
+                    if (base_n < 0) {                                                     // first step after a load or an accepted move
+                        warp_write_lf(A, s, nl);
+                        base_n = warp_build_near_list(s, c, s.base_list(), nl, r2_near);
+                        if (lane == 0) c->base_n = base_n;
+                    }
+                    int dyn_n = -1, dyn_kb = 0, kb = 0, bstat = 0;
+                    bool lists_ok = true;
+                    double bax = 0, bay = 0, baz = 0, bsin = 0, bcos = 1;                 // this lane's attempt of the batch
+                    int k = 0;                                                            // attempts made in this step
                     for (;;) {
-                        // REFERENCE move: JitterAndRotateLigand (:172-184) / JitterLigand (:154-167), in place
+                        ++k;
+                        const uint64_t apos = pos0 + (uint64_t)(k - 1) * (uint64_t)dpa;
                         double ax = 0, ay = 0, az = 0, cos_t = 1, sin_t = 0;
-                        uint64_t jpos = pos;
+                        uint64_t jpos = apos;
                         if (P.rotate) {                                                   // RotateLigand :189-208
-                            double theta;
-                            draw_axis_angle(st, pos, P.max_angle, status, ax, ay, az, theta);
-                            sincos(theta, &sin_t, &cos_t);                               // :214-215
+                            int j = (k - 1) - kb;
+                            if (k == 1 || j == 32) {
+                                kb = k - 1; j = 0; bstat = 0;
+                                double theta;
+                                draw_axis_angle(st, pos0 + (uint64_t)(kb + lane) * (uint64_t)dpa, P.max_angle, bstat, bax, bay, baz, theta);
+                                sincos(theta, &bsin, &bcos);                             // :214-215
+                            }
+                            ax = __shfl_sync(0xffffffffu, bax, j); ay = __shfl_sync(0xffffffffu, bay, j); az = __shfl_sync(0xffffffffu, baz, j);
+                            sin_t = __shfl_sync(0xffffffffu, bsin, j); cos_t = __shfl_sync(0xffffffffu, bcos, j);
+                            status |= __shfl_sync(0xffffffffu, bstat, j);
+                            if (ax == 0.0 && ay == 0.0 && az == 0.0) lists_ok = false;    // Normalize no-op (datatypes.go:33-40): not a rotation
                             jpos += 4;
                         }
+                        const uint64_t b_first = jpos >> 1;
+                        if (use_ubuf && nl > 0) {
+                            const int nb = (int)(((jpos + 3ull * (uint64_t)nl - 1) >> 1) - b_first) + 1;
+                            double2 *ub = reinterpret_cast<double2 *>(s.ubuf());
+#pragma unroll kSmUnroll
+                            for (int b = lane; b < nb; b += 32) {
+                                const uint64_t blk = b_first + (uint64_t)b;
+                                uint32_t o[4];
+                                philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)st.id, (uint32_t)(st.id >> 32),
+                                              (uint32_t)st.seed, (uint32_t)(st.seed >> 32), o);
+                                ub[b] = make_double2(u53(o[0], o[1]), u53(o[2], o[3]));
+                            }
+                            __syncwarp();
+                        }
+                        const double *uu = s.ubuf() + (jpos - 2 * b_first);
+#pragma unroll kSmUnroll
                         for (int i = lane; i < nl; i += 32) {
-                            double x = s.cx()[i], y = s.cy()[i], z = s.cz()[i];
+                            double x = s.cx(i), y = s.cy(i), z = s.cz(i);
                             if (P.rotate) rotate_atom(x, y, z, ax, ay, az, cos_t, sin_t);
                             double u[3];
-                            st.draw3(jpos + 3ull * (uint64_t)i, u, status);
+                            if (use_ubuf) { u[0] = uu[3 * i]; u[1] = uu[3 * i + 1]; u[2] = uu[3 * i + 2]; }
+                            else st.draw3(jpos + 3ull * (uint64_t)i, u, status);
                             x += (u[0] - 0.5) * P.jitter_width;                          // :176-178 / :158-160
                             y += (u[1] - 0.5) * P.jitter_width;
                             z += (u[2] - 0.5) * P.jitter_width;
-                            sm_store_pose(A, s, i, x, y, z);
+                            s.cx(i) = x; s.cy(i) = y; s.cz(i) = z;
                         }
-                        pos += (uint64_t)draws_per_attempt;
                         __syncwarp();
-                        // IsCollisionFree (:180 / :162): fp32 screen, exact fp64 test only inside the 2 % band
-                        const int code = warp_collision_screen(s, nl, m2_f32);
-                        bool collided = __any_sync(0xffffffffu, code & 2) != 0;
-                        if (!collided && __any_sync(0xffffffffu, code & 1))
-                            collided = __any_sync(0xffffffffu, warp_collision_exact(s, nl, P.min_distance)) != 0;
-                        if (!collided) break;
+                        bool collided, lf_fresh = false;
+                        if (lists_ok && base_n <= kNearCap && k <= k_max) collided = warp_check_near_list(s, s.base_list(), base_n, P.min_distance);
+                        else if (lists_ok && dyn_n >= 0 && k - dyn_kb <= k_max) collided = warp_check_near_list(s, s.dyn_list(), dyn_n, P.min_distance);
+                        else {
+                            warp_write_lf(A, s, nl);
+                            lf_fresh = true;
+                            const int n = warp_build_near_list(s, c, s.dyn_list(), nl, r2_near);
+                            if (n <= kNearCap) { dyn_n = n; dyn_kb = k; collided = warp_check_near_list(s, s.dyn_list(), n, P.min_distance); }
+                            else {                                                        // list overflow: screen every pair
+                                dyn_n = -1;
+                                const int code = warp_collision_screen(s, nl, (float)(P.min_distance * P.min_distance));
+                                collided = __any_sync(0xffffffffu, code & 2) != 0;
+                                if (!collided && __any_sync(0xffffffffu, code & 1))
+                                    collided = __any_sync(0xffffffffu, warp_collision_exact(s, nl, P.min_distance)) != 0;
+                            }
+                        }
+                        if (!collided) { if (!lf_fresh) warp_write_lf(A, s, nl); break; }
                         ++rej;                              // retry on the already-moved atoms
                         if (rej >= P.max_retries) { bail = true; break; }
                     }
+                    pos = pos0 + (uint64_t)k * (uint64_t)dpa;
                 }
                 if (bail) {                                  // the reference would spin forever here
                     status |= 1;
-                    for (int i = lane; i < nl; i += 32) { s.cx()[i] = s.px()[i]; s.cy()[i] = s.py()[i]; s.cz()[i] = s.pz()[i]; }
+                    for (int i = lane; i < nl; i += 32) { s.cx(i) = s.px(i); s.cy(i) = s.py(i); s.cz(i) = s.pz(i); }
                 }
                 __syncwarp();
                 if (lane == 0) { c->pos = pos; c->retries += rej; c->bailed = bail ? 1 : 0; }
@@ -390,7 +557,7 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 if (bail) continue;                         // -> ST_PROPOSE sees `bailed` and finalises
                 stage = ST_STEP;
                 flush_status();
-                if (sm_publish(A, c, PRECISE ? 1 : 0, ST_STEP)) return;         // :127
+                if (sm_publish(A, V, c, PRECISE ? 1 : 0, ST_STEP)) return;         // :127
                 e = 0.0;
                 continue;
             }
@@ -400,7 +567,7 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
             const long long out_atom = (long long)a.replicas * c->off + (long long)c->rep * nl - a.out_base;
             double *dst = a.out_xyzq + out_atom * 4;
             for (int i = lane; i < nl; i += 32) {
-                dst[4 * i] = s.cx()[i]; dst[4 * i + 1] = s.cy()[i]; dst[4 * i + 2] = s.cz()[i]; dst[4 * i + 3] = s.q()[i];
+                dst[4 * i] = s.cx(i); dst[4 * i + 1] = s.cy(i); dst[4 * i + 2] = s.cz(i); dst[4 * i + 3] = s.q(i);
             }
             flush_status();
             if (lane == 0) {
@@ -424,43 +591,48 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
     V.raw = ddd_sm_smem; V.slots = A.slots; V.cap = A.c.nl_cap;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = A.slots;
-    if (threadIdx.x == 0) *V.live() = K;
-    if (threadIdx.x < K) V.ctl(threadIdx.x)->next_item = kSlotIdle;
+    if (threadIdx.x == 0) { *V.live() = K; *V.epoch() = 0; wake_init(V.mbar()); }
+    if (threadIdx.x < K) { V.ctl(threadIdx.x)->next_item = kSlotIdle; V.ctl(threadIdx.x)->step = 0; }
     __syncthreads();
     if (warp < K) sm_serial_phase<PRECISE>(A, V, warp, (long long)warp * gridDim.x + blockIdx.x);
 
     int rot = warp % K;
     for (;;) {
-        bool did = false;
+        const int ep = ld_volatile(V.epoch());
+        // the chain that is furthest behind goes first: chains of an SM advance in step and end together, and one that
+        // loses time in collision retries gets its pair sums served ahead of the others
+        int sid = -1, best = 0x7fffffff;
         for (int j = 0; j < K; ++j) {
-            int sid = rot + j; if (sid >= K) sid -= K;
-            SmSlotCtl *c = V.ctl(sid);
+            int t = rot + j; if (t >= K) t -= K;
+            const SmSlotCtl *c = V.ctl(t);
             if (ld_volatile(&c->next_item) >= A.n_items) continue;
-            int it = 0;
-            if (lane == 0) it = atomicAdd(&c->next_item, 1);
-            it = __shfl_sync(0xffffffffu, it, 0);
-            if (it >= A.n_items) continue;
-            __threadfence_block();
-            const SlotView s = V.slot(sid);
-            const int nl = c->nl;
-            const double sum = c->mode ? sm_item_f64(A, s, nl, it) : sm_item_f32(A, s.lf(), nl, it);
-            if (lane == 0) V.items(sid)[it] = sum;
-            __threadfence_block();
-            int d = 0;
-            if (lane == 0) d = atomicAdd(&c->done_items, 1);
-            d = __shfl_sync(0xffffffffu, d, 0);
-            if (d == A.n_items - 1) {                       // this warp completed the evaluation: it runs the serial phase
-                __threadfence_block();
-                sm_serial_phase<PRECISE>(A, V, sid, -1);
-            }
-            did = true;
-            rot = sid + 1; if (rot >= K) rot = 0;
-            break;
+            const int st = ld_volatile(reinterpret_cast<const int *>(&c->step));
+            if (st < best) { best = st; sid = t; if (!DDD_SM_PRIO) break; }
         }
-        if (!did) {
+        if (sid < 0) {
             if (ld_volatile(V.live()) == 0) break;
-            __nanosleep(100);
+            if (DDD_SM_SPIN) __nanosleep(100); else wake_wait(V.mbar(), ep & 1, 20000u);
+            continue;
         }
+        SmSlotCtl *c = V.ctl(sid);
+        int it = 0;
+        if (lane == 0) it = atomicAdd(&c->next_item, 1);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= A.n_items) continue;
+        __threadfence_block();
+        const SlotView s = V.slot(sid);
+        const int nl = c->nl;
+        const double sum = c->mode ? sm_item_f64(A, s, nl, it) : sm_item_f32(A, s.lf(), nl, it);
+        if (lane == 0) V.items(sid)[it] = sum;
+        __threadfence_block();
+        int d = 0;
+        if (lane == 0) d = atomicAdd(&c->done_items, 1);
+        d = __shfl_sync(0xffffffffu, d, 0);
+        if (d == A.n_items - 1) {                       // this warp completed the evaluation: it runs the serial phase
+            __threadfence_block();
+            sm_serial_phase<PRECISE>(A, V, sid, -1);
+        }
+        rot = sid + 1; if (rot >= K) rot = 0;
     }
 }
 

@@ -51,7 +51,7 @@ def test_replay_matches_oracle_sm_persistent_engine(gpu, orc, synth_small, rotat
         scr.set_chain_slots(slots)
         scr.run(120, rotate, T, _p64(gpu), seed=9)
         poses, stats = scr.download()
-        assert scr.chain_threads() == 1024 and scr.chain_slots() == (slots or 1)      # 24 chains on >= 24 SMs: 1 per SM
+        assert scr.chain_threads() == 512 and scr.chain_slots() == (slots or 1)      # 24 chains on >= 24 SMs: 1 per SM
         scr.close()
     for c in range(3 * (len(off) - 1)):
         li, r = divmod(c, 3)
