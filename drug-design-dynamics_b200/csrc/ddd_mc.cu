@@ -324,22 +324,27 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
         a.out_xyzq = d.d_out; a.out_base = d.out_base; a.out_stats = d.d_stats; a.out_trace = d.d_trace;
         a.nl_cap = d.nl_cap;
         const bool precise = p->precision == DDD_PRECISION_F64;
-        if (s->threads_override <= 0 && n_local > 0) {
+        const bool fits_sm_engine = sm_smem_bytes(d.nl_cap, 1) <= dev.max_smem;      // very large ligands: one CTA per chain
+        if (s->threads_override <= 0 && n_local > 0 && fits_sm_engine) {
             // SM-persistent engine: one 32-warp CTA per SM, K resident chains each (ddd_sm_chain.cuh)
             SmArgs A;
             A.c = a;
             const int grid = (int)std::min<int64_t>(dev.sm_count, n_local);
-            const int k_fit = (int)std::min<size_t>(kSmMaxSlots, (dev.max_smem - 16) / (sm_smem_bytes(d.nl_cap, 1) - 16));
-            if (k_fit < 1) return fail(DDD_ELIMIT, "ligand of %d atoms does not fit one SM's shared memory", d.nl_cap);
+            const int k_fit = (int)std::min<size_t>(kSmMaxSlots, (dev.max_smem - kCtaHeaderBytes) / (sm_smem_bytes(d.nl_cap, 1) - kCtaHeaderBytes));
             const int k_want = s->slots_override > 0 ? s->slots_override : pick_chain_slots(n_local, grid);
             A.slots = std::max(1, std::min(k_want, k_fit));
             A.queue = d.d_queue; A.n_local = n_local; A.first_dynamic = (long long)grid * A.slots;
             const int n = (int)s->rec->n;
             A.n_units = (n + 31) / 32;
-            // items per evaluation: a multiple of the warp count, each item <= 16 units (512 receptor atoms) when possible
-            int rounds = std::max(1, (A.n_units + kSmWarps * 16 - 1) / (kSmWarps * 16));
-            rounds = std::min(rounds, kSmMaxItems / kSmWarps);
-            A.upi = std::max(1, (A.n_units + kSmWarps * rounds - 1) / (kSmWarps * rounds));
+            // work items: runs of 4*m units (128*m receptor atoms: whole A=4 warp tiles), m as small as the item-sum
+            // array allows; receptors too small to give every warp such an item are cut into kSmWarps short items
+            if (A.n_units >= 4 * kSmWarps) {
+                const int quads = (A.n_units + 3) / 4;
+#ifndef DDD_SM_ITEM_QUADS
+#define DDD_SM_ITEM_QUADS 3
+#endif
+                A.upi = 4 * std::max(DDD_SM_ITEM_QUADS, (quads + kSmMaxItems - 1) / kSmMaxItems);
+            } else A.upi = std::max(1, (A.n_units + kSmWarps - 1) / kSmWarps);
             A.n_items = (A.n_units + A.upi - 1) / A.upi;
             const size_t smem = sm_smem_bytes(d.nl_cap, A.slots);
             d.threads = kSmThreads; d.slots = A.slots;

@@ -13,6 +13,14 @@
 // one-CTA-per-chain engine (ddd_kernels.cuh) cannot do when a launch has only ~7 chains per SM.
 // Chains beyond grid*K are pulled from a global counter as slots free up.
 //
+// SPECULATIVE PROPOSALS.  At T = 310 K with K = 9e9 nearly every step is rejected, and after a reject the
+// next proposal is fully determined: it starts from the unchanged current pose and from stream position pos + 1 (the
+// accept draw is consumed on every uphill move, :148).  So while the pair sums of step t are being evaluated, a free
+// warp already builds the proposal of step t+1 -- including all its collision retries -- into a third pose buffer
+// (one more work item, handed out first).  On a reject the evaluation of step t+1 starts at once; on the rare accept the
+// speculation is discarded and the proposal is redone from the new pose.  The latency-bound proposal work leaves the
+// chain's critical path: a step costs max(pair sums, proposal) instead of their sum.
+//
 // Results do not depend on which warp computed which item or on K: item sums are stored under their
 // item id and added in id order, and a chain's uniform stream is indexed by (chain id, draw index).
 #pragma once
@@ -37,6 +45,9 @@ constexpr int kNearCap    = 128;            // near-pair list entries per slot
 #ifndef DDD_SM_SPIN
 #define DDD_SM_SPIN 1
 #endif
+#ifndef DDD_SM_IDLE_NS
+#define DDD_SM_IDLE_NS 100
+#endif
 #ifndef DDD_SM_PRIO
 #define DDD_SM_PRIO 1
 #endif
@@ -46,14 +57,16 @@ constexpr int kNearCap    = 128;            // near-pair list entries per slot
 constexpr int kSmUnroll = DDD_SM_UNROLL;
 constexpr double kNearMargin = DDD_NEAR_MARGIN;         // a near-pair list holds every ligand pair closer than MINDISTANCE + this
 
-enum : int { ST_START64 = 0, ST_START32 = 1, ST_STEP = 2, ST_FINAL64 = 3, ST_PROPOSE = 4, ST_LOAD = 5 };
+enum : int { ST_START64 = 0, ST_START32 = 1, ST_STEP = 2, ST_FINAL64 = 3, ST_NEXT = 4, ST_LOAD = 5 };
 
 struct __align__(16) SmSlotCtl {
-    int next_item, done_items, mode, stage;           // mode: 0 = fp32 items, 1 = fp64 items
-    int nl, status, rep, bailed;
+    int next_item, done_items, n_total, mode;         // n_total = n_items + has_spec; mode: 0 = fp32 items, 1 = fp64 items
+    int stage, nl, status, rep;
+    int i_cur, i_trial, i_spec, has_spec;             // pose buffers (0..2): accepted pose, pose being evaluated, speculation
     long long local, step;
-    unsigned long long pos;                           // uniforms consumed so far
-    long long accepted, downhill, retries;
+    unsigned long long pos;                           // uniforms consumed up to and including the trial proposal
+    long long accepted;
+    long long downhill, retries;
     double cur_e, start_e;
     long long off;                                    // first atom of the ligand in the global CSR
     unsigned long long stream_id;
@@ -61,10 +74,17 @@ struct __align__(16) SmSlotCtl {
     long long rec_len;
     int base_n;                                       // near-pair list of the current pose: -1 = not built, > kNearCap = overflow
     int list_cnt;                                     // append counter while a list is being built
-    int pad0, pad1;
+    int spec_status, bailed;
+    unsigned long long spec_pos;                      // results of the speculative proposal: merged only if it is adopted
+    long long spec_rej;
 };
-static_assert(sizeof(SmSlotCtl) == 144, "SmSlotCtl is laid out as nine 16-byte words");
+static_assert(sizeof(SmSlotCtl) == 176, "SmSlotCtl is laid out as eleven 16-byte words");
 constexpr int kSlotFixedBytes = (int)sizeof(SmSlotCtl) + kSmMaxItems * 8 + kUbufDraws * 8 + 2 * kNearCap * 4;
+constexpr int kAtomRecBytes = 88;                     // fp64 record per atom: 3 poses x (x,y,z), q, pad
+constexpr int kAtomBytes = kAtomRecBytes + 3 * 16;    // + three pair-packed fp32 poses
+
+constexpr int kCtaHeaderBytes = 16 + 4 * kSmMaxSlots;   // live, epoch, wake barrier, then one scheduling key per slot
+constexpr int kKeyNone = 0x7fffffff;                    // key of a slot that has nothing to hand out
 
 struct SmArgs {
     ChainArgs c;
@@ -73,17 +93,15 @@ struct SmArgs {
     long long first_dynamic; // gridDim.x * slots: chains below are assigned statically (slot s of CTA b: s*grid + b)
     int slots;               // K
     int n_units;             // receptor units of 32 atoms (one per lane)
-    int upi, n_items;        // units per item; items per energy evaluation (<= kSmMaxItems).  An item is a run of
-                             // consecutive units, cut so that the item count is a multiple of the CTA's warp count:
-                             // a chain that has the SM to itself finishes an evaluation in whole rounds
+    int upi, n_items;        // units per item; items per energy evaluation (<= kSmMaxItems)
 };
 
 __host__ __device__ inline size_t sm_smem_bytes(int nl_cap, int slots) {
-    return 16 + (size_t)slots * (kSlotFixedBytes + (size_t)nl_cap * (7 * sizeof(double) + sizeof(float4)));
+    return kCtaHeaderBytes + (size_t)slots * (kSlotFixedBytes + (size_t)nl_cap * kAtomBytes);
 }
 
-// Views into the CTA's shared memory: [live 16] then per slot [ctl 144][item sums][uniform staging][base list][dyn list]
-// [pose: 56-byte fp64 atom records (cap), then lf (16*cap)]
+// Views into the CTA's shared memory: [live, epoch, wake barrier 16][keys 64] then per slot [ctl][item sums][uniform staging][base list][dyn list]
+// [fp64 atom records (cap x 88 B)][fp32 pair-packed poses (3 x cap x 16 B)]
 struct SlotView {
     unsigned char *blk;      // this slot's block
     unsigned char *pose;     // its pose part
@@ -91,18 +109,11 @@ struct SlotView {
     __device__ __forceinline__ double *ubuf() const { return reinterpret_cast<double *>(blk + sizeof(SmSlotCtl) + kSmMaxItems * 8); }
     __device__ __forceinline__ ushort2 *base_list() const { return reinterpret_cast<ushort2 *>(blk + sizeof(SmSlotCtl) + kSmMaxItems * 8 + kUbufDraws * 8); }
     __device__ __forceinline__ ushort2 *dyn_list() const { return base_list() + kNearCap; }
-    // fp64 pose, one 56-byte record per atom {cx cy cz px py pz q}: every field sits at a compile-time offset from
-    // pose + 56 * i whatever the capacity (half-warp accesses of stride 56 B are bank-conflict free); the pair-packed
-    // fp32 pose follows at pose + 56 * cap.
-    __device__ __forceinline__ double &f64(int i, int field) const { return *reinterpret_cast<double *>(pose + (size_t)i * 56 + field * 8); }
-    __device__ __forceinline__ double &cx(int i) const { return f64(i, 0); }
-    __device__ __forceinline__ double &cy(int i) const { return f64(i, 1); }
-    __device__ __forceinline__ double &cz(int i) const { return f64(i, 2); }
-    __device__ __forceinline__ double &px(int i) const { return f64(i, 3); }
-    __device__ __forceinline__ double &py(int i) const { return f64(i, 4); }
-    __device__ __forceinline__ double &pz(int i) const { return f64(i, 5); }
-    __device__ __forceinline__ double &q(int i) const { return f64(i, 6); }
-    __device__ __forceinline__ float4 *lf() const { return reinterpret_cast<float4 *>(pose + (size_t)cap * 56); }
+    // One 88-byte record per atom {x0 y0 z0 x1 y1 z1 x2 y2 z2 q pad}: every field sits at a compile-time offset from
+    // pose + 88 * i whatever the capacity, and half-warp 8-byte accesses of stride 88 B are bank-conflict free.
+    __device__ __forceinline__ double *xyz(int buf, int i) const { return reinterpret_cast<double *>(pose + (size_t)i * kAtomRecBytes) + 3 * buf; }
+    __device__ __forceinline__ double &q(int i) const { return *(reinterpret_cast<double *>(pose + (size_t)i * kAtomRecBytes) + 9); }
+    __device__ __forceinline__ float4 *lf(int buf) const { return reinterpret_cast<float4 *>(pose + (size_t)cap * kAtomRecBytes) + (size_t)buf * cap; }
 };
 
 struct SmView {
@@ -111,7 +122,9 @@ struct SmView {
     __device__ __forceinline__ int *live() const { return reinterpret_cast<int *>(raw); }
     __device__ __forceinline__ int *epoch() const { return reinterpret_cast<int *>(raw) + 1; }
     __device__ __forceinline__ unsigned long long *mbar() const { return reinterpret_cast<unsigned long long *>(raw + 8); }
-    __device__ __forceinline__ unsigned char *block(int s) const { return raw + 16 + (size_t)s * (kSlotFixedBytes + cap * 72); }
+    // scheduling key of a slot: the chain's step count while it has work to hand out, kKeyNone otherwise
+    __device__ __forceinline__ int *keys() const { return reinterpret_cast<int *>(raw + 16); }
+    __device__ __forceinline__ unsigned char *block(int s) const { return raw + kCtaHeaderBytes + (size_t)s * (kSlotFixedBytes + cap * kAtomBytes); }
     __device__ __forceinline__ SmSlotCtl *ctl(int s) const { return reinterpret_cast<SmSlotCtl *>(block(s)); }
     __device__ __forceinline__ double *items(int s) const { return reinterpret_cast<double *>(block(s) + sizeof(SmSlotCtl)); }
     __device__ __forceinline__ SlotView slot(int s) const {
@@ -123,20 +136,28 @@ struct SmView {
     }
 };
 
-// Idle warps do not spin (31 polling warps slow the one warp that is in a serial phase): they block on an mbarrier
-// whose phase flips whenever work is published or the last slot dies.  `epoch` counts the flips; a warp reads it BEFORE
-// it looks for work and then waits for the phase of that parity, so a publish in between wakes it at once; the rare
-// double flip inside that window is bounded by the wait's time limit.
+// Idle warps: either a short nanosleep poll (default) or a block on an mbarrier whose phase flips whenever work is
+// published (DDD_SM_SPIN=0; measured slower on B200: the wake-up of try_wait costs more than the poll).
 __device__ __forceinline__ void wake_init(unsigned long long *mbar) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((unsigned)__cvta_generic_to_shared(mbar)) : "memory");
 }
 __device__ __forceinline__ void wake_all(int *epoch, unsigned long long *mbar) {     // one lane
+    if (DDD_SM_SPIN) return;
     atomicAdd(epoch, 1);
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"((unsigned)__cvta_generic_to_shared(mbar)) : "memory");
 }
 __device__ __forceinline__ void wake_wait(unsigned long long *mbar, int parity, unsigned ns) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t}"
                  :: "r"((unsigned)__cvta_generic_to_shared(mbar)), "r"(parity), "r"(ns) : "memory");
+}
+
+// CTA-scope acquire/release fence (the default __threadfence_block() is the sequentially-consistent MEMBAR.SC.CTA)
+#ifndef DDD_SM_FENCE_SC
+#define DDD_SM_FENCE_SC 0
+#endif
+__device__ __forceinline__ void cta_fence() {
+    if (DDD_SM_FENCE_SC) __threadfence_block();
+    else asm volatile("fence.acq_rel.cta;" ::: "memory");
 }
 
 __device__ __forceinline__ int ld_volatile(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
@@ -157,14 +178,15 @@ __device__ __forceinline__ double sm_item_f32(const SmArgs &A, const float4 *lf,
 }
 
 // the reference's per-term fp64 arithmetic (:253-258) for the receptor atoms of one item
-__device__ __forceinline__ double sm_item_f64(const SmArgs &A, const SlotView &s, int nl, int it) {
+__device__ __forceinline__ double sm_item_f64(const SmArgs &A, const SlotView &s, int buf, int nl, int it) {
     const int p0 = it * A.upi * 32, p1 = min((it + 1) * A.upi * 32, A.c.rec.n);
     const double K = A.c.prm.k_coulomb, clampd = A.c.prm.clamp_distance;
     double e = 0.0;
     for (int p = p0 + (int)(threadIdx.x & 31); p < p1; p += 32) {
         const Atom64 P = A.c.rec.f64[p];
         for (int l = 0; l < nl; ++l) {
-            const double ddx = P.x - s.cx(l), ddy = P.y - s.cy(l), ddz = P.z - s.cz(l);
+            const double *L = s.xyz(buf, l);
+            const double ddx = P.x - L[0], ddy = P.y - L[1], ddz = P.z - L[2];
             double d = sqrt(ddx * ddx + ddy * ddy + ddz * ddz);          // :253 (Pow(x,2) == x*x)
             if (d < clampd) d = clampd;                                   // :255-257
             e += K * (P.q * s.q(l)) / d;                                  // :258
@@ -174,18 +196,13 @@ __device__ __forceinline__ double sm_item_f64(const SmArgs &A, const SlotView &s
 }
 
 // ------------------------------------------------------------------ one-warp proposal helpers
-__device__ __forceinline__ void sm_store_pose(const SmArgs &A, const SlotView &s, int i, double x, double y, double z) {
-    s.cx(i) = x; s.cy(i) = y; s.cz(i) = z;
-    store_lig_f32(s.lf(), i, (float)(x - A.c.rec.cx), (float)(y - A.c.rec.cy), (float)(z - A.c.rec.cz), (float)s.q(i));
-}
-
 // fp32 screen in front of IsCollisionFree, one warp: atoms in rows of 32 lanes; a short last row gives every atom
 // 32/rem lanes that split the ligand pairs.  Same classification as collision_screen_f32 (ddd_kernels.cuh).
-__device__ __forceinline__ int warp_collision_screen(const SlotView &s, int nl, float m2) {
+__device__ __noinline__ int warp_collision_screen(const float4 *lf, int nl, float m2) {
     const int lane = threadIdx.x & 31;
     const int n_pairs = (nl + 1) >> 1;
-    const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(s.lf());
-    const float *lff = reinterpret_cast<const float *>(s.lf());
+    const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
+    const float *lff = reinterpret_cast<const float *>(lf);
     float dmin = 3.0e38f, slack = 0.f;
     for (int b = 0; b < nl; b += 32) {
         const int rem = nl - b;
@@ -214,7 +231,7 @@ __device__ __forceinline__ int warp_collision_screen(const SlotView &s, int nl, 
 }
 
 // exact IsCollisionFree (:229-242) by one warp: pairs (i, i+m mod nl), m = 1..nl/2, as in collision_partial
-__device__ __forceinline__ bool warp_collision_exact(const SlotView &s, int nl, double min_distance) {
+__device__ __noinline__ bool warp_collision_exact(const SlotView &s, int buf, int nl, double min_distance) {
     const int full_rows = (nl - 1) / 2;
     const int n_full = full_rows * nl;
     const int total = n_full + ((nl & 1) ? 0 : nl / 2);
@@ -224,7 +241,8 @@ __device__ __forceinline__ bool warp_collision_exact(const SlotView &s, int nl, 
         int i, m;
         if (w < n_full) { m = w / nl + 1; i = w - (m - 1) * nl; } else { i = w - n_full; m = nl / 2; }
         int j = i + m; if (j >= nl) j -= nl;
-        const double dx = s.cx(i) - s.cx(j), dy = s.cy(i) - s.cy(j), dz = s.cz(i) - s.cz(j);
+        const double *a = s.xyz(buf, i), *b = s.xyz(buf, j);
+        const double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
         const double d2 = dx * dx + dy * dy + dz * dz;
         if (d2 < m2_lo) hit = true;
         else if (d2 < m2_hi) hit |= (sqrt(d2) < min_distance);              // :235-236
@@ -233,9 +251,13 @@ __device__ __forceinline__ bool warp_collision_exact(const SlotView &s, int nl, 
 }
 
 // fp32 pose of every atom from the fp64 master copy (the pair-packed layout the pair loop and the list scan read)
-__device__ __forceinline__ void warp_write_lf(const SmArgs &A, const SlotView &s, int nl) {
-    for (int i = threadIdx.x & 31; i < nl; i += 32)
-        store_lig_f32(s.lf(), i, (float)(s.cx(i) - A.c.rec.cx), (float)(s.cy(i) - A.c.rec.cy), (float)(s.cz(i) - A.c.rec.cz), (float)s.q(i));
+__device__ __forceinline__ void warp_write_lf(const SmArgs &A, const SlotView &s, int buf, int nl) {
+    float4 *lf = s.lf(buf);
+    for (int i = threadIdx.x & 31; i < nl; i += 32) {
+        const double *a = s.xyz(buf, i);
+        store_lig_f32(lf, i, (float)(a[0] - A.c.rec.cx), (float)(a[1] - A.c.rec.cy), (float)(a[2] - A.c.rec.cz), (float)s.q(i));
+    }
+    if ((nl & 1) && (threadIdx.x & 31) == 0) store_lig_f32(lf, nl, -kPadCoord, -kPadCoord, -kPadCoord, 0.f);   // q = 0 pad atom
     __syncwarp();
 }
 
@@ -244,11 +266,11 @@ __device__ __forceinline__ void warp_write_lf(const SmArgs &A, const SlotView &s
 // NOT listed cannot come within MINDISTANCE during the next k_max attempts (each attempt moves a pair distance by at
 // most jitter_width * sqrt(3); RotateLigand is rigid), so IsCollisionFree (:229-242) for those attempts only has to
 // look at the listed pairs -- with the reference's own fp64 test.  Returns the pair count (> kNearCap: overflow).
-__device__ __forceinline__ int warp_build_near_list(const SlotView &s, SmSlotCtl *c, ushort2 *list, int nl, float r2) {
+__device__ __noinline__ int warp_build_near_list(const float4 *lf, SmSlotCtl *c, ushort2 *list, int nl, float r2) {
     const int lane = threadIdx.x & 31;
     const int n_pairs = (nl + 1) >> 1;
-    const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(s.lf());
-    const float *lff = reinterpret_cast<const float *>(s.lf());
+    const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
+    const float *lff = reinterpret_cast<const float *>(lf);
     if (lane == 0) c->list_cnt = 0;
     __syncwarp();
     for (int b = 0; b < nl; b += 32) {
@@ -278,12 +300,13 @@ __device__ __forceinline__ int warp_build_near_list(const SlotView &s, SmSlotCtl
 }
 
 // IsCollisionFree (:229-242) restricted to the listed pairs, in the reference's fp64 arithmetic; true = some pair collides
-__device__ __forceinline__ bool warp_check_near_list(const SlotView &s, const ushort2 *list, int n, double min_distance) {
+__device__ __forceinline__ bool warp_check_near_list(const SlotView &s, int buf, const ushort2 *list, int n, double min_distance) {
     const double m2 = min_distance * min_distance, m2_lo = m2 * (1.0 - 1e-9), m2_hi = m2 * (1.0 + 1e-9);
     bool hit = false;
     for (int e = threadIdx.x & 31; e < n; e += 32) {
         const ushort2 pr = list[e];
-        const double dx = s.cx(pr.x) - s.cx(pr.y), dy = s.cy(pr.x) - s.cy(pr.y), dz = s.cz(pr.x) - s.cz(pr.y);
+        const double *a = s.xyz(buf, pr.x), *b = s.xyz(buf, pr.y);
+        const double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
         const double d2 = dx * dx + dy * dy + dz * dz;
         if (d2 < m2_lo) hit = true;
         else if (d2 < m2_hi) hit |= (sqrt(d2) < min_distance);              // :235-236
@@ -291,18 +314,166 @@ __device__ __forceinline__ bool warp_check_near_list(const SlotView &s, const us
     return __any_sync(0xffffffffu, hit) != 0;
 }
 
-// hand the slot's pose out for an energy evaluation; false when the receptor has no atoms (nothing to hand out)
-__device__ __forceinline__ bool sm_publish(const SmArgs &A, const SmView &V, SmSlotCtl *c, int mode, int stage) {
-    if ((threadIdx.x & 31) == 0) { c->mode = mode; c->stage = stage; c->done_items = 0; }
-    if (A.n_items == 0) return false;
-    __threadfence_block();
+struct ProposalResult { uint64_t pos; long long rej; int status; };
+
+// One proposal of the chain in slot `c`: pose buffer `src` (the current pose) -> buffer `dst`, uniforms from stream
+// position `pos0`.  REFERENCE move: JitterAndRotateLigand (:172-184) / JitterLigand (:154-167), retried cumulatively on
+// `dst` until IsCollisionFree (:180 / :162).  Latency is what matters here (late in a chain the jitter piles atoms up
+// at MINDISTANCE and a step needs tens of attempts), so:
+//  * axis / angle / sincos of up to 32 FUTURE attempts are computed at once, one attempt per lane (their stream
+//    positions are known in advance); an attempt fetches its own by shuffle;
+//  * the jitter uniforms of an attempt are produced one Philox block per lane and staged in shared memory;
+//  * the collision test looks only at the near-pair list of the current pose (or of a later attempt's pose once the
+//    list's distance budget is spent); the fp32 pose is written only for the attempt that passes.
+// status bit 1: retry bound hit (the pose in dst is meaningless), bit 2: recorded stream exhausted.
+__device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotView &s, SmSlotCtl *c, int src, int dst, uint64_t pos0) {
+    const int lane = threadIdx.x & 31;
+    const ChainArgs &a = A.c;
+    const DevParams &P = a.prm;
+    const int nl = c->nl;
+    Stream st; st.seed = a.seed; st.id = c->stream_id; st.rec = c->rec_ptr; st.rec_len = c->rec_len;
+    ProposalResult R; R.pos = pos0; R.rej = 0; R.status = 0;
+    int status = 0;
+    if (P.move_mode == 1) {
+        // EXTENSION: rigid-body move, draws tx,ty,tz,ax,ay,az,theta (no reference row); no collision test
+        const double tx = (st.draw(pos0, status) - 0.5) * P.rigid_translation;
+        const double ty = (st.draw(pos0 + 1, status) - 0.5) * P.rigid_translation;
+        const double tz = (st.draw(pos0 + 2, status) - 0.5) * P.rigid_translation;
+        double ax, ay, az, theta;
+        draw_axis_angle(st, pos0 + 3, P.rigid_angle, status, ax, ay, az, theta);
+        double gx = 0, gy = 0, gz = 0;
+        for (int i = 0; i < nl; ++i) { const double *p = s.xyz(src, i); gx += p[0]; gy += p[1]; gz += p[2]; }
+        if (nl > 0) { gx /= (double)nl; gy /= (double)nl; gz /= (double)nl; }
+        const double h = 0.5 * theta;
+        double sh, w; sincos(h, &sh, &w);
+        const double qx = sh * ax, qy = sh * ay, qz = sh * az;
+        for (int i = lane; i < nl; i += 32) {
+            const double *p = s.xyz(src, i);
+            const double vx = p[0] - gx, vy = p[1] - gy, vz = p[2] - gz;
+            const double c1x = qy * vz - qz * vy, c1y = qz * vx - qx * vz, c1z = qx * vy - qy * vx;
+            const double c2x = qy * c1z - qz * c1y, c2y = qz * c1x - qx * c1z, c2z = qx * c1y - qy * c1x;
+            double *o = s.xyz(dst, i);
+            o[0] = gx + (vx + 2.0 * (w * c1x + c2x)) + tx;
+            o[1] = gy + (vy + 2.0 * (w * c1y + c2y)) + ty;
+            o[2] = gz + (vz + 2.0 * (w * c1z + c2z)) + tz;
+        }
+        __syncwarp();
+        warp_write_lf(A, s, dst, nl);
+        R.pos = pos0 + 7;
+        R.status = __any_sync(0xffffffffu, status & 2) ? 2 : 0;
+        return R;
+    }
+    const int dpa = (P.rotate ? 4 : 0) + 3 * nl;                         // draws per attempt
+    const double pair_step = fabs(P.jitter_width) * 1.7320508075688774;   // max change of a pair distance per attempt
+    const int k_max = pair_step > 0.0 ? (int)fmin((kNearMargin - 1e-6) / (pair_step * (1.0 + 1e-9)), 1.0e6) : 1000000;
+    const float r_near = (float)(P.min_distance + kNearMargin), r2_near = r_near * r_near;
+    const bool use_ubuf = !st.rec && 3 * nl + 2 <= kUbufDraws;
+    int base_n = c->base_n;
+    if (base_n < 0) {                                                     // first proposal after a load or an accepted move
+        base_n = warp_build_near_list(s.lf(src), c, s.base_list(), nl, r2_near);
+        if (lane == 0) c->base_n = base_n;
+    }
+    int dyn_n = -1, dyn_kb = 0, kb = 0, bstat = 0;
+    bool lists_ok = true, bail = false;
+    double bax = 0, bay = 0, baz = 0, bsin = 0, bcos = 1;                 // this lane's attempt of the batch
+    int k = 0;                                                            // attempts made
+    int from = src;
+    for (;;) {
+        ++k;
+        const uint64_t apos = pos0 + (uint64_t)(k - 1) * (uint64_t)dpa;
+        double ax = 0, ay = 0, az = 0, cos_t = 1, sin_t = 0;
+        uint64_t jpos = apos;
+        if (P.rotate) {                                                   // RotateLigand :189-208
+            int j = (k - 1) - kb;
+            if (k == 1 || j == 32) {
+                kb = k - 1; j = 0; bstat = 0;
+                double theta;
+                draw_axis_angle(st, pos0 + (uint64_t)(kb + lane) * (uint64_t)dpa, P.max_angle, bstat, bax, bay, baz, theta);
+                sincos(theta, &bsin, &bcos);                             // :214-215
+            }
+            ax = __shfl_sync(0xffffffffu, bax, j); ay = __shfl_sync(0xffffffffu, bay, j); az = __shfl_sync(0xffffffffu, baz, j);
+            sin_t = __shfl_sync(0xffffffffu, bsin, j); cos_t = __shfl_sync(0xffffffffu, bcos, j);
+            status |= __shfl_sync(0xffffffffu, bstat, j);
+            if (ax == 0.0 && ay == 0.0 && az == 0.0) lists_ok = false;    // Normalize no-op (datatypes.go:33-40): not a rotation
+            jpos += 4;
+        }
+        const uint64_t b_first = jpos >> 1;
+        if (use_ubuf && nl > 0) {
+            const int nb = (int)(((jpos + 3ull * (uint64_t)nl - 1) >> 1) - b_first) + 1;
+            double2 *ub = reinterpret_cast<double2 *>(s.ubuf());
+#pragma unroll kSmUnroll
+            for (int b = lane; b < nb; b += 32) {
+                const uint64_t blk = b_first + (uint64_t)b;
+                uint32_t o[4];
+                philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)st.id, (uint32_t)(st.id >> 32),
+                              (uint32_t)st.seed, (uint32_t)(st.seed >> 32), o);
+                ub[b] = make_double2(u53(o[0], o[1]), u53(o[2], o[3]));
+            }
+            __syncwarp();
+        }
+        const double *uu = s.ubuf() + (jpos - 2 * b_first);
+#pragma unroll kSmUnroll
+        for (int i = lane; i < nl; i += 32) {
+            const double *p = s.xyz(from, i);
+            double x = p[0], y = p[1], z = p[2];
+            if (P.rotate) rotate_atom(x, y, z, ax, ay, az, cos_t, sin_t);
+            double u[3];
+            if (use_ubuf) { u[0] = uu[3 * i]; u[1] = uu[3 * i + 1]; u[2] = uu[3 * i + 2]; }
+            else st.draw3(jpos + 3ull * (uint64_t)i, u, status);
+            x += (u[0] - 0.5) * P.jitter_width;                          // :176-178 / :158-160
+            y += (u[1] - 0.5) * P.jitter_width;
+            z += (u[2] - 0.5) * P.jitter_width;
+            double *o = s.xyz(dst, i);
+            o[0] = x; o[1] = y; o[2] = z;
+        }
+        from = dst;                                                       // retries are cumulative
+        __syncwarp();
+        bool collided, lf_fresh = false;
+        if (lists_ok && base_n <= kNearCap && k <= k_max) collided = warp_check_near_list(s, dst, s.base_list(), base_n, P.min_distance);
+        else if (lists_ok && dyn_n >= 0 && k - dyn_kb <= k_max) collided = warp_check_near_list(s, dst, s.dyn_list(), dyn_n, P.min_distance);
+        else {
+            warp_write_lf(A, s, dst, nl);
+            lf_fresh = true;
+            const int n = warp_build_near_list(s.lf(dst), c, s.dyn_list(), nl, r2_near);
+            if (n <= kNearCap) { dyn_n = n; dyn_kb = k; collided = warp_check_near_list(s, dst, s.dyn_list(), n, P.min_distance); }
+            else {                                                        // list overflow: screen every pair
+                dyn_n = -1;
+                const int code = warp_collision_screen(s.lf(dst), nl, (float)(P.min_distance * P.min_distance));
+                collided = __any_sync(0xffffffffu, code & 2) != 0;
+                if (!collided && __any_sync(0xffffffffu, code & 1))
+                    collided = __any_sync(0xffffffffu, warp_collision_exact(s, dst, nl, P.min_distance)) != 0;
+            }
+        }
+        if (!collided) { if (!lf_fresh) warp_write_lf(A, s, dst, nl); break; }
+        ++R.rej;
+        if (R.rej >= P.max_retries) { bail = true; break; }                // the reference would spin forever here
+    }
+    R.pos = pos0 + (uint64_t)k * (uint64_t)dpa;
+    R.status = (bail ? 1 : 0) | (__any_sync(0xffffffffu, status & 2) ? 2 : 0);
+    return R;
+}
+
+// Hand the slot out: pair-sum items of the trial pose (mode/stage) and, when `with_spec`, the speculative proposal of the
+// following step.  False when the receptor has no atoms (nothing to hand out: the caller goes on inline).
+__device__ __forceinline__ bool sm_publish(const SmArgs &A, const SmView &V, int slot_id, SmSlotCtl *c, int mode, int stage, bool with_spec) {
+    if (A.n_items == 0) { if ((threadIdx.x & 31) == 0) { c->mode = mode; c->stage = stage; c->has_spec = 0; } __syncwarp(); return false; }
+    if ((threadIdx.x & 31) == 0) {
+        c->mode = mode; c->stage = stage; c->done_items = 0; c->has_spec = with_spec ? 1 : 0;
+        c->n_total = A.n_items + (with_spec ? 1 : 0);
+    }
+    cta_fence();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) { st_volatile(&c->next_item, 0); __threadfence_block(); wake_all(V.epoch(), V.mbar()); }
+    if ((threadIdx.x & 31) == 0) {
+        st_volatile(&c->next_item, 0);
+        st_volatile(V.keys() + slot_id, (int)(c->step & 0x3fffffff));
+        cta_fence();
+        wake_all(V.epoch(), V.mbar());
+    }
     return true;
 }
 
 // ------------------------------------------------------------------ serial phase (one warp)
-// `load_pos` >= 0: (re)start the slot with the chain at launch position load_pos; -1: the slot's items are complete.
+// `load_pos` >= 0: (re)start the slot with the chain at launch position load_pos; -1: everything handed out is complete.
 template <bool PRECISE>
 __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, int slot_id, long long load_pos) {
     const int lane = threadIdx.x & 31;
@@ -312,21 +483,15 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
     const DevParams &P = a.prm;
     int stage;
     double e = 0.0;
+    bool spec_ready = false;
     if (load_pos >= 0) stage = ST_LOAD;
     else {
         stage = c->stage;
+        spec_ready = c->has_spec != 0;
         const double *items = V.items(slot_id);
         for (int it = lane; it < A.n_items; it += 32) e += items[it];       // fixed order: independent of who computed what
         e = warp_sum(e);
     }
-    int status = 0;
-    // fold this invocation's status bits into the slot (bit 2 can be raised by any lane that drew)
-    auto flush_status = [&]() {
-        const int st_or = __any_sync(0xffffffffu, status & 2) ? 2 : 0;
-        if (lane == 0) c->status |= (status & 1) | st_or;
-        status = 0;
-        __syncwarp();
-    };
     for (;;) {
         if (stage == ST_LOAD) {
             if (load_pos < 0) {                                                 // pull the next chain of the launch
@@ -336,7 +501,7 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 load_pos = A.first_dynamic + (long long)t;
             }
             if (load_pos >= A.n_local) {                                        // nothing left: the slot dies
-                if (lane == 0) { st_volatile(&c->next_item, kSlotIdle); atomicSub(V.live(), 1); __threadfence_block(); wake_all(V.epoch(), V.mbar()); }
+                if (lane == 0) { st_volatile(&c->next_item, kSlotIdle); atomicSub(V.live(), 1); cta_fence(); wake_all(V.epoch(), V.mbar()); }
                 return;
             }
             const long long local = a.order ? (long long)a.order[load_pos] : load_pos;
@@ -346,12 +511,13 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
             const int nl = (int)(a.offsets[lig + 1] - off);
             const double *src = a.lig_xyzq + (off - a.atom_base) * 4;           // private copy of the start pose
             for (int i = lane; i < nl; i += 32) {
+                double *o = s.xyz(0, i);
+                o[0] = src[4 * i]; o[1] = src[4 * i + 1]; o[2] = src[4 * i + 2];
                 s.q(i) = src[4 * i + 3];
-                sm_store_pose(A, s, i, src[4 * i], src[4 * i + 1], src[4 * i + 2]);
             }
             if (lane == 0) {
-                if (nl & 1) store_lig_f32(s.lf(), nl, -kPadCoord, -kPadCoord, -kPadCoord, 0.f);   // q = 0 pad atom
                 c->nl = nl; c->status = 0; c->rep = (int)(chain - lig * a.replicas); c->bailed = 0;
+                c->i_cur = 0; c->i_trial = 0; c->i_spec = 1; c->has_spec = 0;
                 c->local = local; c->step = 0; c->pos = 0; c->accepted = 0; c->downhill = 0; c->retries = 0;
                 c->cur_e = 0.0; c->start_e = 0.0; c->off = off; c->base_n = -1; c->list_cnt = 0;
                 c->stream_id = a.chain_id_base + (uint64_t)chain;
@@ -362,33 +528,34 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 }
             }
             __syncwarp();
+            warp_write_lf(A, s, 0, nl);
             load_pos = -1;
-            status = 0;
+            spec_ready = false;
             stage = ST_START64;
-            if (sm_publish(A, V, c, 1, ST_START64)) return;                        // :118 in fp64
+            if (sm_publish(A, V, slot_id, c, 1, ST_START64, false)) return;             // :118 in fp64
             e = 0.0;
         }
         const int nl = c->nl;
         if (stage == ST_START64) {
             if (lane == 0) { c->start_e = e; c->cur_e = e; }
             __syncwarp();
-            if (PRECISE) stage = ST_PROPOSE;
+            if (PRECISE) stage = ST_NEXT;
             else {
                 stage = ST_START32;                                             // the chain's own currentEnergy, fp32-summed
-                flush_status();
-                if (sm_publish(A, V, c, 0, ST_START32)) return;
+                if (sm_publish(A, V, slot_id, c, 0, ST_START32, false)) return;
                 e = 0.0;
             }
         }
         if (stage == ST_START32) {
             if (lane == 0) c->cur_e = P.k_coulomb * e;
             __syncwarp();
-            stage = ST_PROPOSE;
+            stage = ST_NEXT;
         }
         if (stage == ST_STEP) {                                                 // AcceptMove :141-149
             const double new_e = PRECISE ? e : P.k_coulomb * e;
             const double cur_e = c->cur_e;
             uint64_t pos = c->pos;
+            int status = 0;
             bool acc;
             const bool dh = new_e < cur_e;
             if (dh) acc = true;
@@ -403,173 +570,66 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 }
                 pos += 1;
             }
-            if (!acc) for (int i = lane; i < nl; i += 32) { s.cx(i) = s.px(i); s.cy(i) = s.py(i); s.cz(i) = s.pz(i); }  // :132
             __syncwarp();
             if (lane == 0) {
-                if (acc) { c->cur_e = new_e; c->base_n = -1; }                  // :129-130; the near-pair list described the old pose
-                c->pos = pos;
+                const int t = c->i_trial, sp = c->i_spec, cu = c->i_cur;
+                if (acc) { c->cur_e = new_e; c->base_n = -1; c->i_cur = t; c->i_trial = cu; c->i_spec = sp; }   // :129-130
+                else { c->i_trial = sp; c->i_spec = t; }                        // :132: the current pose was never touched
+                c->pos = pos; c->status |= status & 2;
                 c->accepted += acc ? 1 : 0; c->downhill += dh ? 1 : 0;
                 if (a.out_trace) a.out_trace[c->local * a.steps + c->step] = acc ? 1 : 0;
                 c->step += 1;
             }
             __syncwarp();
-            stage = ST_PROPOSE;
+            if (acc) spec_ready = false;                                        // the speculation assumed a reject
+            stage = ST_NEXT;
         }
-        if (stage == ST_PROPOSE) {
-            if (c->step >= a.steps || c->bailed) {
-                if (PRECISE) { e = c->cur_e; stage = ST_FINAL64; }
+        if (stage == ST_NEXT) {
+            bool finish = c->step >= a.steps || c->bailed;
+            if (!finish) {
+                if (c->i_trial == c->i_cur) {                                   // first step: the start stages evaluated the current pose
+                    __syncwarp();
+                    if (lane == 0) { const int cu = c->i_cur; c->i_trial = (cu + 1) % 3; c->i_spec = (cu + 2) % 3; }
+                    __syncwarp();
+                }
+                // the trial pose of this step: the adopted speculation (after a reject) or a proposal made here
+                ProposalResult R;
+                if (spec_ready) { R.pos = c->spec_pos; R.rej = c->spec_rej; R.status = c->spec_status; }
+                else R = sm_propose(A, s, c, c->i_cur, c->i_trial, c->pos);
+                spec_ready = false;
+                __syncwarp();
+                if (lane == 0) {
+                    c->pos = R.pos; c->retries += R.rej; c->status |= R.status;
+                    if (R.status & 1) c->bailed = 1;
+                }
+                __syncwarp();
+                if (R.status & 1) finish = true;                                // retry bound: the chain ends on its current pose
                 else {
-                    stage = ST_FINAL64;                                         // CalculateEnergy of the returned pose in fp64 (:61 / :104)
-                    flush_status();
-                    if (sm_publish(A, V, c, 1, ST_FINAL64)) return;
+                    stage = ST_STEP;
+                    if (sm_publish(A, V, slot_id, c, PRECISE ? 1 : 0, ST_STEP, c->step + 1 < a.steps)) return;   // :127
                     e = 0.0;
+                    continue;
                 }
-            } else {
-                Stream st; st.seed = a.seed; st.id = c->stream_id; st.rec = c->rec_ptr; st.rec_len = c->rec_len;
-                uint64_t pos = c->pos;
-                for (int i = lane; i < nl; i += 32) { s.px(i) = s.cx(i); s.py(i) = s.cy(i); s.pz(i) = s.cz(i); }   // :121
-                __syncwarp();
-                long long rej = 0;
-                bool bail = false;
-                if (P.move_mode == 1) {
-                    // EXTENSION: rigid-body move, draws tx,ty,tz,ax,ay,az,theta (no reference row); no collision test
-                    const double tx = (st.draw(pos, status) - 0.5) * P.rigid_translation;
-                    const double ty = (st.draw(pos + 1, status) - 0.5) * P.rigid_translation;
-                    const double tz = (st.draw(pos + 2, status) - 0.5) * P.rigid_translation;
-                    double ax, ay, az, theta;
-                    draw_axis_angle(st, pos + 3, P.rigid_angle, status, ax, ay, az, theta);
-                    double gx = 0, gy = 0, gz = 0;
-                    for (int i = 0; i < nl; ++i) { gx += s.px(i); gy += s.py(i); gz += s.pz(i); }
-                    if (nl > 0) { gx /= (double)nl; gy /= (double)nl; gz /= (double)nl; }
-                    const double h = 0.5 * theta;
-                    double sh, w; sincos(h, &sh, &w);
-                    const double qx = sh * ax, qy = sh * ay, qz = sh * az;
-                    for (int i = lane; i < nl; i += 32) {
-                        const double vx = s.px(i) - gx, vy = s.py(i) - gy, vz = s.pz(i) - gz;
-                        const double c1x = qy * vz - qz * vy, c1y = qz * vx - qx * vz, c1z = qx * vy - qy * vx;
-                        const double c2x = qy * c1z - qz * c1y, c2y = qz * c1x - qx * c1z, c2z = qx * c1y - qy * c1x;
-                        sm_store_pose(A, s, i, gx + (vx + 2.0 * (w * c1x + c2x)) + tx,
-                                      gy + (vy + 2.0 * (w * c1y + c2y)) + ty, gz + (vz + 2.0 * (w * c1z + c2z)) + tz);
-                    }
-                    pos += 7;
-                } else {
-                    // REFERENCE move: JitterAndRotateLigand (:172-184) / JitterLigand (:154-167), in place, retried
-                    // cumulatively until IsCollisionFree (:180 / :162).  Latency is what matters here (late in a chain the
-                    // jitter piles atoms up at MINDISTANCE and a step needs tens of attempts), so:
-                    //  * axis / angle / sincos of up to 32 FUTURE attempts are computed at once, one attempt per lane
-                    //    (their stream positions are known in advance); an attempt fetches its own by shuffle;
-                    //  * the jitter uniforms of an attempt are produced one Philox block per lane and staged in shared memory;
-                    //  * the collision test looks only at the near-pair list of the step's start pose (or of a later
-                    //    attempt's pose once the list's distance budget is spent); the fp32 pose is written only for
-                    //    the attempt that passes.
-                    const int dpa = (P.rotate ? 4 : 0) + 3 * nl;                         // draws per attempt
-                    const uint64_t pos0 = pos;
-                    const double pair_step = fabs(P.jitter_width) * 1.7320508075688774;   // max change of a pair distance per attempt
-                    const int k_max = pair_step > 0.0 ? (int)fmin((kNearMargin - 1e-6) / (pair_step * (1.0 + 1e-9)), 1.0e6) : 1000000;
-                    const float r_near = (float)(P.min_distance + kNearMargin), r2_near = r_near * r_near;
-                    const bool use_ubuf = !st.rec && 3 * nl + 2 <= kUbufDraws;
-                    int base_n = c->base_n;
-                    if (base_n < 0) {                                                     // first step after a load or an accepted move
-                        warp_write_lf(A, s, nl);
-                        base_n = warp_build_near_list(s, c, s.base_list(), nl, r2_near);
-                        if (lane == 0) c->base_n = base_n;
-                    }
-                    int dyn_n = -1, dyn_kb = 0, kb = 0, bstat = 0;
-                    bool lists_ok = true;
-                    double bax = 0, bay = 0, baz = 0, bsin = 0, bcos = 1;                 // this lane's attempt of the batch
-                    int k = 0;                                                            // attempts made in this step
-                    for (;;) {
-                        ++k;
-                        const uint64_t apos = pos0 + (uint64_t)(k - 1) * (uint64_t)dpa;
-                        double ax = 0, ay = 0, az = 0, cos_t = 1, sin_t = 0;
-                        uint64_t jpos = apos;
-                        if (P.rotate) {                                                   // RotateLigand :189-208
-                            int j = (k - 1) - kb;
-                            if (k == 1 || j == 32) {
-                                kb = k - 1; j = 0; bstat = 0;
-                                double theta;
-                                draw_axis_angle(st, pos0 + (uint64_t)(kb + lane) * (uint64_t)dpa, P.max_angle, bstat, bax, bay, baz, theta);
-                                sincos(theta, &bsin, &bcos);                             // :214-215
-                            }
-                            ax = __shfl_sync(0xffffffffu, bax, j); ay = __shfl_sync(0xffffffffu, bay, j); az = __shfl_sync(0xffffffffu, baz, j);
-                            sin_t = __shfl_sync(0xffffffffu, bsin, j); cos_t = __shfl_sync(0xffffffffu, bcos, j);
-                            status |= __shfl_sync(0xffffffffu, bstat, j);
-                            if (ax == 0.0 && ay == 0.0 && az == 0.0) lists_ok = false;    // Normalize no-op (datatypes.go:33-40): not a rotation
-                            jpos += 4;
-                        }
-                        const uint64_t b_first = jpos >> 1;
-                        if (use_ubuf && nl > 0) {
-                            const int nb = (int)(((jpos + 3ull * (uint64_t)nl - 1) >> 1) - b_first) + 1;
-                            double2 *ub = reinterpret_cast<double2 *>(s.ubuf());
-#pragma unroll kSmUnroll
-                            for (int b = lane; b < nb; b += 32) {
-                                const uint64_t blk = b_first + (uint64_t)b;
-                                uint32_t o[4];
-                                philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)st.id, (uint32_t)(st.id >> 32),
-                                              (uint32_t)st.seed, (uint32_t)(st.seed >> 32), o);
-                                ub[b] = make_double2(u53(o[0], o[1]), u53(o[2], o[3]));
-                            }
-                            __syncwarp();
-                        }
-                        const double *uu = s.ubuf() + (jpos - 2 * b_first);
-#pragma unroll kSmUnroll
-                        for (int i = lane; i < nl; i += 32) {
-                            double x = s.cx(i), y = s.cy(i), z = s.cz(i);
-                            if (P.rotate) rotate_atom(x, y, z, ax, ay, az, cos_t, sin_t);
-                            double u[3];
-                            if (use_ubuf) { u[0] = uu[3 * i]; u[1] = uu[3 * i + 1]; u[2] = uu[3 * i + 2]; }
-                            else st.draw3(jpos + 3ull * (uint64_t)i, u, status);
-                            x += (u[0] - 0.5) * P.jitter_width;                          // :176-178 / :158-160
-                            y += (u[1] - 0.5) * P.jitter_width;
-                            z += (u[2] - 0.5) * P.jitter_width;
-                            s.cx(i) = x; s.cy(i) = y; s.cz(i) = z;
-                        }
-                        __syncwarp();
-                        bool collided, lf_fresh = false;
-                        if (lists_ok && base_n <= kNearCap && k <= k_max) collided = warp_check_near_list(s, s.base_list(), base_n, P.min_distance);
-                        else if (lists_ok && dyn_n >= 0 && k - dyn_kb <= k_max) collided = warp_check_near_list(s, s.dyn_list(), dyn_n, P.min_distance);
-                        else {
-                            warp_write_lf(A, s, nl);
-                            lf_fresh = true;
-                            const int n = warp_build_near_list(s, c, s.dyn_list(), nl, r2_near);
-                            if (n <= kNearCap) { dyn_n = n; dyn_kb = k; collided = warp_check_near_list(s, s.dyn_list(), n, P.min_distance); }
-                            else {                                                        // list overflow: screen every pair
-                                dyn_n = -1;
-                                const int code = warp_collision_screen(s, nl, (float)(P.min_distance * P.min_distance));
-                                collided = __any_sync(0xffffffffu, code & 2) != 0;
-                                if (!collided && __any_sync(0xffffffffu, code & 1))
-                                    collided = __any_sync(0xffffffffu, warp_collision_exact(s, nl, P.min_distance)) != 0;
-                            }
-                        }
-                        if (!collided) { if (!lf_fresh) warp_write_lf(A, s, nl); break; }
-                        ++rej;                              // retry on the already-moved atoms
-                        if (rej >= P.max_retries) { bail = true; break; }
-                    }
-                    pos = pos0 + (uint64_t)k * (uint64_t)dpa;
-                }
-                if (bail) {                                  // the reference would spin forever here
-                    status |= 1;
-                    for (int i = lane; i < nl; i += 32) { s.cx(i) = s.px(i); s.cy(i) = s.py(i); s.cz(i) = s.pz(i); }
-                }
-                __syncwarp();
-                if (lane == 0) { c->pos = pos; c->retries += rej; c->bailed = bail ? 1 : 0; }
-                __syncwarp();
-                if (bail) continue;                         // -> ST_PROPOSE sees `bailed` and finalises
-                stage = ST_STEP;
-                flush_status();
-                if (sm_publish(A, V, c, PRECISE ? 1 : 0, ST_STEP)) return;         // :127
+            }
+            // CalculateEnergy of the returned pose in fp64 (:61 / :104)
+            if (lane == 0) c->i_trial = c->i_cur;
+            __syncwarp();
+            stage = ST_FINAL64;
+            if (PRECISE) e = c->cur_e;
+            else {
+                if (sm_publish(A, V, slot_id, c, 1, ST_FINAL64, false)) return;
                 e = 0.0;
-                continue;
             }
         }
         if (stage == ST_FINAL64) {
             const double final_energy = e;
             const long long out_atom = (long long)a.replicas * c->off + (long long)c->rep * nl - a.out_base;
             double *dst = a.out_xyzq + out_atom * 4;
+            const int cu = c->i_cur;
             for (int i = lane; i < nl; i += 32) {
-                dst[4 * i] = s.cx(i); dst[4 * i + 1] = s.cy(i); dst[4 * i + 2] = s.cz(i); dst[4 * i + 3] = s.q(i);
+                const double *p = s.xyz(cu, i);
+                dst[4 * i] = p[0]; dst[4 * i + 1] = p[1]; dst[4 * i + 2] = p[2]; dst[4 * i + 3] = s.q(i);
             }
-            flush_status();
             if (lane == 0) {
                 ChainStats cs;
                 cs.accepted = c->accepted; cs.downhill = c->downhill; cs.retries = c->retries; cs.steps = c->step;
@@ -578,10 +638,18 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 reinterpret_cast<ChainStats *>(a.out_stats)[c->local] = cs;
             }
             __syncwarp();
-            status = 0;
             stage = ST_LOAD;                                // load_pos == -1: pull from the queue
         }
     }
+}
+
+// the speculative proposal of the step after the one being evaluated: assumes a reject (pose unchanged, one accept draw)
+__device__ __forceinline__ void sm_spec_task(const SmArgs &A, const SmView &V, int slot_id) {
+    SmSlotCtl *c = V.ctl(slot_id);
+    const SlotView s = V.slot(slot_id);
+    const ProposalResult R = sm_propose(A, s, c, c->i_cur, c->i_spec, c->pos + 1);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) { c->spec_pos = R.pos; c->spec_rej = R.rej; c->spec_status = R.status; }
 }
 
 template <bool PRECISE>
@@ -592,44 +660,51 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = A.slots;
     if (threadIdx.x == 0) { *V.live() = K; *V.epoch() = 0; wake_init(V.mbar()); }
-    if (threadIdx.x < K) { V.ctl(threadIdx.x)->next_item = kSlotIdle; V.ctl(threadIdx.x)->step = 0; }
+    if (threadIdx.x < kSmMaxSlots) V.keys()[threadIdx.x] = kKeyNone;
+    if (threadIdx.x < K) { V.ctl(threadIdx.x)->next_item = kSlotIdle; V.ctl(threadIdx.x)->n_total = 0; V.ctl(threadIdx.x)->step = 0; }
     __syncthreads();
-    if (warp < K) sm_serial_phase<PRECISE>(A, V, warp, (long long)warp * gridDim.x + blockIdx.x);
+    for (int sl = warp; sl < K; sl += kSmWarps) sm_serial_phase<PRECISE>(A, V, sl, (long long)sl * gridDim.x + blockIdx.x);
 
     int rot = warp % K;
     for (;;) {
-        const int ep = ld_volatile(V.epoch());
+        const int ep = DDD_SM_SPIN ? 0 : ld_volatile(V.epoch());
         // the chain that is furthest behind goes first: chains of an SM advance in step and end together, and one that
         // loses time in collision retries gets its pair sums served ahead of the others
-        int sid = -1, best = 0x7fffffff;
+        int sid = -1, best = kKeyNone;
         for (int j = 0; j < K; ++j) {
             int t = rot + j; if (t >= K) t -= K;
-            const SmSlotCtl *c = V.ctl(t);
-            if (ld_volatile(&c->next_item) >= A.n_items) continue;
-            const int st = ld_volatile(reinterpret_cast<const int *>(&c->step));
-            if (st < best) { best = st; sid = t; if (!DDD_SM_PRIO) break; }
+            const int key = ld_volatile(V.keys() + t);
+            if (key < best) { best = key; sid = t; if (!DDD_SM_PRIO) break; }
         }
         if (sid < 0) {
             if (ld_volatile(V.live()) == 0) break;
-            if (DDD_SM_SPIN) __nanosleep(100); else wake_wait(V.mbar(), ep & 1, 20000u);
+            if (DDD_SM_SPIN) __nanosleep(DDD_SM_IDLE_NS); else wake_wait(V.mbar(), ep & 1, 20000u);
             continue;
         }
         SmSlotCtl *c = V.ctl(sid);
         int it = 0;
         if (lane == 0) it = atomicAdd(&c->next_item, 1);
         it = __shfl_sync(0xffffffffu, it, 0);
-        if (it >= A.n_items) continue;
-        __threadfence_block();
-        const SlotView s = V.slot(sid);
-        const int nl = c->nl;
-        const double sum = c->mode ? sm_item_f64(A, s, nl, it) : sm_item_f32(A, s.lf(), nl, it);
-        if (lane == 0) V.items(sid)[it] = sum;
-        __threadfence_block();
+        cta_fence();
+        const int n_total = ld_volatile(&c->n_total);
+        // whoever takes the last piece clears the key (it still holds that piece, so the slot cannot be re-published before)
+        if (it == n_total - 1 && lane == 0) st_volatile(V.keys() + sid, kKeyNone);
+        if (it >= n_total) continue;
+        const int has_spec = n_total - A.n_items;           // the speculative proposal is handed out first: it is the long pole
+        if (has_spec && it == 0) sm_spec_task(A, V, sid);
+        else {
+            const int e_it = it - has_spec;
+            const SlotView s = V.slot(sid);
+            const int nl = c->nl, buf = c->i_trial;
+            const double sum = c->mode ? sm_item_f64(A, s, buf, nl, e_it) : sm_item_f32(A, s.lf(buf), nl, e_it);
+            if (lane == 0) V.items(sid)[e_it] = sum;
+        }
+        cta_fence();
         int d = 0;
         if (lane == 0) d = atomicAdd(&c->done_items, 1);
         d = __shfl_sync(0xffffffffu, d, 0);
-        if (d == A.n_items - 1) {                       // this warp completed the evaluation: it runs the serial phase
-            __threadfence_block();
+        if (d == n_total - 1) {                         // this warp completed the hand-out: it runs the serial phase
+            cta_fence();
             sm_serial_phase<PRECISE>(A, V, sid, -1);
         }
         rot = sid + 1; if (rot >= K) rot = 0;
