@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- Metropolis Monte-Carlo hot path: MC steps/s and atom-pair evaluations/s on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config 2|3] [--chain-steps S]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config 2|3|5] [--chain-steps S]
 
 One bench "step" = one pass of the hot path over one batch of synthetic input: every ligand chain of
 the workload runs `chain_steps` (default 10 000) Metropolis iterations (metropolis.go:119-134) against
@@ -10,6 +10,9 @@ the synthetic 5 000-atom receptor (BASELINE.json configs[1]):
   config 2 (default, the N=1 headline): 1024 ligands x 40 atoms x 1 chain per GPU.  With N > 1 every rank
            runs its own 1024 ligands (ligand indices rank*1024 ...): weak scaling, no data-path collective.
   config 3: 4096 ligands x 8 replica chains, sharded over the N ranks by contiguous ligand blocks (strong).
+  config 5: virtual-screen sweep, 100 000 ligands of 20..80 atoms (1 chain each), sharded over the N ranks (strong),
+           followed by the batched RMSD validation (CompareRMSD of every chain, device-resident): the line gains an
+           "rmsd" object with the RMSD kernel's GB/s against the measured HBM peak.  Default chain_steps 1000.
 
 `value`  = MC steps/s, whole job, chains resident in HBM (ddd_screen_*), max over ranks of the device time.
 `e2e`    = the same metric through the reference-facing call (ddd_minimize_batch = SimulateMultipleLigands-
@@ -19,7 +22,9 @@ the synthetic 5 000-atom receptor (BASELINE.json configs[1]):
            own launch stream) against the FP32 FMA-pipe peak SMs*128*2*f_max (f_max = sm_max_mhz from
            MEASURED_PEAKS.json); the binding pipe is MUFU.RSQ (16/clk/SM = 75 % of that peak).
 `cpu_baseline` = the C float64 restatement of the reference (oracle/, "port": NOT Go -- there is no Go
-           toolchain) timed on this box's host cores on a bounded sample of the same workload.
+           toolchain) timed on this box's host cores on a bounded sample of the same workload.  Its `value` is the
+           build that squares through the restated Go math.Pow (what metropolis.go:253 executes; bit-identical
+           results); the plain x*x build (faster than Go can be) and the glibc-pow build are reported beside it.
 --impl reference times that restatement alone (rank 0 only), same metric/config/units.
 """
 from __future__ import annotations
@@ -49,10 +54,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3])
-    ap.add_argument("--chain-steps", type=int, default=10000)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5])
+    ap.add_argument("--chain-steps", type=int, default=0, help="MC steps per chain (default 10000; config 5: 1000)")
     ap.add_argument("--ligands", type=int, default=0, help="override ligands per GPU (config 2) / total (config 3)")
-    ap.add_argument("--chain-threads", type=int, default=0, help="force the chain CTA width (0 = auto)")
+    ap.add_argument("--chain-threads", type=int, default=0, help="one-CTA-per-chain engine with this CTA width (0 = SM-persistent engine)")
+    ap.add_argument("--chain-slots", type=int, default=0, help="SM-persistent engine: chains resident per SM (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -69,6 +75,10 @@ def workload(config, rank, world, n_override):
     if config == 2:
         n = n_override or 1024
         return rank * n, n, 1, f"synthetic {NP}-atom receptor x {n} ligands x {NL} atoms per GPU, 1 chain each"
+    if config == 5:
+        total = n_override or 100000
+        lo, hi = rank * total // world, (rank + 1) * total // world
+        return lo, hi - lo, 1, f"virtual-screen sweep: synthetic {NP}-atom receptor x {total} ligands of 20..80 atoms, 1 chain each, sharded; then batched RMSD"
     total = n_override or 4096
     lo, hi = rank * total // world, (rank + 1) * total // world
     return lo, hi - lo, 8, f"synthetic {NP}-atom receptor x {total} ligands x {NL} atoms x 8 replica chains, sharded"
@@ -130,6 +140,8 @@ def cpu_oracle_rate(prot, off, lig, seconds, variant=""):
 
 def main():
     args = parse_args()
+    if not args.chain_steps:
+        args.chain_steps = 1000 if args.config == 5 else 10000
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -150,18 +162,21 @@ def main():
         per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
         rates = []
         for i in range(args.warmup + args.steps):
-            r, cores, sample, pr = cpu_oracle_rate(prot, off, lig, per_step)
+            r, cores, sample, pr = cpu_oracle_rate(prot, off, lig, per_step, "gopow")
             if i >= args.warmup:
                 rates.append((r, pr, sample))
         v = float(np.mean([r[0] for r in rates]))
+        r_xx, _, sample_xx, _ = cpu_oracle_rate(prot, off, lig, min(per_step, 6.0))
         out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "pair_evals_per_sec": float(np.mean([r[1] for r in rates])),
                "config": {"workload": desc, "chain_steps": args.chain_steps, "rotate": True, "temperature": TEMPERATURE,
-                          "note": "reference = C float64 restatement of metropolis.go on host cores (no Go toolchain in this image); "
-                                  "each step is a bounded sample of the workload"},
-               "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": rates[-1][2]},
+                          "note": "reference = C float64 restatement of metropolis.go on host cores (no Go toolchain in this image), "
+                                  "squares through the restated Go math.Pow as metropolis.go:253 does; each step is a bounded sample of the workload"},
+               "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": rates[-1][2],
+                                "xx_variant_value": r_xx,
+                                "note": "xx_variant = the same restatement with x*x instead of math.Pow(x, 2): identical bits, faster than the Go program can be"},
                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "gpu_launches": 0}
         print(json.dumps(out))
@@ -178,7 +193,11 @@ def main():
     capi.init([local_rank])
     info = capi.device_info(0)
 
-    sizes = [NL] * n_lig
+    if args.config == 5:
+        total = args.ligands or 100000
+        sizes = synth.sweep_sizes(total)[first:first + n_lig].tolist()
+    else:
+        sizes = [NL] * n_lig
     off, lig = synth.make_ligands(sizes, prot, first_index=first)
     rec = capi.Receptor(prot)
     prm = capi.default_params()                       # F32 pair sum, REFERENCE move, reference constants
@@ -208,6 +227,8 @@ def main():
     scr = capi.Screen(rec, off, lig, replicas, first_chain_id=first_chain)
     if args.chain_threads:
         scr.set_chain_threads(args.chain_threads)
+    if args.chain_slots:
+        scr.set_chain_slots(args.chain_slots)
     for w in range(args.warmup):
         scr.run(args.chain_steps, True, TEMPERATURE, prm, seed=100 + w)
         scr.sync()
@@ -225,16 +246,26 @@ def main():
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     _, st = scr.download()
+    rmsd_info = None
+    if args.config == 5:                              # batched RMSD validation of the sweep (TestMethodRMSD shape), device-resident
+        scr.rmsd()
+        r_all, r_ms = scr.rmsd()
+        r_bytes = 2.0 * 32.0 * float(off[-1]) * replicas + 8.0 * n_lig * replicas      # two 32-byte atoms per ligand atom + one result
+        rmsd_info = {"pairs": int(n_lig * replicas), "kernel_ms": r_ms, "bytes": r_bytes, "finite": bool(np.all(np.isfinite(r_all)))}
     my_steps = float(st["steps"].sum()) * 1.0         # steps of the LAST bench step, all chains of this rank
     assert my_steps == n_lig * replicas * args.chain_steps, "chains stopped early"
     assert not np.any(st["status"]), "chain status flags set"
-    width = scr.chain_threads()
+    width, slots = scr.chain_threads(), scr.chain_slots()
     scr.close()
     dev_s = max_over_ranks(kernel_ms * 1e-3)          # max over ranks of the device time of K steps
     wall_s = max_over_ranks(wall)
     total_steps = sum_over_ranks(my_steps) * args.steps
-    total_pairs = total_steps * NP * NL
+    my_pairs = float((st["steps"] * np.repeat(np.diff(off), replicas)).sum()) * NP      # sum_chains steps * nP * nL_chain
+    total_pairs = sum_over_ranks(my_pairs) * args.steps
     value = total_steps / dev_s
+    if rmsd_info is not None:
+        rmsd_info["kernel_ms"] = max_over_ranks(rmsd_info["kernel_ms"])
+        rmsd_info["bytes"] = sum_over_ranks(rmsd_info["bytes"]); rmsd_info["pairs"] = int(sum_over_ranks(rmsd_info["pairs"]))
 
     # ---- end to end through the reference-facing call with pinned host buffers
     pin_lig = torch.empty(lig.shape, dtype=torch.float64).pin_memory()
@@ -267,20 +298,30 @@ def main():
     achieved = FLOP_PER_PAIR * total_pairs / dev_s / 1e12 / world                     # per GPU
     cpu = None
     if not args.no_cpu_baseline:
-        r, cores, sample, pr = cpu_oracle_rate(prot, off[:min(n_lig, 64) + 1], lig[:off[min(n_lig, 64)]], 12.0)
-        rp, _, sample_p, _ = cpu_oracle_rate(prot, off[:min(n_lig, 64) + 1], lig[:off[min(n_lig, 64)]], 6.0, "pow")
+        sub = (off[:min(n_lig, 64) + 1], lig[:off[min(n_lig, 64)]])
+        r, cores, sample, pr = cpu_oracle_rate(prot, sub[0], sub[1], 12.0, "gopow")
+        rx, _, _, _ = cpu_oracle_rate(prot, sub[0], sub[1], 6.0)
+        rp, _, _, _ = cpu_oracle_rate(prot, sub[0], sub[1], 4.0, "pow")
         cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "pair_evals_per_sec": pr,
-               "pow_variant_value": rp,
-               "note": "C float64 restatement of metropolis.go (x*x squares), NOT Go; pow_variant mimics the cost of Go's out-of-line math.Pow"}
+               "xx_variant_value": rx, "libm_pow_variant_value": rp,
+               "note": "C float64 restatement of metropolis.go, NOT Go (no Go toolchain here), one thread per chain on all host cores. "
+                       "value: squares through the restated Go math.Pow (pow.go/frexp.go/ldexp.go, out of line), i.e. the arithmetic "
+                       "metropolis.go:253 executes; xx_variant: x*x (same bits, faster than Go can be); libm_pow_variant: glibc pow()"}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_s * 1e3 / args.steps, "higher_is_better": True,
         "scaling": "weak" if args.config == 2 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        **({"rmsd": {"pairs": rmsd_info["pairs"], "kernel_ms": rmsd_info["kernel_ms"], "algorithmic_bytes": rmsd_info["bytes"],
+                     "achieved_gbs": rmsd_info["bytes"] / (rmsd_info["kernel_ms"] * 1e-3) / 1e9 / world, "peak_gbs": peaks.get("hbm_gbs"),
+                     "frac": rmsd_info["bytes"] / (rmsd_info["kernel_ms"] * 1e-3) / 1e9 / world / peaks.get("hbm_gbs", 6540.8),
+                     "bound": "hbm", "note": "CalculateRMSD of every chain (final vs start pose), Go []Atom layout (32 B/atom), device-resident"}}
+           if rmsd_info else {}),
         "pair_evals_per_sec": total_pairs / dev_s,
-        "config": {"workload": desc, "receptor_atoms": NP, "ligand_atoms": NL, "ligands_per_gpu": n_lig, "replicas": replicas,
+        "config": {"workload": desc, "receptor_atoms": NP, "ligand_atoms": NL if args.config != 5 else "20..80", "ligands_per_gpu": n_lig, "replicas": replicas,
                    "chain_steps": args.chain_steps, "rotate": True, "temperature": TEMPERATURE, "move": "REFERENCE",
-                   "pair_precision": "fp32 terms, fp64 accumulation", "chain_cta_threads": width,
+                   "pair_precision": "fp32 terms, fp64 accumulation", "chain_cta_threads": width, "chains_per_sm": slots,
+                   "engine": "SM-persistent (one CTA per SM, speculative proposals)" if slots else "one CTA per chain",
                    "l2": "receptor (80 KB) and poses are L1/L2-resident by design; the kernel is FP32/MUFU-bound, HBM traffic ~0, so no L2 flush applies",
                    "parallelism": f"{world} x independent chain shards, no collective"},
         "wall_ms_per_step": wall_s * 1e3 / args.steps,

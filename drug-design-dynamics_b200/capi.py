@@ -21,7 +21,7 @@ SYMBOLS = [
     "ddd_closest_atom_batch", "ddd_shift_closer_batch", "ddd_randomize_pose_batch",
     "ddd_screen_create", "ddd_screen_run", "ddd_screen_sync", "ddd_screen_last_kernel_ms",
     "ddd_screen_download", "ddd_screen_destroy", "ddd_screen_set_chain_threads", "ddd_screen_chain_threads",
-    "ddd_screen_set_chain_slots", "ddd_screen_chain_slots",
+    "ddd_screen_set_chain_slots", "ddd_screen_chain_slots", "ddd_screen_rmsd",
     "ddd_shard_plan", "ddd_device_info",
     "ddd_chain_kernel_info",
 ]
@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
         "ddd_screen_chain_threads": (i32, [vp]),
         "ddd_screen_set_chain_slots": (C.c_int, [vp, i32]),
         "ddd_screen_chain_slots": (i32, [vp]),
+        "ddd_screen_rmsd": (C.c_int, [vp, vp, C.POINTER(dbl)]),
         "ddd_screen_last_kernel_ms": (dbl, [vp]),
         "ddd_screen_download": (C.c_int, [vp, vp, vp]),
         "ddd_screen_destroy": (C.c_int, [vp]),
@@ -361,6 +362,13 @@ class Screen:
         stats = np.zeros(self.n_chains, dtype=STATS_DTYPE)
         _check(lib().ddd_screen_download(self._h, _ptr(out), _ptr(stats)))
         return out, stats
+
+    def rmsd(self):
+        """CompareRMSD per chain (final pose vs the ligand's start pose), device-resident; returns (rmsd[n_chains], kernel ms)."""
+        out = np.zeros(self.n_chains)
+        ms = C.c_double()
+        _check(lib().ddd_screen_rmsd(self._h, _ptr(out), C.byref(ms)))
+        return out, ms.value
 
     def close(self):
         if self._h:

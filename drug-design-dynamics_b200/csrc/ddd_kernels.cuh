@@ -770,6 +770,31 @@ __global__ void __launch_bounds__(256) rmsd_batch_kernel(const long long *__rest
     if (lane == 0) out[pair] = sqrt(acc / (double)n);                         // :64 (n == 0 -> NaN)
 }
 
+// CalculateRMSD (validateResults.go:50-65) of every chain of a resident screen: final pose (chain-major output) against
+// the ligand's start pose, without leaving the device.  One warp per chain, 32-byte atoms (Go layout) read as double4.
+__global__ void __launch_bounds__(256) rmsd_chains_kernel(const long long *__restrict__ offsets, const double *__restrict__ start_xyzq,
+                                                          long long atom_base, const double *__restrict__ final_xyzq, long long out_base,
+                                                          long long chain_begin, long long n_local, int replicas, double *__restrict__ out) {
+    const long long local = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (local >= n_local) return;
+    const int lane = threadIdx.x & 31;
+    const long long chain = chain_begin + local;
+    const long long lig = chain / replicas;
+    const int rep = (int)(chain - lig * replicas);
+    const long long off = offsets[lig];
+    const int n = (int)(offsets[lig + 1] - off);
+    const double4 *r4 = reinterpret_cast<const double4 *>(start_xyzq) + (off - atom_base);
+    const double4 *s4 = reinterpret_cast<const double4 *>(final_xyzq) + ((long long)replicas * off + (long long)rep * n - out_base);
+    double acc = 0.0;
+    for (int i = lane; i < n; i += 32) {
+        const double4 sa = s4[i], ra = r4[i];
+        const double dx = sa.x - ra.x, dy = sa.y - ra.y, dz = sa.z - ra.z;
+        acc += dx * dx + dy * dy + dz * dz;                               // :58-62
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[local] = sqrt(acc / (double)n);                    // :64 (n == 0 -> NaN)
+}
+
 // ------------------------------------------------------------------ RandomizeLigandPose (validateResults.go:70-79)
 __global__ void __launch_bounds__(kThreads) randomize_pose_kernel(const long long *offsets, double *lig_xyzq,
                                                                   uint64_t seed, uint64_t first_index) {

@@ -142,6 +142,8 @@ struct ScreenDev {
     int threads = 0;                       // CTA width used by the last launch
     int slots = 0;                         // chains resident per SM in the last launch (0: one-CTA-per-chain engine)
     int *d_queue = nullptr;                // SM-persistent engine: dynamic chain counter
+    double *d_rmsd = nullptr;              // per-chain RMSD (ddd_screen_rmsd)
+    float rmsd_ms = 0.f;
 };
 
 struct ddd_screen {
@@ -202,7 +204,7 @@ void plan_shards(const int64_t *offsets, int64_t n_lig, int replicas, int n_shar
 void free_screen_dev(ScreenDev &sd) {
     cudaSetDevice(g_devs[sd.di].id);
     cudaFree(sd.d_offsets); cudaFree(sd.d_lig); cudaFree(sd.d_order); cudaFree(sd.d_out);
-    cudaFree(sd.d_stats); cudaFree(sd.d_trace); cudaFree(sd.d_rec); cudaFree(sd.d_rec_off); cudaFree(sd.d_queue);
+    cudaFree(sd.d_stats); cudaFree(sd.d_trace); cudaFree(sd.d_rec); cudaFree(sd.d_rec_off); cudaFree(sd.d_queue); cudaFree(sd.d_rmsd);
     sd = ScreenDev();
 }
 
@@ -844,6 +846,38 @@ int ddd_screen_download(ddd_screen *s, double *out_xyzq, ddd_chain_stats *out_st
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     REQUIRE_INIT();
     return screen_download_impl(s, out_xyzq, out_stats, nullptr);
+}
+
+// CompareRMSD (validateResults.go:40-45) for every chain of the screen, device-resident: CalculateRMSD(final pose of the
+// chain, start pose of its ligand).  out_rmsd[n_chains]; the kernel time is returned through out_kernel_ms (nullable).
+int ddd_screen_rmsd(ddd_screen *s, double *out_rmsd, double *out_kernel_ms) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    REQUIRE_INIT();
+    if (!s) return fail(DDD_EINVAL, "screen is NULL");
+    if (!s->launched) return fail(DDD_EINVAL, "screen has not been run");
+    if (!out_rmsd && s->n_chains > 0) return fail(DDD_EINVAL, "out_rmsd is NULL");
+    for (auto &d : s->devs) {
+        const Dev &dev = g_devs[d.di];
+        CUDA_TRY(cudaSetDevice(dev.id));
+        const int64_t n_local = d.c1 - d.c0;
+        if (!d.d_rmsd) { if (int rc = dev_alloc(&d.d_rmsd, (size_t)n_local)) return rc; }
+        CUDA_TRY(cudaEventRecord(dev.ev0, dev.stream));
+        rmsd_chains_kernel<<<(unsigned)((n_local + 7) / 8), 256, 0, dev.stream>>>(d.d_offsets, d.d_lig, d.atom_base, d.d_out, d.out_base,
+                                                                               d.c0, n_local, s->replicas, d.d_rmsd);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(dev.ev1, dev.stream));
+        CUDA_TRY(cudaMemcpyAsync(out_rmsd + d.c0, d.d_rmsd, sizeof(double) * (size_t)n_local, cudaMemcpyDeviceToHost, dev.stream));
+    }
+    double mx = 0.0;
+    for (auto &d : s->devs) {
+        const Dev &dev = g_devs[d.di];
+        CUDA_TRY(cudaSetDevice(dev.id));
+        CUDA_TRY(cudaStreamSynchronize(dev.stream));
+        CUDA_TRY(cudaEventElapsedTime(&d.rmsd_ms, dev.ev0, dev.ev1));
+        mx = std::max(mx, (double)d.rmsd_ms);
+    }
+    if (out_kernel_ms) *out_kernel_ms = mx;
+    return DDD_OK;
 }
 
 int ddd_screen_destroy(ddd_screen *s) {

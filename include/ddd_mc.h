@@ -175,6 +175,10 @@ int    ddd_screen_run(ddd_screen *s, int64_t steps_per_chain, int32_t rotate, do
 int    ddd_screen_sync(ddd_screen *s);
 double ddd_screen_last_kernel_ms(const ddd_screen *s);
 int    ddd_screen_download(ddd_screen *s, double *out_xyzq, ddd_chain_stats *out_stats);
+/* CompareRMSD (validateResults.go:40-45) for every chain of the screen without leaving the device:
+ * out_rmsd[c] = CalculateRMSD(final pose of chain c, start pose of its ligand) (validateResults.go:50-65).
+ * out_kernel_ms (nullable): CUDA-event time of the RMSD kernel, max over devices. */
+int    ddd_screen_rmsd(ddd_screen *s, double *out_rmsd, double *out_kernel_ms);
 int    ddd_screen_destroy(ddd_screen *s);
 
 /* ---- sharding plan (pure host logic, works without a device): chains

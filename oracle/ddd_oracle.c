@@ -150,7 +150,122 @@ int orc_is_collision_free(const orc_atom *lig, int64_t nl, double min_distance) 
     return 1;
 }
 
-#ifdef ORC_SQUARE_VIA_POW
+/* ------------------------------------------------------------------ Go math.Pow (third-party to the reference)
+ * metropolis.go:253 squares through math.Pow(x, 2).  The Go standard library is not under /root/reference and
+ * its version is unpinned (go.mod is git-ignored; go1.23.0 inferred from the one shipped binary);
+ * on amd64 math.Pow, math.Frexp, math.Ldexp and math.Modf are the portable Go functions of src/math/pow.go,
+ * frexp.go, ldexp.go, modf.go (no assembly stubs), none of them inlinable.  Their published algorithm is restated
+ * here so that (i) the claim "math.Pow(x, 2) == x*x bit for bit" is tested instead of assumed
+ * (tests/test_oracle_reference_kats.py) and (ii) the CPU baseline can be timed with the arithmetic the Go
+ * program really executes (-DORC_SQUARE_VIA_GOPOW).  noinline mirrors Go's call structure. */
+#define GO_SHIFT 52
+#define GO_MASK  0x7FFull
+#define GO_BIAS  1023
+static inline uint64_t go_bits(double f) { uint64_t u; memcpy(&u, &f, 8); return u; }
+static inline double go_frombits(uint64_t u) { double f; memcpy(&f, &u, 8); return f; }
+
+static inline double go_normalize(double x, int *e) {                 /* bits.go normalize */
+    if (fabs(x) < 2.2250738585072014e-308) { *e = -52; return x * 4503599627370496.0; }
+    *e = 0;
+    return x;
+}
+
+double orc_go_frexp(double f, int *exp_out) {  /* frexp.go */
+    if (f == 0 || isinf(f) || isnan(f)) { *exp_out = 0; return f; }
+    int e;
+    f = go_normalize(f, &e);
+    uint64_t x = go_bits(f);
+    e += (int)((x >> GO_SHIFT) & GO_MASK) - GO_BIAS + 1;
+    x &= ~(GO_MASK << GO_SHIFT);
+    x |= (uint64_t)(-1 + GO_BIAS) << GO_SHIFT;
+    *exp_out = e;
+    return go_frombits(x);
+}
+
+double orc_go_ldexp(double frac, int exp_) {   /* ldexp.go */
+    if (frac == 0 || isinf(frac) || isnan(frac)) return frac;
+    int e;
+    frac = go_normalize(frac, &e);
+    exp_ += e;
+    uint64_t x = go_bits(frac);
+    exp_ += (int)((x >> GO_SHIFT) & GO_MASK) - GO_BIAS;
+    if (exp_ < -1075) return copysign(0.0, frac);                     /* underflow */
+    if (exp_ > 1023) return frac < 0 ? -INFINITY : INFINITY;          /* overflow */
+    double m = 1;
+    if (exp_ < -1022) { exp_ += 53; m = 1.0 / 9007199254740992.0; }   /* denormal */
+    x &= ~(GO_MASK << GO_SHIFT);
+    x |= (uint64_t)(exp_ + GO_BIAS) << GO_SHIFT;
+    return m * go_frombits(x);
+}
+
+double orc_go_modf(double f, double *frac) {   /* modf.go */
+    if (f < 1) {
+        if (f < 0) { double fr; const double ip = orc_go_modf(-f, &fr); *frac = -fr; return -ip; }
+        if (f == 0) { *frac = f; return f; }
+        *frac = f;
+        return 0;
+    }
+    uint64_t x = go_bits(f);
+    const unsigned e = (unsigned)((x >> GO_SHIFT) & GO_MASK) - GO_BIAS;
+    if (e < 64 - 12) x &= ~((1ull << (64 - 12 - e)) - 1);             /* keep the top 12+e bits: the integer part */
+    const double ip = go_frombits(x);
+    *frac = f - ip;
+    return ip;
+}
+
+static int go_is_odd_int(double x) {
+    double fr;
+    const double xi = orc_go_modf(x, &fr);
+    return fr == 0 && ((int64_t)xi & 1) == 1;
+}
+
+__attribute__((noinline)) double orc_go_pow(double x, double y) {         /* pow.go */
+    if (y == 0 || x == 1) return 1;
+    if (y == 1) return x;
+    if (isnan(x) || isnan(y)) return NAN;
+    if (x == 0) {
+        if (y < 0) return (signbit(x) && go_is_odd_int(y)) ? copysign(INFINITY, x) : INFINITY;
+        return (signbit(x) && go_is_odd_int(y)) ? x : 0;
+    }
+    if (isinf(y)) {
+        if (x == -1) return 1;
+        return ((fabs(x) < 1) == (y > 0)) ? 0 : INFINITY;
+    }
+    if (isinf(x)) {
+        if (x < 0) return orc_go_pow(1 / x, -y);
+        return y < 0 ? 0 : INFINITY;
+    }
+    if (y == 0.5) return sqrt(x);
+    if (y == -0.5) return 1 / sqrt(x);
+    double yf;
+    double yi = orc_go_modf(fabs(y), &yf);
+    if (yf != 0 && x < 0) return NAN;
+    if (yi >= 9.223372036854775808e18) {
+        if (x == -1) return 1;
+        return ((fabs(x) < 1) == (y > 0)) ? 0 : INFINITY;
+    }
+    double a1 = 1.0;                                                   /* ans = a1 * 2**ae */
+    int ae = 0;
+    if (yf != 0) {
+        if (yf > 0.5) { yf--; yi++; }
+        a1 = exp(yf * log(x));
+    }
+    int xe;
+    double x1 = orc_go_frexp(x, &xe);
+    for (int64_t i = (int64_t)yi; i != 0; i >>= 1) {
+        if (xe < -(1 << 12) || (1 << 12) < xe) { ae += xe; break; }   /* catastrophic overflow */
+        if (i & 1) { a1 *= x1; ae += xe; }
+        x1 *= x1;
+        xe <<= 1;
+        if (x1 < .5) { x1 += x1; xe--; }
+    }
+    if (y < 0) { a1 = 1 / a1; ae = -ae; }
+    return orc_go_ldexp(a1, ae);
+}
+
+#if defined(ORC_SQUARE_VIA_GOPOW)
+#define ORC_SQ(x) orc_go_pow((x), 2)
+#elif defined(ORC_SQUARE_VIA_POW)
 #define ORC_SQ(x) pow((x), 2)
 #else
 #define ORC_SQ(x) ((x) * (x))     /* math.Pow(x,2) == x*x bit for bit */
@@ -581,7 +696,9 @@ double orc_bench_chains(const orc_atom *prot, int64_t np, const orc_atom *lig,
 }
 
 const char *orc_build_info(void) {
-#ifdef ORC_SQUARE_VIA_POW
+#if defined(ORC_SQUARE_VIA_GOPOW)
+    return "ddd_oracle C float64 restatement (NOT Go); squares via the restated Go math.Pow (pow.go/frexp.go/ldexp.go)";
+#elif defined(ORC_SQUARE_VIA_POW)
     return "ddd_oracle C float64 restatement (NOT Go); squares via out-of-line pow()";
 #else
     return "ddd_oracle C float64 restatement (NOT Go); squares as x*x";

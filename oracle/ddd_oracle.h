@@ -167,6 +167,12 @@ double orc_bench_chains(const orc_atom *prot, int64_t np, const orc_atom *lig,
                         const orc_params *p, uint64_t seed, int n_threads,
                         int64_t *total_steps, int64_t *total_pairs);
 
+/* Go standard library math.Pow / Frexp / Ldexp / Modf restated (go1.23 src/math; third-party to the reference) */
+double orc_go_pow(double x, double y);
+double orc_go_frexp(double f, int *exp_out);
+double orc_go_ldexp(double frac, int exp_);
+double orc_go_modf(double f, double *frac);
+
 const char *orc_build_info(void);
 
 #ifdef __cplusplus

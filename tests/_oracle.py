@@ -55,7 +55,7 @@ def _atoms(a):
 
 class Oracle:
     def __init__(self, variant: str = ""):
-        name = "libddd_oracle_pow.so" if variant == "pow" else "libddd_oracle.so"
+        name = {"pow": "libddd_oracle_pow.so", "gopow": "libddd_oracle_gopow.so"}.get(variant, "libddd_oracle.so")
         path = ORACLE_DIR / name
         src_m = max((ORACLE_DIR / f).stat().st_mtime for f in ("ddd_oracle.c", "ddd_oracle.h"))
         if not path.exists() or path.stat().st_mtime < src_m:
@@ -94,6 +94,10 @@ class Oracle:
             "orc_parse_mol2": (i64, [C.c_char_p, vp, i64]),
             "orc_bench_chains": (d, [vp, i64, vp, vp, i64, C.c_int, i64, C.c_int, d, PP, u64, C.c_int, vp, vp]),
             "orc_build_info": (C.c_char_p, []),
+            "orc_go_pow": (d, [d, d]),
+            "orc_go_frexp": (d, [d, C.POINTER(C.c_int)]),
+            "orc_go_ldexp": (d, [d, C.c_int]),
+            "orc_go_modf": (d, [d, C.POINTER(d)]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)

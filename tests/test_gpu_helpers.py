@@ -110,3 +110,21 @@ def test_reference_api_mirror_reads_like_the_go_tests(gpu, ddd):
     keep = mk(mock_ligand())
     M.SimulateEnergyMinimizationParallel(protein, keep, 400, True, 300.0, 4)
     assert np.array_equal(keep.xyzq, mock_ligand())
+
+
+def test_screen_rmsd_is_compare_rmsd_without_leaving_the_device(gpu, orc, synth_small):
+    # CompareRMSD (validateResults.go:40-45): chains, then CalculateRMSD(final pose, start pose) per chain
+    prot, off, lig = synth_small
+    with gpu.Receptor(prot) as rec:
+        scr = gpu.Screen(rec, off, lig, 3)
+        scr.run(80, True, 310.15, gpu.default_params(), seed=4)
+        poses, stats = scr.download()
+        r, ms = scr.rmsd()
+        scr.close()
+    assert ms > 0 and r.shape == (3 * (len(off) - 1),)
+    for c in range(len(r)):
+        li, rep = divmod(c, 3)
+        ref = lig[off[li]:off[li + 1]]
+        want = orc.rmsd(gpu.chain_pose(off, 3, poses, li, rep), ref)
+        assert r[c] == pytest.approx(want, rel=1e-13, abs=0) or (r[c] == 0.0 and want == 0.0)
+    assert np.all((r > 0) == (stats["accepted"] > 0))

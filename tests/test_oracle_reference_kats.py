@@ -118,3 +118,45 @@ def test_num_procs_zero_is_an_error(orc):
     # Go: iterations / numProcs panics with integer divide by zero (metropolis.go:97)
     rc, *_ = orc.minimize_parallel(mock_protein(1, 1), mock_ligand(), 10, True, 300.0, 0, seed=1)
     assert rc != 0
+
+
+# ---- Go standard library math.Pow (metropolis.go:253 calls it; third-party to the reference, restated in oracle/)
+def test_go_pow_square_is_one_rounded_multiply(orc):
+    # math.Pow(x, 2) == x*x bit for bit (frexp, one rounded multiply of the mantissas, ldexp)
+    import ctypes as C
+    import math
+    rng = np.random.default_rng(7)
+    xs = np.concatenate([rng.normal(0, 40, 4000), rng.uniform(-1e-3, 1e-3, 1000), 10.0 ** rng.uniform(-150, 150, 1000),
+                         [0.5, -0.5, 1.0, -1.0, 3.0, 1e-160, 1.5e154, 7.0e-155]])
+    for x in xs:
+        assert orc.L.orc_go_pow(float(x), 2.0) == float(x) * float(x), x
+    # documented special cases of pow.go and a few general values against libm (<= 1 ulp)
+    P = orc.L.orc_go_pow
+    assert P(5.0, 0.0) == 1.0 and P(1.0, float("nan")) == 1.0 and P(3.0, 1.0) == 3.0
+    assert math.isnan(P(float("nan"), 2.0)) and math.isnan(P(-8.0, 1.0 / 3.0))
+    assert P(0.0, -1.0) == float("inf") and P(-0.0, -3.0) == float("-inf") and P(-0.0, 3.0) == 0.0
+    assert P(2.0, float("inf")) == float("inf") and P(0.5, float("inf")) == 0.0 and P(-1.0, float("inf")) == 1.0
+    assert P(float("inf"), -2.0) == 0.0 and P(float("-inf"), 3.0) == float("-inf")
+    assert P(2.0, 0.5) == math.sqrt(2.0) and P(4.0, -0.5) == 0.5
+    assert P(2.0, 10.0) == 1024.0 and P(2.0, -2.0) == 0.25 and P(-3.0, 3.0) == -27.0
+    for x, y in [(1.7, 2.5), (9.1, -1.25), (0.3, 7.0), (123.456, 0.75)]:
+        assert P(x, y) == pytest.approx(x ** y, rel=4e-16)
+    e = C.c_int()
+    assert orc.L.orc_go_frexp(8.0, C.byref(e)) == 0.5 and e.value == 4
+    assert orc.L.orc_go_frexp(5e-324, C.byref(e)) == 0.5 and e.value == -1073
+    assert orc.L.orc_go_ldexp(0.75, 3) == 6.0 and orc.L.orc_go_ldexp(0.5, -1073) == 5e-324
+    fr = C.c_double()
+    assert orc.L.orc_go_modf(-3.25, C.byref(fr)) == -3.0 and fr.value == -0.25
+
+
+def test_gopow_build_is_bit_identical_to_the_oracle():
+    # the -DORC_SQUARE_VIA_GOPOW build (the arithmetic Go executes) is a COST model only: same bits as x*x
+    from _oracle import Oracle
+    a, b = Oracle(), Oracle("gopow")
+    prot = np.array([[0.0, 0, 0, 0.3], [1.5, -2, 0.25, -0.41], [7.0, 3, -1, 0.2]])
+    lig = np.array([[4.0, 4, 4, 1.0], [3.0, 3, 3, -1.0], [2.5, 3.5, 4.25, 0.17]])
+    assert a.energy(prot, lig) == b.energy(prot, lig)
+    pa, sa = a.chain(prot, lig, 200, True, 310.15, a.philox_stream(3, 0))
+    pb, sb = b.chain(prot, lig, 200, True, 310.15, b.philox_stream(3, 0))
+    assert np.array_equal(pa, pb) and sa == sb
+    assert "Go math.Pow" in b.build_info()
