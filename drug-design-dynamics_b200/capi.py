@@ -21,7 +21,7 @@ SYMBOLS = [
     "ddd_closest_atom_batch", "ddd_shift_closer_batch", "ddd_randomize_pose_batch",
     "ddd_screen_create", "ddd_screen_run", "ddd_screen_sync", "ddd_screen_last_kernel_ms",
     "ddd_screen_download", "ddd_screen_destroy", "ddd_screen_set_chain_threads", "ddd_screen_chain_threads",
-    "ddd_screen_set_chain_slots", "ddd_screen_chain_slots", "ddd_screen_rmsd",
+    "ddd_screen_set_chain_slots", "ddd_screen_chain_slots", "ddd_screen_rmsd", "ddd_screen_pair_units",
     "ddd_shard_plan", "ddd_device_info",
     "ddd_chain_kernel_info",
 ]
@@ -48,6 +48,7 @@ class Params(C.Structure):
         ("max_angle", C.c_double), ("jitter_width", C.c_double), ("clamp_distance", C.c_double),
         ("rigid_translation", C.c_double), ("rigid_angle", C.c_double),
         ("max_retries", C.c_int64), ("precision", C.c_int32), ("move_mode", C.c_int32),
+        ("cutoff", C.c_double),
     ]
 
 
@@ -108,6 +109,7 @@ def lib() -> C.CDLL:
         "ddd_screen_set_chain_slots": (C.c_int, [vp, i32]),
         "ddd_screen_chain_slots": (i32, [vp]),
         "ddd_screen_rmsd": (C.c_int, [vp, vp, C.POINTER(dbl)]),
+        "ddd_screen_pair_units": (C.c_int, [vp, vp]),
         "ddd_screen_last_kernel_ms": (dbl, [vp]),
         "ddd_screen_download": (C.c_int, [vp, vp, vp]),
         "ddd_screen_destroy": (C.c_int, [vp]),
@@ -362,6 +364,12 @@ class Screen:
         stats = np.zeros(self.n_chains, dtype=STATS_DTYPE)
         _check(lib().ddd_screen_download(self._h, _ptr(out), _ptr(stats)))
         return out, stats
+
+    def pair_units(self):
+        """cutoff extension: receptor atoms visited by each chain's pair sums, summed over its evaluations"""
+        out = np.zeros(self.n_chains, dtype=np.int64)
+        _check(lib().ddd_screen_pair_units(self._h, _ptr(out)))
+        return out
 
     def rmsd(self):
         """CompareRMSD per chain (final pose vs the ligand's start pose), device-resident; returns (rmsd[n_chains], kernel ms)."""

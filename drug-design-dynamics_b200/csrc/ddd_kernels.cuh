@@ -30,6 +30,8 @@ struct DevParams {
     long long max_retries;
     float rinv_max;              // 1 / clamp_distance: clamp d >= 1e-6  <=>  1/d <= 1e6 (:255-257)
     int move_mode, rotate;
+    double cutoff;               // EXTENSION: > 0 = shifted-Coulomb cutoff radius (0: the reference's untruncated sum)
+    float rc_inv;                // 1 / cutoff (0 when off)
 };
 
 struct RecView {
@@ -37,6 +39,12 @@ struct RecView {
     const Atom64 *f64;           // absolute, n atoms
     int n, n_pad;
     double cx, cy, cz;           // receptor centroid: origin of the fp32 frame
+    // cell list for the cutoff extension: the same fp32 atoms sorted along a Morton curve of 6 A grid cells, cut into
+    // units of 32 consecutive atoms (one per lane); ubox[2u], ubox[2u+1] = (min xyz, max xyz) of unit u's real atoms
+    const float4 *f32s;
+    const Atom64 *f64s;          // the fp64 atoms in the same Morton order (absolute coordinates)
+    const float4 *ubox;
+    int n_units_s;
 };
 
 // ------------------------------------------------------------------ Philox4x32-10
@@ -177,18 +185,19 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
 // 3 FADD2, FMUL2 + 2 FFMA2 (d^2), 2 MUFU.RSQ, 2 FMNMX (clamp d >= 1e-6 <=> 1/d <= 1e6), FFMA2
 // (s += q_l / d): 11 issue slots per 2 pair terms.  MUFU (16/clk/SM) is the binding pipe.
 // q_p is applied once per tile and K once per call.  An odd ligand is padded with a q = 0 atom.
-template <int A>
-__device__ __forceinline__ float warp_tile_sum_f32(const float4 *__restrict__ rec, int base,
-                                                   const ulonglong2 *__restrict__ lf2, int n_pairs, float rinv_max) {
+// CUT (the cutoff extension): every term becomes max(min(1/d, 1/clamp) - 1/cutoff, 0) -- the shifted Coulomb term, which
+// is exactly 0 from the cutoff outwards, so no distance compare is needed: + 1 FADD2 and 2 FMNMX per ligand pair.
+// `ubase[a]` is the first atom of the a-th unit of 32 receptor atoms this call covers (units need not be adjacent).
+template <int A, bool CUT>
+__device__ __forceinline__ float warp_atoms_sum_f32(const float4 (&P)[A], const ulonglong2 *__restrict__ lf2, int n_pairs,
+                                                    float rinv_max, float rc_inv) {
     f32x2 px[A], py[A], pz[A], s[A];
-    float q[A];
-    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int a = 0; a < A; ++a) {
-        const float4 P = __ldg(rec + base + a * 32 + lane);
-        px[a] = pack2(P.x, P.x); py[a] = pack2(P.y, P.y); pz[a] = pack2(P.z, P.z);
-        q[a] = P.w; s[a] = pack2(0.f, 0.f);
+        px[a] = pack2(P[a].x, P[a].x); py[a] = pack2(P[a].y, P[a].y); pz[a] = pack2(P[a].z, P[a].z);
+        s[a] = pack2(0.f, 0.f);
     }
+    const f32x2 m_rc = pack2(-rc_inv, -rc_inv);
 #pragma unroll 2
     for (int k = 0; k < n_pairs; ++k) {
         const ulonglong2 Lxy = lf2[2 * k], Lzq = lf2[2 * k + 1];
@@ -198,14 +207,37 @@ __device__ __forceinline__ float warp_tile_sum_f32(const float4 *__restrict__ re
             const f32x2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
             float d2a, d2b;
             unpack2(d2, d2a, d2b);
-            const float ra = fminf(rsqrt_approx(d2a), rinv_max), rb = fminf(rsqrt_approx(d2b), rinv_max);
+            float ra = fminf(rsqrt_approx(d2a), rinv_max), rb = fminf(rsqrt_approx(d2b), rinv_max);
+            if (CUT) {
+                unpack2(add2(pack2(ra, rb), m_rc), ra, rb);
+                ra = fmaxf(ra, 0.f); rb = fmaxf(rb, 0.f);
+            }
             s[a] = fma2(Lzq.y, pack2(ra, rb), s[a]);
         }
     }
     float t = 0.f;                       // fp32 within the lane's A * nl terms, fp64 beyond
 #pragma unroll
-    for (int a = 0; a < A; ++a) { float sa, sb; unpack2(s[a], sa, sb); t = fmaf(q[a], sa + sb, t); }
+    for (int a = 0; a < A; ++a) { float sa, sb; unpack2(s[a], sa, sb); t = fmaf(P[a].w, sa + sb, t); }
     return t;
+}
+
+template <int A, bool CUT>
+__device__ __forceinline__ float warp_units_sum_f32(const float4 *__restrict__ rec, const int (&ubase)[A],
+                                                    const ulonglong2 *__restrict__ lf2, int n_pairs, float rinv_max, float rc_inv) {
+    float4 P[A];
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int a = 0; a < A; ++a) P[a] = __ldg(rec + ubase[a] + lane);
+    return warp_atoms_sum_f32<A, CUT>(P, lf2, n_pairs, rinv_max, rc_inv);
+}
+
+template <int A, bool CUT = false>
+__device__ __forceinline__ float warp_tile_sum_f32(const float4 *__restrict__ rec, int base,
+                                                   const ulonglong2 *__restrict__ lf2, int n_pairs, float rinv_max, float rc_inv = 0.f) {
+    int ub[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) ub[a] = base + a * 32;
+    return warp_units_sum_f32<A, CUT>(rec, ub, lf2, n_pairs, rinv_max, rc_inv);
 }
 
 // sum_p sum_l q_p q_l / max(d, clamp) for the whole CTA, returned to every thread (K applied by the caller).
@@ -220,16 +252,16 @@ __host__ __device__ constexpr int max_items(int threads) { return threads > 32 ?
 #ifndef DDD_DYNAMIC_TILES
 #define DDD_DYNAMIC_TILES 1
 #endif
-template <int THREADS>
+template <int THREADS, bool CUT = false>
 __device__ __forceinline__ double cta_pair_sum_f32(const RecView &rv, const float4 *lf, int nl, float rinv_max,
-                                                   int *ctl, double *item_out, double *red, int &parity) {
+                                                   int *ctl, double *item_out, double *red, int &parity, float rc_inv = 0.f) {
     const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
     const int n_pairs = (nl + 1) >> 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_wt = (rv.n + kWarpTile - 1) / kWarpTile;                 // n_pad is a multiple of kRecPad >= kWarpTile
     if (THREADS == 32) {                                                  // one warp: tiles in order, no staging
         double e1 = 0.0;
-        for (int t = 0; t < n_wt; ++t) e1 += (double)warp_tile_sum_f32<kTileA>(rv.f32, t * kWarpTile, lf2, n_pairs, rinv_max);
+        for (int t = 0; t < n_wt; ++t) e1 += (double)warp_tile_sum_f32<kTileA, CUT>(rv.f32, t * kWarpTile, lf2, n_pairs, rinv_max, rc_inv);
         return warp_sum(e1);
     }
     constexpr int kMaxItems = max_items(THREADS) > 0 ? max_items(THREADS) : 1;
@@ -246,7 +278,7 @@ __device__ __forceinline__ double cta_pair_sum_f32(const RecView &rv, const floa
         const int t_end = min((it + 1) * chunk, n_wt);
         double acc = 0.0;
         for (int t = it * chunk; t < t_end; ++t)
-            acc += (double)warp_tile_sum_f32<kTileA>(rv.f32, t * kWarpTile, lf2, n_pairs, rinv_max);
+            acc += (double)warp_tile_sum_f32<kTileA, CUT>(rv.f32, t * kWarpTile, lf2, n_pairs, rinv_max, rc_inv);
         item_out[it * 32 + lane] = acc;                                   // per item AND per lane: no reduction here
     }
     __syncthreads();
@@ -267,15 +299,17 @@ __device__ __forceinline__ void store_lig_f32(float4 *lf, int i, float x, float 
 template <int THREADS, bool WITH_ABS>
 __device__ __forceinline__ double pair_sum_f64(const RecView &rv, const double *lx, const double *ly,
                                                const double *lz, const double *lq, int nl,
-                                               double K, double clampd, double *abs_out) {
+                                               double K, double clampd, double *abs_out, double cutoff = 0.0) {
     double e = 0.0, ab = 0.0;
     for (int p = threadIdx.x; p < rv.n; p += THREADS) {
         const Atom64 P = rv.f64[p];
         for (int l = 0; l < nl; ++l) {
             const double ddx = P.x - lx[l], ddy = P.y - ly[l], ddz = P.z - lz[l];
             double d = sqrt(ddx * ddx + ddy * ddy + ddz * ddz);          // :253 (Pow(x,2) == x*x)
+            if (cutoff > 0 && !(d < cutoff)) continue;                    // EXTENSION: shifted-Coulomb cutoff
             if (d < clampd) d = clampd;                                   // :255-257
-            const double term = K * (P.q * lq[l]) / d;                    // :258
+            double term = K * (P.q * lq[l]) / d;                          // :258
+            if (cutoff > 0) term -= K * (P.q * lq[l]) / cutoff;
             e += term;
             if (WITH_ABS) ab += fabs(term);
         }
@@ -653,9 +687,11 @@ __global__ void __launch_bounds__(kThreads) energy_batch_kernel(const EnergyArgs
     int parity = 0;
     double part = 0.0, ab = 0.0, e;
     if (PRECISE || WITH_ABS) {
-        part = pair_sum_f64<kThreads, WITH_ABS>(a.rec, s.cx(), s.cy(), s.cz(), s.q(), nl, a.prm.k_coulomb, a.prm.clamp_distance, &ab);
+        part = pair_sum_f64<kThreads, WITH_ABS>(a.rec, s.cx(), s.cy(), s.cz(), s.q(), nl, a.prm.k_coulomb, a.prm.clamp_distance, &ab, a.prm.cutoff);
     }
     if (PRECISE) e = block_sum<kThreads>(part, s.red(), parity);
+    else if (a.prm.cutoff > 0)                          // every unit, no cell list: this entry point is not the hot path
+        e = a.prm.k_coulomb * cta_pair_sum_f32<kThreads, true>(a.rec, s.lf(), nl, a.prm.rinv_max, s.ctl(), s.item_out(), s.red(), parity, a.prm.rc_inv);
     else e = a.prm.k_coulomb * cta_pair_sum_f32<kThreads>(a.rec, s.lf(), nl, a.prm.rinv_max, s.ctl(), s.item_out(), s.red(), parity);
     if (WITH_ABS) ab = block_sum<kThreads>(ab, s.red(), parity);
     if (tid == 0) {

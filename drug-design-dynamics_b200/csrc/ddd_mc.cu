@@ -70,6 +70,8 @@ DevParams make_dev_params(const ddd_params &p, int rotate, double temperature) {
     d.max_retries = p.max_retries > 0 ? p.max_retries : (1ll << 62);
     d.rinv_max = p.clamp_distance > 0 ? (float)(1.0 / p.clamp_distance) : 3.402823466e38f;
     d.move_mode = p.move_mode; d.rotate = rotate ? 1 : 0;
+    d.cutoff = p.cutoff > 0 ? p.cutoff : 0.0;
+    d.rc_inv = p.cutoff > 0 ? (float)(1.0 / p.cutoff) : 0.f;
     return d;
 }
 
@@ -79,6 +81,7 @@ int check_params(const ddd_params *p) {
         return fail(DDD_EINVAL, "params.precision %d unknown", p->precision);
     if (p->move_mode != DDD_MOVE_REFERENCE && p->move_mode != DDD_MOVE_RIGID)
         return fail(DDD_EINVAL, "params.move_mode %d unknown", p->move_mode);
+    if (!(p->cutoff >= 0.0) || std::isinf(p->cutoff)) return fail(DDD_EINVAL, "params.cutoff must be 0 (off) or a finite radius");
     return DDD_OK;
 }
 
@@ -116,8 +119,12 @@ struct ddd_receptor {
     double cx = 0, cy = 0, cz = 0;
     std::vector<float4 *> f32;     // per device
     std::vector<Atom64 *> f64;
+    std::vector<float4 *> f32s, ubox;   // cell list (cutoff extension): Morton-sorted atoms, unit boxes
+    std::vector<Atom64 *> f64s;
+    int64_t n_units_s = 0;
     RecView view(size_t di) const {
         RecView v; v.f32 = f32[di]; v.f64 = f64[di]; v.n = (int)n; v.n_pad = (int)n_pad; v.cx = cx; v.cy = cy; v.cz = cz;
+        v.f32s = f32s[di]; v.f64s = f64s[di]; v.ubox = ubox[di]; v.n_units_s = (int)n_units_s;
         return v;
     }
 };
@@ -143,6 +150,7 @@ struct ScreenDev {
     int slots = 0;                         // chains resident per SM in the last launch (0: one-CTA-per-chain engine)
     int *d_queue = nullptr;                // SM-persistent engine: dynamic chain counter
     double *d_rmsd = nullptr;              // per-chain RMSD (ddd_screen_rmsd)
+    long long *d_units = nullptr;          // per-chain receptor units evaluated (cutoff extension)
     float rmsd_ms = 0.f;
 };
 
@@ -156,6 +164,7 @@ struct ddd_screen {
     bool launched = false;
     int threads_override = 0;              // > 0: one-CTA-per-chain engine with this CTA width
     int slots_override = 0;                // > 0: SM-persistent engine with this many chains per SM; both 0: automatic
+    bool last_cut = false;                 // the last run used the cutoff extension
 };
 
 namespace {
@@ -204,7 +213,7 @@ void plan_shards(const int64_t *offsets, int64_t n_lig, int replicas, int n_shar
 void free_screen_dev(ScreenDev &sd) {
     cudaSetDevice(g_devs[sd.di].id);
     cudaFree(sd.d_offsets); cudaFree(sd.d_lig); cudaFree(sd.d_order); cudaFree(sd.d_out);
-    cudaFree(sd.d_stats); cudaFree(sd.d_trace); cudaFree(sd.d_rec); cudaFree(sd.d_rec_off); cudaFree(sd.d_queue); cudaFree(sd.d_rmsd);
+    cudaFree(sd.d_stats); cudaFree(sd.d_trace); cudaFree(sd.d_rec); cudaFree(sd.d_rec_off); cudaFree(sd.d_queue); cudaFree(sd.d_rmsd); cudaFree(sd.d_units);
     sd = ScreenDev();
 }
 
@@ -295,6 +304,7 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
     if ((recorded == nullptr) != (recorded_offsets == nullptr) && s->n_chains > 0)
         return fail(DDD_EINVAL, "recorded and recorded_offsets must be given together");
     s->steps = steps;
+    s->last_cut = p->cutoff > 0;
     const DevParams prm = make_dev_params(*p, rotate, temperature);
     for (auto &d : s->devs) {
         const Dev &dev = g_devs[d.di];
@@ -326,13 +336,18 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
         a.out_xyzq = d.d_out; a.out_base = d.out_base; a.out_stats = d.d_stats; a.out_trace = d.d_trace;
         a.nl_cap = d.nl_cap;
         const bool precise = p->precision == DDD_PRECISION_F64;
-        const bool fits_sm_engine = sm_smem_bytes(d.nl_cap, 1) <= dev.max_smem;      // very large ligands: one CTA per chain
+        const bool cut = p->cutoff > 0;
+        const int ulb = cut ? 3 * kUnitCap * (int)sizeof(unsigned short) : 0;
+        const bool fits_sm_engine = sm_smem_bytes(d.nl_cap, 1, ulb) <= dev.max_smem;      // very large ligands: one CTA per chain
+        if (cut && (s->threads_override > 0 || !fits_sm_engine))
+            return fail(DDD_EINVAL, "params.cutoff needs the SM-persistent engine (chain_threads 0 and a ligand that fits one SM's shared memory)");
+        if (cut && s->rec->n_units_s > 65535) return fail(DDD_ELIMIT, "params.cutoff supports receptors up to 2097120 atoms");
         if (s->threads_override <= 0 && n_local > 0 && fits_sm_engine) {
             // SM-persistent engine: one 32-warp CTA per SM, K resident chains each (ddd_sm_chain.cuh)
             SmArgs A;
             A.c = a;
             const int grid = (int)std::min<int64_t>(dev.sm_count, n_local);
-            const int k_fit = (int)std::min<size_t>(kSmMaxSlots, (dev.max_smem - kCtaHeaderBytes) / (sm_smem_bytes(d.nl_cap, 1) - kCtaHeaderBytes));
+            const int k_fit = (int)std::min<size_t>(kSmMaxSlots, (dev.max_smem - kCtaHeaderBytes) / (sm_smem_bytes(d.nl_cap, 1, ulb) - kCtaHeaderBytes));
             const int k_want = s->slots_override > 0 ? s->slots_override : pick_chain_slots(n_local, grid);
             A.slots = std::max(1, std::min(k_want, k_fit));
             A.queue = d.d_queue; A.n_local = n_local; A.first_dynamic = (long long)grid * A.slots;
@@ -348,7 +363,12 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
                 A.upi = 4 * std::max(DDD_SM_ITEM_QUADS, (quads + kSmMaxItems - 1) / kSmMaxItems);
             } else A.upi = std::max(1, (A.n_units + kSmWarps - 1) / kSmWarps);
             A.n_items = (A.n_units + A.upi - 1) / A.upi;
-            const size_t smem = sm_smem_bytes(d.nl_cap, A.slots);
+            A.cut = cut ? 1 : 0; A.unit_list_bytes = ulb; A.out_units = nullptr;
+            if (cut) {
+                if (!d.d_units) { if (int rc = dev_alloc(&d.d_units, (size_t)n_local)) return rc; }
+                A.out_units = d.d_units;
+            }
+            const size_t smem = sm_smem_bytes(d.nl_cap, A.slots, ulb);
             d.threads = kSmThreads; d.slots = A.slots;
             CUDA_TRY(cudaMemsetAsync(d.d_queue, 0, sizeof(int), dev.stream));
             CUDA_TRY(cudaEventRecord(dev.ev0, dev.stream));
@@ -506,6 +526,7 @@ void ddd_params_default(ddd_params *p) {
     p->max_retries = 1024;
     p->precision = DDD_PRECISION_F32;
     p->move_mode = DDD_MOVE_REFERENCE;
+    p->cutoff = 0.0;               // extension, off: every pair is summed (metropolis.go:249-259)
 }
 
 // pure host logic, usable without a device: chains [out_begin[k], out_begin[k+1]) -> shard k
@@ -539,14 +560,67 @@ int ddd_receptor_create(const double *xyzq, int64_t n_atoms, ddd_receptor **out)
                                          (float)(xyzq[4 * i + 2] - r->cz), (float)xyzq[4 * i + 3]);
         else h32[(size_t)i] = make_float4(kPadCoord, kPadCoord, kPadCoord, 0.f);
     }
+    // Cell list for the cutoff extension: atoms sorted along the Morton curve of a 6 A grid (ties: input order), cut
+    // into units of 32 consecutive atoms, each with the box of its real atoms (padding atoms are parked far away, q = 0)
+    std::vector<float4> h32s;
+    std::vector<float4> hbox;
+    std::vector<Atom64> h64s;
+    {
+        const float cell = 6.0f;
+        float mn[3] = {0, 0, 0};
+        for (int64_t i = 0; i < n_atoms; ++i) {
+            const float v[3] = {h32[(size_t)i].x, h32[(size_t)i].y, h32[(size_t)i].z};
+            for (int d = 0; d < 3; ++d) mn[d] = i == 0 ? v[d] : std::min(mn[d], v[d]);
+        }
+        auto spread = [](uint64_t x) {       // 21 bits -> every third bit
+            x &= 0x1fffff; x = (x | x << 32) & 0x1f00000000ffffull; x = (x | x << 16) & 0x1f0000ff0000ffull;
+            x = (x | x << 8) & 0x100f00f00f00f00full; x = (x | x << 4) & 0x10c30c30c30c30c3ull; x = (x | x << 2) & 0x1249249249249249ull;
+            return x;
+        };
+        std::vector<std::pair<uint64_t, int64_t>> key((size_t)n_atoms);
+        for (int64_t i = 0; i < n_atoms; ++i) {
+            const float4 a = h32[(size_t)i];
+            const uint64_t ix = (uint64_t)std::max(0.f, (a.x - mn[0]) / cell), iy = (uint64_t)std::max(0.f, (a.y - mn[1]) / cell),
+                           iz = (uint64_t)std::max(0.f, (a.z - mn[2]) / cell);
+            key[(size_t)i] = {spread(ix) | spread(iy) << 1 | spread(iz) << 2, i};
+        }
+        std::sort(key.begin(), key.end());
+        r->n_units_s = (n_atoms + 31) / 32;
+        const int64_t n_pad_s = (r->n_units_s + 3) / 4 * 4 * 32;            // whole A=4 groups may be read
+        h32s.assign((size_t)std::max<int64_t>(n_pad_s, 1), make_float4(kPadCoord, kPadCoord, kPadCoord, 0.f));
+        hbox.assign((size_t)std::max<int64_t>(2 * r->n_units_s, 1), make_float4(0, 0, 0, 0));
+        h64s.resize((size_t)std::max<int64_t>(n_atoms, 1));
+        for (int64_t i = 0; i < n_atoms; ++i) {
+            const int64_t src = key[(size_t)i].second;
+            h32s[(size_t)i] = h32[(size_t)src];
+            h64s[(size_t)i] = Atom64{xyzq[4 * src], xyzq[4 * src + 1], xyzq[4 * src + 2], xyzq[4 * src + 3]};
+        }
+        for (int64_t u = 0; u < r->n_units_s; ++u) {
+            float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+            for (int64_t i = 32 * u; i < std::min<int64_t>(32 * u + 32, n_atoms); ++i) {
+                const float v[3] = {h32s[(size_t)i].x, h32s[(size_t)i].y, h32s[(size_t)i].z};
+                for (int d = 0; d < 3; ++d) { lo[d] = std::min(lo[d], v[d]); hi[d] = std::max(hi[d], v[d]); }
+            }
+            hbox[(size_t)(2 * u)] = make_float4(lo[0], lo[1], lo[2], 0.f);
+            hbox[(size_t)(2 * u + 1)] = make_float4(hi[0], hi[1], hi[2], 0.f);
+        }
+    }
     r->f32.assign(g_devs.size(), nullptr);
     r->f64.assign(g_devs.size(), nullptr);
+    r->f32s.assign(g_devs.size(), nullptr);
+    r->ubox.assign(g_devs.size(), nullptr);
+    r->f64s.assign(g_devs.size(), nullptr);
     int rc = DDD_OK;
     for (size_t di = 0; di < g_devs.size() && !rc; ++di) {
         cudaError_t ce = cudaSetDevice(g_devs[di].id);
         if (ce == cudaSuccess) { rc = dev_alloc(&r->f32[di], (size_t)r->n_pad); if (rc) break; rc = dev_alloc(&r->f64[di], (size_t)n_atoms); if (rc) break; }
         if (ce == cudaSuccess && r->n_pad > 0) ce = cudaMemcpy(r->f32[di], h32.data(), sizeof(float4) * (size_t)r->n_pad, cudaMemcpyHostToDevice);
         if (ce == cudaSuccess && n_atoms > 0) ce = cudaMemcpy(r->f64[di], xyzq, sizeof(Atom64) * (size_t)n_atoms, cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) { rc = dev_alloc(&r->f32s[di], h32s.size()); if (rc) break; rc = dev_alloc(&r->ubox[di], hbox.size()); if (rc) break; }
+        if (ce == cudaSuccess) ce = cudaMemcpy(r->f32s[di], h32s.data(), sizeof(float4) * h32s.size(), cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) ce = cudaMemcpy(r->ubox[di], hbox.data(), sizeof(float4) * hbox.size(), cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) { rc = dev_alloc(&r->f64s[di], h64s.size()); if (rc) break; }
+        if (ce == cudaSuccess) ce = cudaMemcpy(r->f64s[di], h64s.data(), sizeof(Atom64) * h64s.size(), cudaMemcpyHostToDevice);
         if (ce != cudaSuccess) rc = fail(DDD_ECUDA, "receptor upload on device %d: %s", g_devs[di].id, cudaGetErrorString(ce));
     }
     if (rc) { ddd_receptor_destroy(r); return rc; }
@@ -560,6 +634,7 @@ int ddd_receptor_destroy(ddd_receptor *r) {
     for (size_t di = 0; di < r->f32.size() && di < g_devs.size(); ++di) {
         cudaSetDevice(g_devs[di].id);
         cudaFree(r->f32[di]); cudaFree(r->f64[di]);
+        if (di < r->f32s.size()) { cudaFree(r->f32s[di]); cudaFree(r->ubox[di]); cudaFree(r->f64s[di]); }
     }
     delete r;
     return DDD_OK;
@@ -877,6 +952,25 @@ int ddd_screen_rmsd(ddd_screen *s, double *out_rmsd, double *out_kernel_ms) {
         mx = std::max(mx, (double)d.rmsd_ms);
     }
     if (out_kernel_ms) *out_kernel_ms = mx;
+    return DDD_OK;
+}
+
+// Cutoff extension: receptor atoms actually paired with each ligand atom by chain c's fp32 sums, summed over its
+// evaluations (32 x the units its poses' cell-list queries returned).  Zero-filled when the last run had no cutoff.
+int ddd_screen_pair_units(ddd_screen *s, int64_t *out_receptor_atoms) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    REQUIRE_INIT();
+    if (!s) return fail(DDD_EINVAL, "screen is NULL");
+    if (!s->launched) return fail(DDD_EINVAL, "screen has not been run");
+    if (!out_receptor_atoms && s->n_chains > 0) return fail(DDD_EINVAL, "out is NULL");
+    if (int rc = screen_sync_impl(s)) return rc;
+    for (auto &d : s->devs) {
+        const int64_t n_local = d.c1 - d.c0;
+        if (!d.d_units || !s->last_cut) { std::fill(out_receptor_atoms + d.c0, out_receptor_atoms + d.c1, (int64_t)0); continue; }
+        CUDA_TRY(cudaSetDevice(g_devs[d.di].id));
+        CUDA_TRY(cudaMemcpy(out_receptor_atoms + d.c0, d.d_units, sizeof(int64_t) * (size_t)n_local, cudaMemcpyDeviceToHost));
+        for (int64_t i = d.c0; i < d.c1; ++i) out_receptor_atoms[i] *= 32;
+    }
     return DDD_OK;
 }
 

@@ -39,6 +39,7 @@ constexpr int kSmMaxItems = 128;            // work items per energy evaluation 
 constexpr int kSlotIdle   = 0x3fffffff;     // next_item of a slot that has nothing to hand out
 constexpr int kUbufDraws  = 256;            // jitter uniforms staged per proposal attempt (ligands up to 84 atoms)
 constexpr int kNearCap    = 128;            // near-pair list entries per slot
+constexpr int kUnitCap    = 512;            // cutoff extension: receptor units (32 atoms) within reach of one pose
 #ifndef DDD_NEAR_MARGIN
 #define DDD_NEAR_MARGIN 0.9
 #endif
@@ -77,8 +78,13 @@ struct __align__(16) SmSlotCtl {
     int spec_status, bailed;
     unsigned long long spec_pos;                      // results of the speculative proposal: merged only if it is adopted
     long long spec_rej;
+    int n_e, upi_e;                                   // pair-sum items of the evaluation handed out, receptor units per item
+    int n_surv[3];                                    // cutoff extension: units within reach of pose buffer b (-1: list overflow)
+    int pad0, pad1, pad2;
+    long long units_done;                             // cutoff extension: receptor units evaluated by the chain's fp32 sums
+    long long pad3;
 };
-static_assert(sizeof(SmSlotCtl) == 176, "SmSlotCtl is laid out as eleven 16-byte words");
+static_assert(sizeof(SmSlotCtl) == 224, "SmSlotCtl is laid out as fourteen 16-byte words");
 constexpr int kSlotFixedBytes = (int)sizeof(SmSlotCtl) + kSmMaxItems * 8 + kUbufDraws * 8 + 2 * kNearCap * 4;
 constexpr int kAtomRecBytes = 88;                     // fp64 record per atom: 3 poses x (x,y,z), q, pad
 constexpr int kAtomBytes = kAtomRecBytes + 3 * 16;    // + three pair-packed fp32 poses
@@ -94,10 +100,13 @@ struct SmArgs {
     int slots;               // K
     int n_units;             // receptor units of 32 atoms (one per lane)
     int upi, n_items;        // units per item; items per energy evaluation (<= kSmMaxItems)
+    int cut;                 // cutoff extension on: fp32 sums run over the per-pose unit lists of the sorted receptor
+    int unit_list_bytes;     // per slot: 3 * kUnitCap * 2 when cut, else 0
+    long long *out_units;    // nullable: per-chain count of receptor units evaluated (ddd_screen_pair_units)
 };
 
-__host__ __device__ inline size_t sm_smem_bytes(int nl_cap, int slots) {
-    return kCtaHeaderBytes + (size_t)slots * (kSlotFixedBytes + (size_t)nl_cap * kAtomBytes);
+__host__ __device__ inline size_t sm_smem_bytes(int nl_cap, int slots, int unit_list_bytes = 0) {
+    return kCtaHeaderBytes + (size_t)slots * (kSlotFixedBytes + (size_t)nl_cap * kAtomBytes + unit_list_bytes);
 }
 
 // Views into the CTA's shared memory: [live, epoch, wake barrier 16][keys 64] then per slot [ctl][item sums][uniform staging][base list][dyn list]
@@ -114,17 +123,19 @@ struct SlotView {
     __device__ __forceinline__ double *xyz(int buf, int i) const { return reinterpret_cast<double *>(pose + (size_t)i * kAtomRecBytes) + 3 * buf; }
     __device__ __forceinline__ double &q(int i) const { return *(reinterpret_cast<double *>(pose + (size_t)i * kAtomRecBytes) + 9); }
     __device__ __forceinline__ float4 *lf(int buf) const { return reinterpret_cast<float4 *>(pose + (size_t)cap * kAtomRecBytes) + (size_t)buf * cap; }
+    // cutoff extension: ids of the receptor units within reach of pose buffer `buf`, ascending
+    __device__ __forceinline__ unsigned short *units(int buf) const { return reinterpret_cast<unsigned short *>(pose + (size_t)cap * kAtomBytes) + buf * kUnitCap; }
 };
 
 struct SmView {
     unsigned char *raw;
-    int slots, cap;
+    int slots, cap, ulb;
     __device__ __forceinline__ int *live() const { return reinterpret_cast<int *>(raw); }
     __device__ __forceinline__ int *epoch() const { return reinterpret_cast<int *>(raw) + 1; }
     __device__ __forceinline__ unsigned long long *mbar() const { return reinterpret_cast<unsigned long long *>(raw + 8); }
     // scheduling key of a slot: the chain's step count while it has work to hand out, kKeyNone otherwise
     __device__ __forceinline__ int *keys() const { return reinterpret_cast<int *>(raw + 16); }
-    __device__ __forceinline__ unsigned char *block(int s) const { return raw + kCtaHeaderBytes + (size_t)s * (kSlotFixedBytes + cap * kAtomBytes); }
+    __device__ __forceinline__ unsigned char *block(int s) const { return raw + kCtaHeaderBytes + (size_t)s * (kSlotFixedBytes + cap * kAtomBytes + ulb); }
     __device__ __forceinline__ SmSlotCtl *ctl(int s) const { return reinterpret_cast<SmSlotCtl *>(block(s)); }
     __device__ __forceinline__ double *items(int s) const { return reinterpret_cast<double *>(block(s) + sizeof(SmSlotCtl)); }
     __device__ __forceinline__ SlotView slot(int s) const {
@@ -177,19 +188,77 @@ __device__ __forceinline__ double sm_item_f32(const SmArgs &A, const float4 *lf,
     return warp_sum(acc);
 }
 
+// cutoff extension: item `it` covers entries [it*upi, (it+1)*upi) of the pose's unit list (or of all units after a list
+// overflow); the units are whatever the Morton order put within reach, so each A-wide call gathers its own bases
+__device__ __forceinline__ double sm_item_f32_cut(const SmArgs &A, const SlotView &s, const SmSlotCtl *c, int buf, int nl, int it) {
+    const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(s.lf(buf));
+    const int n_pairs = (nl + 1) >> 1;
+    const int ns = c->n_surv[buf];
+    const int nu = ns >= 0 ? ns : A.c.rec.n_units_s;
+    const unsigned short *ul = s.units(buf);
+    const int upi = c->upi_e;
+    int j = it * upi;
+    const int j1 = min(j + upi, nu);
+    const float rmax = A.c.prm.rinv_max, rci = A.c.prm.rc_inv;
+    const float4 *rec = A.c.rec.f32s;
+    double acc = 0.0;
+    // the sorted receptor of a large complex lives in L2, not L1: the next group's atoms are prefetched into L1 while
+    // this group's pairs are summed
+    const int lane = threadIdx.x & 31;
+    for (; j + 4 <= j1; j += 4) {
+        int ub[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) ub[a] = 32 * (ns >= 0 ? (int)ul[j + a] : j + a);
+        if (j + 8 <= j1) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(rec + 32 * (ns >= 0 ? (int)ul[j + 4 + a] : j + 4 + a) + lane));
+        }
+        acc += (double)warp_units_sum_f32<4, true>(rec, ub, lf2, n_pairs, rmax, rci);
+    }
+    for (; j < j1; ++j) {
+        int ub[1] = {32 * (ns >= 0 ? (int)ul[j] : j)};
+        acc += (double)warp_units_sum_f32<1, true>(rec, ub, lf2, n_pairs, rmax, rci);
+    }
+    return warp_sum(acc);
+}
+
 // the reference's per-term fp64 arithmetic (:253-258) for the receptor atoms of one item
-__device__ __forceinline__ double sm_item_f64(const SmArgs &A, const SlotView &s, int buf, int nl, int it) {
-    const int p0 = it * A.upi * 32, p1 = min((it + 1) * A.upi * 32, A.c.rec.n);
-    const double K = A.c.prm.k_coulomb, clampd = A.c.prm.clamp_distance;
+__device__ __forceinline__ double sm_item_f64(const SmArgs &A, const SlotView &s, const SmSlotCtl *c, int buf, int nl, int it) {
+    const double K = A.c.prm.k_coulomb, clampd = A.c.prm.clamp_distance, cutoff = A.c.prm.cutoff;
     double e = 0.0;
+    if (A.cut) {                                                          // the pose's cell-list units, exact per-pair test
+        const int ns = c->n_surv[buf];
+        const int nu = ns >= 0 ? ns : A.c.rec.n_units_s;
+        const unsigned short *ul = s.units(buf);
+        const int j1 = min((it + 1) * c->upi_e, nu);
+        for (int j = it * c->upi_e; j < j1; ++j) {
+            const int p = 32 * (ns >= 0 ? (int)ul[j] : j) + (int)(threadIdx.x & 31);
+            if (p >= A.c.rec.n) continue;
+            const Atom64 P = A.c.rec.f64s[p];
+            for (int l = 0; l < nl; ++l) {
+                const double *L = s.xyz(buf, l);
+                const double ddx = P.x - L[0], ddy = P.y - L[1], ddz = P.z - L[2];
+                double d = sqrt(ddx * ddx + ddy * ddy + ddz * ddz);
+                if (!(d < cutoff)) continue;
+                if (d < clampd) d = clampd;
+                e += K * (P.q * s.q(l)) / d - K * (P.q * s.q(l)) / cutoff;
+            }
+        }
+        return warp_sum(e);
+    }
+    const int p0 = it * A.upi * 32, p1 = min((it + 1) * A.upi * 32, A.c.rec.n);
     for (int p = p0 + (int)(threadIdx.x & 31); p < p1; p += 32) {
         const Atom64 P = A.c.rec.f64[p];
         for (int l = 0; l < nl; ++l) {
             const double *L = s.xyz(buf, l);
             const double ddx = P.x - L[0], ddy = P.y - L[1], ddz = P.z - L[2];
             double d = sqrt(ddx * ddx + ddy * ddy + ddz * ddz);          // :253 (Pow(x,2) == x*x)
+            if (cutoff > 0 && !(d < cutoff)) continue;                    // EXTENSION: shifted-Coulomb cutoff
             if (d < clampd) d = clampd;                                   // :255-257
-            e += K * (P.q * s.q(l)) / d;                                  // :258
+            double term = K * (P.q * s.q(l)) / d;                         // :258
+            if (cutoff > 0) term -= K * (P.q * s.q(l)) / cutoff;
+            e += term;
         }
     }
     return warp_sum(e);
@@ -258,6 +327,53 @@ __device__ __forceinline__ void warp_write_lf(const SmArgs &A, const SlotView &s
         store_lig_f32(lf, i, (float)(a[0] - A.c.rec.cx), (float)(a[1] - A.c.rec.cy), (float)(a[2] - A.c.rec.cz), (float)s.q(i));
     }
     if ((nl & 1) && (threadIdx.x & 31) == 0) store_lig_f32(lf, nl, -kPadCoord, -kPadCoord, -kPadCoord, 0.f);   // q = 0 pad atom
+    __syncwarp();
+}
+
+// Cutoff extension, the cell-list query of one pose: the ligand's fp32 bounding box against the box of every receptor
+// unit (32 Morton-ordered atoms); a unit whose box is farther than the cutoff from the ligand's box cannot hold a pair
+// inside the cutoff and is dropped.  The survivors' ids go to the pose buffer's list in ascending order (deterministic);
+// more than kUnitCap survivors: -1, the sums then run over every unit.  One warp, 32 units per step.
+__device__ __noinline__ void warp_build_unit_list(const SmArgs &A, const SlotView &s, SmSlotCtl *c, int buf, int nl) {
+    const int lane = threadIdx.x & 31;
+    const float *lff = reinterpret_cast<const float *>(s.lf(buf));
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int i = lane; i < nl; i += 32) {
+        const float *mine = lff + 8 * (i >> 1) + (i & 1);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { const float v = -mine[2 * d]; lo[d] = fminf(lo[d], v); hi[d] = fmaxf(hi[d], v); }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+    const float rc = (float)A.c.prm.cutoff;
+    const float rc2 = rc * rc * 1.0001f + 1e-3f;                      // conservative: fp32 boxes, fp32 pose
+    unsigned short *ul = s.units(buf);
+    const int n_units = A.c.rec.n_units_s;
+    int count = 0;
+    for (int b = 0; b < n_units; b += 32) {
+        const int u = b + lane;
+        bool keep = false;
+        if (u < n_units && nl > 0) {
+            const float4 bmin = __ldg(A.c.rec.ubox + 2 * u), bmax = __ldg(A.c.rec.ubox + 2 * u + 1);
+            const float gx = fmaxf(0.f, fmaxf(bmin.x - hi[0], lo[0] - bmax.x));
+            const float gy = fmaxf(0.f, fmaxf(bmin.y - hi[1], lo[1] - bmax.y));
+            const float gz = fmaxf(0.f, fmaxf(bmin.z - hi[2], lo[2] - bmax.z));
+            keep = gx * gx + gy * gy + gz * gz < rc2;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int idx = count + __popc(m & ((1u << lane) - 1));
+            if (idx < kUnitCap) ul[idx] = (unsigned short)u;
+        }
+        count += __popc(m);
+    }
+    __syncwarp();
+    if (lane == 0) c->n_surv[buf] = count <= kUnitCap ? count : -1;
     __syncwarp();
 }
 
@@ -359,6 +475,7 @@ __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotVie
         }
         __syncwarp();
         warp_write_lf(A, s, dst, nl);
+        if (A.cut) warp_build_unit_list(A, s, c, dst, nl);
         R.pos = pos0 + 7;
         R.status = __any_sync(0xffffffffu, status & 2) ? 2 : 0;
         return R;
@@ -448,6 +565,7 @@ __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotVie
         ++R.rej;
         if (R.rej >= P.max_retries) { bail = true; break; }                // the reference would spin forever here
     }
+    if (A.cut && !bail) warp_build_unit_list(A, s, c, dst, nl);         // the cell-list query of the pose that will be evaluated
     R.pos = pos0 + (uint64_t)k * (uint64_t)dpa;
     R.status = (bail ? 1 : 0) | (__any_sync(0xffffffffu, status & 2) ? 2 : 0);
     return R;
@@ -456,10 +574,25 @@ __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotVie
 // Hand the slot out: pair-sum items of the trial pose (mode/stage) and, when `with_spec`, the speculative proposal of the
 // following step.  False when the receptor has no atoms (nothing to hand out: the caller goes on inline).
 __device__ __forceinline__ bool sm_publish(const SmArgs &A, const SmView &V, int slot_id, SmSlotCtl *c, int mode, int stage, bool with_spec) {
-    if (A.n_items == 0) { if ((threadIdx.x & 31) == 0) { c->mode = mode; c->stage = stage; c->has_spec = 0; } __syncwarp(); return false; }
+    // pair-sum items of this evaluation: the static cut of the receptor, or (cutoff extension, fp32 sums) runs of the
+    // trial pose's unit list, 4*m units per item with m as small as the item-sum array allows
+    int n_e = A.n_items, upi_e = A.upi;
+    if (A.cut) {
+        const int ns = c->n_surv[c->i_trial];
+        const int nu = ns >= 0 ? ns : A.c.rec.n_units_s;
+        upi_e = max(A.upi, 4 * ((nu + 4 * kSmMaxItems - 1) / (4 * kSmMaxItems)));
+        n_e = (nu + upi_e - 1) / upi_e;
+        if ((threadIdx.x & 31) == 0 && mode == 0) c->units_done += nu;
+    }
+    if (n_e == 0 && (!with_spec || A.n_items == 0)) {
+        if ((threadIdx.x & 31) == 0) { c->mode = mode; c->stage = stage; c->has_spec = 0; c->n_e = 0; }
+        __syncwarp();
+        return false;
+    }
     if ((threadIdx.x & 31) == 0) {
         c->mode = mode; c->stage = stage; c->done_items = 0; c->has_spec = with_spec ? 1 : 0;
-        c->n_total = A.n_items + (with_spec ? 1 : 0);
+        c->n_e = n_e; c->upi_e = upi_e;
+        c->n_total = n_e + (with_spec ? 1 : 0);
     }
     cta_fence();
     __syncwarp();
@@ -489,7 +622,8 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
         stage = c->stage;
         spec_ready = c->has_spec != 0;
         const double *items = V.items(slot_id);
-        for (int it = lane; it < A.n_items; it += 32) e += items[it];       // fixed order: independent of who computed what
+        const int n_e = c->n_e;
+        for (int it = lane; it < n_e; it += 32) e += items[it];             // fixed order: independent of who computed what
         e = warp_sum(e);
     }
     for (;;) {
@@ -519,7 +653,7 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 c->nl = nl; c->status = 0; c->rep = (int)(chain - lig * a.replicas); c->bailed = 0;
                 c->i_cur = 0; c->i_trial = 0; c->i_spec = 1; c->has_spec = 0;
                 c->local = local; c->step = 0; c->pos = 0; c->accepted = 0; c->downhill = 0; c->retries = 0;
-                c->cur_e = 0.0; c->start_e = 0.0; c->off = off; c->base_n = -1; c->list_cnt = 0;
+                c->cur_e = 0.0; c->start_e = 0.0; c->off = off; c->base_n = -1; c->list_cnt = 0; c->units_done = 0;
                 c->stream_id = a.chain_id_base + (uint64_t)chain;
                 c->rec_ptr = nullptr; c->rec_len = 0;
                 if (a.recorded) {
@@ -529,6 +663,7 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
             }
             __syncwarp();
             warp_write_lf(A, s, 0, nl);
+            if (A.cut) warp_build_unit_list(A, s, c, 0, nl);
             load_pos = -1;
             spec_ready = false;
             stage = ST_START64;
@@ -636,6 +771,7 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 cs.draws = (long long)c->pos; cs.status = c->status;
                 cs.final_energy = final_energy; cs.start_energy = c->start_e; cs.chain_energy = c->cur_e;
                 reinterpret_cast<ChainStats *>(a.out_stats)[c->local] = cs;
+                if (A.out_units) A.out_units[c->local] = c->units_done;
             }
             __syncwarp();
             stage = ST_LOAD;                                // load_pos == -1: pull from the queue
@@ -656,7 +792,7 @@ template <bool PRECISE>
 __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_constant__ SmArgs A) {
     extern __shared__ __align__(16) unsigned char ddd_sm_smem[];
     SmView V;
-    V.raw = ddd_sm_smem; V.slots = A.slots; V.cap = A.c.nl_cap;
+    V.raw = ddd_sm_smem; V.slots = A.slots; V.cap = A.c.nl_cap; V.ulb = A.unit_list_bytes;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = A.slots;
     if (threadIdx.x == 0) { *V.live() = K; *V.epoch() = 0; wake_init(V.mbar()); }
@@ -690,13 +826,14 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
         // whoever takes the last piece clears the key (it still holds that piece, so the slot cannot be re-published before)
         if (it == n_total - 1 && lane == 0) st_volatile(V.keys() + sid, kKeyNone);
         if (it >= n_total) continue;
-        const int has_spec = n_total - A.n_items;           // the speculative proposal is handed out first: it is the long pole
+        const int has_spec = c->has_spec;                   // the speculative proposal is handed out first: it is the long pole
         if (has_spec && it == 0) sm_spec_task(A, V, sid);
         else {
             const int e_it = it - has_spec;
             const SlotView s = V.slot(sid);
             const int nl = c->nl, buf = c->i_trial;
-            const double sum = c->mode ? sm_item_f64(A, s, buf, nl, e_it) : sm_item_f32(A, s.lf(buf), nl, e_it);
+            const double sum = c->mode ? sm_item_f64(A, s, c, buf, nl, e_it)
+                             : A.cut ? sm_item_f32_cut(A, s, c, buf, nl, e_it) : sm_item_f32(A, s.lf(buf), nl, e_it);
             if (lane == 0) V.items(sid)[e_it] = sum;
         }
         cta_fence();

@@ -69,6 +69,11 @@ typedef struct ddd_params {
     int64_t max_retries;        /* collision-retry bound per step (1024); <= 0: 2^62 */
     int32_t precision;          /* DDD_PRECISION_*  (default F32) */
     int32_t move_mode;          /* DDD_MOVE_*       (default REFERENCE) */
+    double  cutoff;             /* EXTENSION, default 0 = off (the reference sums every pair, metropolis.go:249-259).
+                                   > 0: shifted-Coulomb cutoff radius in A -- a pair with d < cutoff contributes
+                                   K q_p q_l (1/max(d, clamp) - 1/cutoff), a pair beyond it nothing.  The chains then
+                                   evaluate only the receptor cells within reach of the pose (uniform-grid cell list
+                                   built at ddd_receptor_create); needs the SM-persistent engine. */
 } ddd_params;
 
 /* per-chain counters returned by ddd_run_chains (no reference counterpart; SURVEY 5 "metrics") */
@@ -179,6 +184,9 @@ int    ddd_screen_download(ddd_screen *s, double *out_xyzq, ddd_chain_stats *out
  * out_rmsd[c] = CalculateRMSD(final pose of chain c, start pose of its ligand) (validateResults.go:50-65).
  * out_kernel_ms (nullable): CUDA-event time of the RMSD kernel, max over devices. */
 int    ddd_screen_rmsd(ddd_screen *s, double *out_rmsd, double *out_kernel_ms);
+/* Cutoff extension (params.cutoff > 0): out[c] = receptor atoms that chain c's pair sums visited, summed over its
+ * evaluations (what the cell-list queries of its poses returned); x nL(c) = pair terms evaluated.  Zeros without cutoff. */
+int    ddd_screen_pair_units(ddd_screen *s, int64_t *out_receptor_atoms);
 int    ddd_screen_destroy(ddd_screen *s);
 
 /* ---- sharding plan (pure host logic, works without a device): chains

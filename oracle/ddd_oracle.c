@@ -35,6 +35,7 @@ void orc_params_default(orc_params *p) {
     p->rigid_translation = 0.5;
     p->rigid_angle = 0.79;
     p->max_retries = 1024;
+    p->cutoff = 0.0;             /* extension, off: the reference sums every pair */
 }
 
 /* ------------------------------------------------------------------ philox */
@@ -275,15 +276,17 @@ __attribute__((noinline)) double orc_go_pow(double x, double y) {         /* pow
 double orc_calculate_energy_abs(const orc_atom *prot, int64_t np, const orc_atom *lig, int64_t nl,
                                 const orc_params *p, double *abs_sum) {
     double energy = 0.0, asum = 0.0;
-    const double K = p->k_coulomb, clampd = p->clamp_distance;
+    const double K = p->k_coulomb, clampd = p->clamp_distance, cutoff = p->cutoff;
     for (int64_t i = 0; i < np; ++i) {
         for (int64_t j = 0; j < nl; ++j) {
             double ddx = prot[i].x - lig[j].x;
             double ddy = prot[i].y - lig[j].y;
             double ddz = prot[i].z - lig[j].z;
             double distance = sqrt(ORC_SQ(ddx) + ORC_SQ(ddy) + ORC_SQ(ddz));      /* :253 */
+            if (cutoff > 0 && !(distance < cutoff)) continue;                     /* EXTENSION (no reference row) */
             if (distance < clampd) distance = clampd;                             /* :255-257 */
             double term = K * (prot[i].q * lig[j].q) / distance;                  /* :258 */
+            if (cutoff > 0) term -= K * (prot[i].q * lig[j].q) / cutoff;          /* shifted: continuous at the cutoff */
             energy += term;
             asum += fabs(term);
         }
@@ -294,6 +297,7 @@ double orc_calculate_energy_abs(const orc_atom *prot, int64_t np, const orc_atom
 
 double orc_calculate_energy(const orc_atom *prot, int64_t np, const orc_atom *lig, int64_t nl,
                             const orc_params *p) {
+    if (p->cutoff > 0) return orc_calculate_energy_abs(prot, np, lig, nl, p, NULL);   /* EXTENSION: shifted-Coulomb cutoff */
     double energy = 0.0;
     const double K = p->k_coulomb, clampd = p->clamp_distance;
     for (int64_t i = 0; i < np; ++i) {

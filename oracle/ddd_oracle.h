@@ -49,6 +49,9 @@ typedef struct {
     double rigid_angle;      /* RIGID only: max |angle| in rad */
     int64_t max_retries;     /* bound on the collision retry loop (reference: unbounded,
                                 metropolis.go:155,173).  <=0 means unbounded. */
+    double cutoff;           /* EXTENSION (no reference row, parity unpinned): > 0 = shifted-Coulomb cutoff in A:
+                                pairs with d < cutoff add K q q (1/max(d,clamp) - 1/cutoff), the others nothing.
+                                0 (default) = the reference's sum over every pair */
 } orc_params;
 
 void orc_params_default(orc_params *p);

@@ -22,7 +22,7 @@ class OrcParams(C.Structure):
         ("k_coulomb", C.c_double), ("threshold", C.c_double), ("min_distance", C.c_double),
         ("max_angle", C.c_double), ("jitter_width", C.c_double), ("clamp_distance", C.c_double),
         ("move_mode", C.c_int), ("rigid_translation", C.c_double), ("rigid_angle", C.c_double),
-        ("max_retries", C.c_int64),
+        ("max_retries", C.c_int64), ("cutoff", C.c_double),
     ]
 
 
