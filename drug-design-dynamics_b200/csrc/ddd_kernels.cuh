@@ -44,6 +44,7 @@ struct RecView {
     const float4 *f32s;
     const Atom64 *f64s;          // the fp64 atoms in the same Morton order (absolute coordinates)
     const float4 *ubox;
+    const float4 *gbox;          // (min xyz, max xyz) of every group of 4 consecutive units (128 atoms)
     int n_units_s;
 };
 
@@ -188,7 +189,9 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
 // CUT (the cutoff extension): every term becomes max(min(1/d, 1/clamp) - 1/cutoff, 0) -- the shifted Coulomb term, which
 // is exactly 0 from the cutoff outwards, so no distance compare is needed: + 1 FADD2 and 2 FMNMX per ligand pair.
 // `ubase[a]` is the first atom of the a-th unit of 32 receptor atoms this call covers (units need not be adjacent).
-template <int A, bool CUT>
+// CLAMP = false drops the two FMNMX of the d >= 1e-6 clamp (:255-257): the caller has established that no atom of these
+// units can be within the clamp distance of the ligand (their boxes are apart), so min(1/d, 1/clamp) == 1/d bit for bit.
+template <int A, bool CUT, bool CLAMP = true>
 __device__ __forceinline__ float warp_atoms_sum_f32(const float4 (&P)[A], const ulonglong2 *__restrict__ lf2, int n_pairs,
                                                     float rinv_max, float rc_inv) {
     f32x2 px[A], py[A], pz[A], s[A];
@@ -207,7 +210,8 @@ __device__ __forceinline__ float warp_atoms_sum_f32(const float4 (&P)[A], const 
             const f32x2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
             float d2a, d2b;
             unpack2(d2, d2a, d2b);
-            float ra = fminf(rsqrt_approx(d2a), rinv_max), rb = fminf(rsqrt_approx(d2b), rinv_max);
+            float ra = rsqrt_approx(d2a), rb = rsqrt_approx(d2b);
+            if (CLAMP) { ra = fminf(ra, rinv_max); rb = fminf(rb, rinv_max); }
             if (CUT) {
                 unpack2(add2(pack2(ra, rb), m_rc), ra, rb);
                 ra = fmaxf(ra, 0.f); rb = fmaxf(rb, 0.f);
@@ -221,14 +225,14 @@ __device__ __forceinline__ float warp_atoms_sum_f32(const float4 (&P)[A], const 
     return t;
 }
 
-template <int A, bool CUT>
+template <int A, bool CUT, bool CLAMP = true>
 __device__ __forceinline__ float warp_units_sum_f32(const float4 *__restrict__ rec, const int (&ubase)[A],
                                                     const ulonglong2 *__restrict__ lf2, int n_pairs, float rinv_max, float rc_inv) {
     float4 P[A];
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int a = 0; a < A; ++a) P[a] = __ldg(rec + ubase[a] + lane);
-    return warp_atoms_sum_f32<A, CUT>(P, lf2, n_pairs, rinv_max, rc_inv);
+    return warp_atoms_sum_f32<A, CUT, CLAMP>(P, lf2, n_pairs, rinv_max, rc_inv);
 }
 
 template <int A, bool CUT = false>

@@ -119,12 +119,12 @@ struct ddd_receptor {
     double cx = 0, cy = 0, cz = 0;
     std::vector<float4 *> f32;     // per device
     std::vector<Atom64 *> f64;
-    std::vector<float4 *> f32s, ubox;   // cell list (cutoff extension): Morton-sorted atoms, unit boxes
+    std::vector<float4 *> f32s, ubox, gbox;   // Morton-sorted atoms, unit boxes, boxes of groups of 4 units
     std::vector<Atom64 *> f64s;
     int64_t n_units_s = 0;
     RecView view(size_t di) const {
         RecView v; v.f32 = f32[di]; v.f64 = f64[di]; v.n = (int)n; v.n_pad = (int)n_pad; v.cx = cx; v.cy = cy; v.cz = cz;
-        v.f32s = f32s[di]; v.f64s = f64s[di]; v.ubox = ubox[di]; v.n_units_s = (int)n_units_s;
+        v.f32s = f32s[di]; v.f64s = f64s[di]; v.ubox = ubox[di]; v.gbox = gbox[di]; v.n_units_s = (int)n_units_s;
         return v;
     }
 };
@@ -511,7 +511,7 @@ int ddd_num_devices(void) {
 
 const char *ddd_last_error(void) { return g_err.c_str(); }
 
-const char *ddd_version(void) { return "ddd_mc 0.1 (sm_100a; chain CTA = 128 threads, fp32 tile 4x128)"; }
+const char *ddd_version(void) { return "ddd_mc 0.2 (sm_100a; SM-persistent chain engine: 16 warps per SM, speculative proposals, 384-atom pair-sum items)"; }
 
 void ddd_params_default(ddd_params *p) {
     if (!p) return;
@@ -563,7 +563,7 @@ int ddd_receptor_create(const double *xyzq, int64_t n_atoms, ddd_receptor **out)
     // Cell list for the cutoff extension: atoms sorted along the Morton curve of a 6 A grid (ties: input order), cut
     // into units of 32 consecutive atoms, each with the box of its real atoms (padding atoms are parked far away, q = 0)
     std::vector<float4> h32s;
-    std::vector<float4> hbox;
+    std::vector<float4> hbox, hgbox;
     std::vector<Atom64> h64s;
     {
         const float cell = 6.0f;
@@ -604,12 +604,24 @@ int ddd_receptor_create(const double *xyzq, int64_t n_atoms, ddd_receptor **out)
             hbox[(size_t)(2 * u)] = make_float4(lo[0], lo[1], lo[2], 0.f);
             hbox[(size_t)(2 * u + 1)] = make_float4(hi[0], hi[1], hi[2], 0.f);
         }
+        const int64_t n_groups = (r->n_units_s + 3) / 4;
+        hgbox.assign((size_t)std::max<int64_t>(2 * n_groups, 1), make_float4(0, 0, 0, 0));
+        for (int64_t g = 0; g < n_groups; ++g) {
+            float4 lo = make_float4(3e38f, 3e38f, 3e38f, 0.f), hi = make_float4(-3e38f, -3e38f, -3e38f, 0.f);
+            for (int64_t u = 4 * g; u < std::min<int64_t>(4 * g + 4, r->n_units_s); ++u) {
+                const float4 a = hbox[(size_t)(2 * u)], b = hbox[(size_t)(2 * u + 1)];
+                lo.x = std::min(lo.x, a.x); lo.y = std::min(lo.y, a.y); lo.z = std::min(lo.z, a.z);
+                hi.x = std::max(hi.x, b.x); hi.y = std::max(hi.y, b.y); hi.z = std::max(hi.z, b.z);
+            }
+            hgbox[(size_t)(2 * g)] = lo; hgbox[(size_t)(2 * g + 1)] = hi;
+        }
     }
     r->f32.assign(g_devs.size(), nullptr);
     r->f64.assign(g_devs.size(), nullptr);
     r->f32s.assign(g_devs.size(), nullptr);
     r->ubox.assign(g_devs.size(), nullptr);
     r->f64s.assign(g_devs.size(), nullptr);
+    r->gbox.assign(g_devs.size(), nullptr);
     int rc = DDD_OK;
     for (size_t di = 0; di < g_devs.size() && !rc; ++di) {
         cudaError_t ce = cudaSetDevice(g_devs[di].id);
@@ -619,6 +631,8 @@ int ddd_receptor_create(const double *xyzq, int64_t n_atoms, ddd_receptor **out)
         if (ce == cudaSuccess) { rc = dev_alloc(&r->f32s[di], h32s.size()); if (rc) break; rc = dev_alloc(&r->ubox[di], hbox.size()); if (rc) break; }
         if (ce == cudaSuccess) ce = cudaMemcpy(r->f32s[di], h32s.data(), sizeof(float4) * h32s.size(), cudaMemcpyHostToDevice);
         if (ce == cudaSuccess) ce = cudaMemcpy(r->ubox[di], hbox.data(), sizeof(float4) * hbox.size(), cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) { rc = dev_alloc(&r->gbox[di], hgbox.size()); if (rc) break; }
+        if (ce == cudaSuccess) ce = cudaMemcpy(r->gbox[di], hgbox.data(), sizeof(float4) * hgbox.size(), cudaMemcpyHostToDevice);
         if (ce == cudaSuccess) { rc = dev_alloc(&r->f64s[di], h64s.size()); if (rc) break; }
         if (ce == cudaSuccess) ce = cudaMemcpy(r->f64s[di], h64s.data(), sizeof(Atom64) * h64s.size(), cudaMemcpyHostToDevice);
         if (ce != cudaSuccess) rc = fail(DDD_ECUDA, "receptor upload on device %d: %s", g_devs[di].id, cudaGetErrorString(ce));
@@ -634,7 +648,7 @@ int ddd_receptor_destroy(ddd_receptor *r) {
     for (size_t di = 0; di < r->f32.size() && di < g_devs.size(); ++di) {
         cudaSetDevice(g_devs[di].id);
         cudaFree(r->f32[di]); cudaFree(r->f64[di]);
-        if (di < r->f32s.size()) { cudaFree(r->f32s[di]); cudaFree(r->ubox[di]); cudaFree(r->f64s[di]); }
+        if (di < r->f32s.size()) { cudaFree(r->f32s[di]); cudaFree(r->ubox[di]); cudaFree(r->f64s[di]); cudaFree(r->gbox[di]); }
     }
     delete r;
     return DDD_OK;

@@ -83,8 +83,9 @@ struct __align__(16) SmSlotCtl {
     int pad0, pad1, pad2;
     long long units_done;                             // cutoff extension: receptor units evaluated by the chain's fp32 sums
     long long pad3;
+    float lbox[3][8];                                 // fp32 bounding box of pose buffer b: (min xyz, -, max xyz, -)
 };
-static_assert(sizeof(SmSlotCtl) == 224, "SmSlotCtl is laid out as fourteen 16-byte words");
+static_assert(sizeof(SmSlotCtl) == 320, "SmSlotCtl is laid out as twenty 16-byte words");
 constexpr int kSlotFixedBytes = (int)sizeof(SmSlotCtl) + kSmMaxItems * 8 + kUbufDraws * 8 + 2 * kNearCap * 4;
 constexpr int kAtomRecBytes = 88;                     // fp64 record per atom: 3 poses x (x,y,z), q, pad
 constexpr int kAtomBytes = kAtomRecBytes + 3 * 16;    // + three pair-packed fp32 poses
@@ -175,16 +176,30 @@ __device__ __forceinline__ int ld_volatile(const int *p) { return *reinterpret_c
 __device__ __forceinline__ void st_volatile(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
 
 // ------------------------------------------------------------------ energy work items
-__device__ __forceinline__ double sm_item_f32(const SmArgs &A, const float4 *lf, int nl, int it) {
+__device__ __forceinline__ double sm_item_f32(const SmArgs &A, const float4 *lf, const float *lbox, int nl, int it) {
     const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
     const int n_pairs = (nl + 1) >> 1;
     int u = it * A.upi;
     const int u1 = min(u + A.upi, A.n_units);
     const float rmax = A.c.prm.rinv_max;
+    const float4 *rec = A.c.rec.f32s;                 // Morton order: a group of 4 units is spatially compact
     double acc = 0.0;
-    for (; u + 4 <= u1; u += 4) acc += (double)warp_tile_sum_f32<4>(A.c.rec.f32, u * 32, lf2, n_pairs, rmax);
-    if (u + 2 <= u1) { acc += (double)warp_tile_sum_f32<2>(A.c.rec.f32, u * 32, lf2, n_pairs, rmax); u += 2; }
-    if (u < u1) acc += (double)warp_tile_sum_f32<1>(A.c.rec.f32, u * 32, lf2, n_pairs, rmax);
+    if ((A.upi & 3) == 0) {
+        for (; u + 4 <= u1; u += 4) {
+            // The clamp d >= 1e-6 (:255-257) can only matter where the group's box touches the ligand's box; everywhere
+            // else min(1/d, 1e6) == 1/d exactly and the loop without the two FMNMX gives the same bits.
+            const float4 gmin = __ldg(A.c.rec.gbox + (u >> 1)), gmax = __ldg(A.c.rec.gbox + (u >> 1) + 1);
+            const bool apart = gmin.x - lbox[4] > 1e-3f || lbox[0] - gmax.x > 1e-3f || gmin.y - lbox[5] > 1e-3f ||
+                               lbox[1] - gmax.y > 1e-3f || gmin.z - lbox[6] > 1e-3f || lbox[2] - gmax.z > 1e-3f;
+            int ub[4] = {u * 32, u * 32 + 32, u * 32 + 64, u * 32 + 96};
+            if (apart) acc += (double)warp_units_sum_f32<4, false, false>(rec, ub, lf2, n_pairs, rmax, 0.f);
+            else acc += (double)warp_units_sum_f32<4, false, true>(rec, ub, lf2, n_pairs, rmax, 0.f);
+        }
+    } else {
+        for (; u + 4 <= u1; u += 4) acc += (double)warp_tile_sum_f32<4>(rec, u * 32, lf2, n_pairs, rmax);
+    }
+    if (u + 2 <= u1) { acc += (double)warp_tile_sum_f32<2>(rec, u * 32, lf2, n_pairs, rmax); u += 2; }
+    if (u < u1) acc += (double)warp_tile_sum_f32<1>(rec, u * 32, lf2, n_pairs, rmax);
     return warp_sum(acc);
 }
 
@@ -320,13 +335,27 @@ __device__ __noinline__ bool warp_collision_exact(const SlotView &s, int buf, in
 }
 
 // fp32 pose of every atom from the fp64 master copy (the pair-packed layout the pair loop and the list scan read)
-__device__ __forceinline__ void warp_write_lf(const SmArgs &A, const SlotView &s, int buf, int nl) {
+__device__ __forceinline__ void warp_write_lf(const SmArgs &A, const SlotView &s, SmSlotCtl *c, int buf, int nl) {
     float4 *lf = s.lf(buf);
-    for (int i = threadIdx.x & 31; i < nl; i += 32) {
+    const int lane = threadIdx.x & 31;
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int i = lane; i < nl; i += 32) {
         const double *a = s.xyz(buf, i);
-        store_lig_f32(lf, i, (float)(a[0] - A.c.rec.cx), (float)(a[1] - A.c.rec.cy), (float)(a[2] - A.c.rec.cz), (float)s.q(i));
+        const float x = (float)(a[0] - A.c.rec.cx), y = (float)(a[1] - A.c.rec.cy), z = (float)(a[2] - A.c.rec.cz);
+        store_lig_f32(lf, i, x, y, z, (float)s.q(i));
+        lo[0] = fminf(lo[0], x); hi[0] = fmaxf(hi[0], x); lo[1] = fminf(lo[1], y); hi[1] = fmaxf(hi[1], y);
+        lo[2] = fminf(lo[2], z); hi[2] = fmaxf(hi[2], z);
     }
-    if ((nl & 1) && (threadIdx.x & 31) == 0) store_lig_f32(lf, nl, -kPadCoord, -kPadCoord, -kPadCoord, 0.f);   // q = 0 pad atom
+    if ((nl & 1) && lane == 0) store_lig_f32(lf, nl, -kPadCoord, -kPadCoord, -kPadCoord, 0.f);   // q = 0 pad atom
+    // the pose's fp32 bounding box: lets the pair loop skip the clamp (and the cutoff extension skip whole units)
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+    if (lane < 3) { c->lbox[buf][lane] = lo[lane]; c->lbox[buf][4 + lane] = hi[lane]; }
     __syncwarp();
 }
 
@@ -336,20 +365,7 @@ __device__ __forceinline__ void warp_write_lf(const SmArgs &A, const SlotView &s
 // more than kUnitCap survivors: -1, the sums then run over every unit.  One warp, 32 units per step.
 __device__ __noinline__ void warp_build_unit_list(const SmArgs &A, const SlotView &s, SmSlotCtl *c, int buf, int nl) {
     const int lane = threadIdx.x & 31;
-    const float *lff = reinterpret_cast<const float *>(s.lf(buf));
-    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    for (int i = lane; i < nl; i += 32) {
-        const float *mine = lff + 8 * (i >> 1) + (i & 1);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) { const float v = -mine[2 * d]; lo[d] = fminf(lo[d], v); hi[d] = fmaxf(hi[d], v); }
-    }
-#pragma unroll
-    for (int d = 0; d < 3; ++d)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
-            hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
-        }
+    const float lo[3] = {c->lbox[buf][0], c->lbox[buf][1], c->lbox[buf][2]}, hi[3] = {c->lbox[buf][4], c->lbox[buf][5], c->lbox[buf][6]};
     const float rc = (float)A.c.prm.cutoff;
     const float rc2 = rc * rc * 1.0001f + 1e-3f;                      // conservative: fp32 boxes, fp32 pose
     unsigned short *ul = s.units(buf);
@@ -474,7 +490,7 @@ __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotVie
             o[2] = gz + (vz + 2.0 * (w * c1z + c2z)) + tz;
         }
         __syncwarp();
-        warp_write_lf(A, s, dst, nl);
+        warp_write_lf(A, s, c, dst, nl);
         if (A.cut) warp_build_unit_list(A, s, c, dst, nl);
         R.pos = pos0 + 7;
         R.status = __any_sync(0xffffffffu, status & 2) ? 2 : 0;
@@ -549,7 +565,7 @@ __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotVie
         if (lists_ok && base_n <= kNearCap && k <= k_max) collided = warp_check_near_list(s, dst, s.base_list(), base_n, P.min_distance);
         else if (lists_ok && dyn_n >= 0 && k - dyn_kb <= k_max) collided = warp_check_near_list(s, dst, s.dyn_list(), dyn_n, P.min_distance);
         else {
-            warp_write_lf(A, s, dst, nl);
+            warp_write_lf(A, s, c, dst, nl);
             lf_fresh = true;
             const int n = warp_build_near_list(s.lf(dst), c, s.dyn_list(), nl, r2_near);
             if (n <= kNearCap) { dyn_n = n; dyn_kb = k; collided = warp_check_near_list(s, dst, s.dyn_list(), n, P.min_distance); }
@@ -561,7 +577,7 @@ __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotVie
                     collided = __any_sync(0xffffffffu, warp_collision_exact(s, dst, nl, P.min_distance)) != 0;
             }
         }
-        if (!collided) { if (!lf_fresh) warp_write_lf(A, s, dst, nl); break; }
+        if (!collided) { if (!lf_fresh) warp_write_lf(A, s, c, dst, nl); break; }
         ++R.rej;
         if (R.rej >= P.max_retries) { bail = true; break; }                // the reference would spin forever here
     }
@@ -662,7 +678,7 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 }
             }
             __syncwarp();
-            warp_write_lf(A, s, 0, nl);
+            warp_write_lf(A, s, c, 0, nl);
             if (A.cut) warp_build_unit_list(A, s, c, 0, nl);
             load_pos = -1;
             spec_ready = false;
@@ -833,7 +849,7 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
             const SlotView s = V.slot(sid);
             const int nl = c->nl, buf = c->i_trial;
             const double sum = c->mode ? sm_item_f64(A, s, c, buf, nl, e_it)
-                             : A.cut ? sm_item_f32_cut(A, s, c, buf, nl, e_it) : sm_item_f32(A, s.lf(buf), nl, e_it);
+                             : A.cut ? sm_item_f32_cut(A, s, c, buf, nl, e_it) : sm_item_f32(A, s.lf(buf), c->lbox[buf], nl, e_it);
             if (lane == 0) V.items(sid)[e_it] = sum;
         }
         cta_fence();
