@@ -43,19 +43,12 @@ constexpr int kUnitCap    = 512;            // cutoff extension: receptor units 
 #ifndef DDD_NEAR_MARGIN
 #define DDD_NEAR_MARGIN 0.9
 #endif
-#ifndef DDD_SM_SPIN
-#define DDD_SM_SPIN 1
-#endif
 #ifndef DDD_SM_IDLE_NS
 #define DDD_SM_IDLE_NS 100
 #endif
 #ifndef DDD_SM_PRIO
 #define DDD_SM_PRIO 1
 #endif
-#ifndef DDD_SM_UNROLL
-#define DDD_SM_UNROLL 1
-#endif
-constexpr int kSmUnroll = DDD_SM_UNROLL;
 constexpr double kNearMargin = DDD_NEAR_MARGIN;         // a near-pair list holds every ligand pair closer than MINDISTANCE + this
 
 enum : int { ST_START64 = 0, ST_START32 = 1, ST_STEP = 2, ST_FINAL64 = 3, ST_NEXT = 4, ST_LOAD = 5 };
@@ -90,7 +83,7 @@ constexpr int kSlotFixedBytes = (int)sizeof(SmSlotCtl) + kSmMaxItems * 8 + kUbuf
 constexpr int kAtomRecBytes = 88;                     // fp64 record per atom: 3 poses x (x,y,z), q, pad
 constexpr int kAtomBytes = kAtomRecBytes + 3 * 16;    // + three pair-packed fp32 poses
 
-constexpr int kCtaHeaderBytes = 16 + 4 * kSmMaxSlots;   // live, epoch, wake barrier, then one scheduling key per slot
+constexpr int kCtaHeaderBytes = 16 + 4 * kSmMaxSlots;   // live-slot count, then one scheduling key per slot
 constexpr int kKeyNone = 0x7fffffff;                    // key of a slot that has nothing to hand out
 
 struct SmArgs {
@@ -110,7 +103,7 @@ __host__ __device__ inline size_t sm_smem_bytes(int nl_cap, int slots, int unit_
     return kCtaHeaderBytes + (size_t)slots * (kSlotFixedBytes + (size_t)nl_cap * kAtomBytes + unit_list_bytes);
 }
 
-// Views into the CTA's shared memory: [live, epoch, wake barrier 16][keys 64] then per slot [ctl][item sums][uniform staging][base list][dyn list]
+// Views into the CTA's shared memory: [live 16][keys 64] then per slot [ctl][item sums][uniform staging][base list][dyn list]
 // [fp64 atom records (cap x 88 B)][fp32 pair-packed poses (3 x cap x 16 B)]
 struct SlotView {
     unsigned char *blk;      // this slot's block
@@ -132,8 +125,6 @@ struct SmView {
     unsigned char *raw;
     int slots, cap, ulb;
     __device__ __forceinline__ int *live() const { return reinterpret_cast<int *>(raw); }
-    __device__ __forceinline__ int *epoch() const { return reinterpret_cast<int *>(raw) + 1; }
-    __device__ __forceinline__ unsigned long long *mbar() const { return reinterpret_cast<unsigned long long *>(raw + 8); }
     // scheduling key of a slot: the chain's step count while it has work to hand out, kKeyNone otherwise
     __device__ __forceinline__ int *keys() const { return reinterpret_cast<int *>(raw + 16); }
     __device__ __forceinline__ unsigned char *block(int s) const { return raw + kCtaHeaderBytes + (size_t)s * (kSlotFixedBytes + cap * kAtomBytes + ulb); }
@@ -148,21 +139,8 @@ struct SmView {
     }
 };
 
-// Idle warps: either a short nanosleep poll (default) or a block on an mbarrier whose phase flips whenever work is
-// published (DDD_SM_SPIN=0; measured slower on B200: the wake-up of try_wait costs more than the poll).
-__device__ __forceinline__ void wake_init(unsigned long long *mbar) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((unsigned)__cvta_generic_to_shared(mbar)) : "memory");
-}
-__device__ __forceinline__ void wake_all(int *epoch, unsigned long long *mbar) {     // one lane
-    if (DDD_SM_SPIN) return;
-    atomicAdd(epoch, 1);
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"((unsigned)__cvta_generic_to_shared(mbar)) : "memory");
-}
-__device__ __forceinline__ void wake_wait(unsigned long long *mbar, int parity, unsigned ns) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t}"
-                 :: "r"((unsigned)__cvta_generic_to_shared(mbar)), "r"(parity), "r"(ns) : "memory");
-}
-
+// Idle warps poll the scheduling keys with a short nanosleep in between.  (Blocking them on an mbarrier that flips on
+// every hand-out was measured slower on B200: the wake-up of try_wait costs more than the poll.)
 // CTA-scope acquire/release fence (the default __threadfence_block() is the sequentially-consistent MEMBAR.SC.CTA)
 #ifndef DDD_SM_FENCE_SC
 #define DDD_SM_FENCE_SC 0
@@ -534,7 +512,6 @@ __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotVie
         if (use_ubuf && nl > 0) {
             const int nb = (int)(((jpos + 3ull * (uint64_t)nl - 1) >> 1) - b_first) + 1;
             double2 *ub = reinterpret_cast<double2 *>(s.ubuf());
-#pragma unroll kSmUnroll
             for (int b = lane; b < nb; b += 32) {
                 const uint64_t blk = b_first + (uint64_t)b;
                 uint32_t o[4];
@@ -545,7 +522,6 @@ __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotVie
             __syncwarp();
         }
         const double *uu = s.ubuf() + (jpos - 2 * b_first);
-#pragma unroll kSmUnroll
         for (int i = lane; i < nl; i += 32) {
             const double *p = s.xyz(from, i);
             double x = p[0], y = p[1], z = p[2];
@@ -615,8 +591,6 @@ __device__ __forceinline__ bool sm_publish(const SmArgs &A, const SmView &V, int
     if ((threadIdx.x & 31) == 0) {
         st_volatile(&c->next_item, 0);
         st_volatile(V.keys() + slot_id, (int)(c->step & 0x3fffffff));
-        cta_fence();
-        wake_all(V.epoch(), V.mbar());
     }
     return true;
 }
@@ -651,7 +625,7 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 load_pos = A.first_dynamic + (long long)t;
             }
             if (load_pos >= A.n_local) {                                        // nothing left: the slot dies
-                if (lane == 0) { st_volatile(&c->next_item, kSlotIdle); atomicSub(V.live(), 1); cta_fence(); wake_all(V.epoch(), V.mbar()); }
+                if (lane == 0) { st_volatile(&c->next_item, kSlotIdle); atomicSub(V.live(), 1); }
                 return;
             }
             const long long local = a.order ? (long long)a.order[load_pos] : load_pos;
@@ -811,26 +785,24 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
     V.raw = ddd_sm_smem; V.slots = A.slots; V.cap = A.c.nl_cap; V.ulb = A.unit_list_bytes;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = A.slots;
-    if (threadIdx.x == 0) { *V.live() = K; *V.epoch() = 0; wake_init(V.mbar()); }
+    if (threadIdx.x == 0) *V.live() = K;
     if (threadIdx.x < kSmMaxSlots) V.keys()[threadIdx.x] = kKeyNone;
     if (threadIdx.x < K) { V.ctl(threadIdx.x)->next_item = kSlotIdle; V.ctl(threadIdx.x)->n_total = 0; V.ctl(threadIdx.x)->step = 0; }
     __syncthreads();
     for (int sl = warp; sl < K; sl += kSmWarps) sm_serial_phase<PRECISE>(A, V, sl, (long long)sl * gridDim.x + blockIdx.x);
 
-    int rot = warp % K;
     for (;;) {
-        const int ep = DDD_SM_SPIN ? 0 : ld_volatile(V.epoch());
         // the chain that is furthest behind goes first: chains of an SM advance in step and end together, and one that
         // loses time in collision retries gets its pair sums served ahead of the others
         int sid = -1, best = kKeyNone;
-        for (int j = 0; j < K; ++j) {
-            int t = rot + j; if (t >= K) t -= K;
+#pragma unroll
+        for (int t = 0; t < kSmMaxSlots; ++t) {             // all keys in flight at once; unused slots hold kKeyNone
             const int key = ld_volatile(V.keys() + t);
-            if (key < best) { best = key; sid = t; if (!DDD_SM_PRIO) break; }
+            if (key < best) { best = key; sid = t; }
         }
         if (sid < 0) {
             if (ld_volatile(V.live()) == 0) break;
-            if (DDD_SM_SPIN) __nanosleep(DDD_SM_IDLE_NS); else wake_wait(V.mbar(), ep & 1, 20000u);
+            __nanosleep(DDD_SM_IDLE_NS);
             continue;
         }
         SmSlotCtl *c = V.ctl(sid);
@@ -860,7 +832,6 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
             cta_fence();
             sm_serial_phase<PRECISE>(A, V, sid, -1);
         }
-        rot = sid + 1; if (rot >= K) rot = 0;
     }
 }
 

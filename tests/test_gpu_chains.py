@@ -164,6 +164,30 @@ def test_zero_steps_and_tiny_ligands(gpu, orc, synth_small):
         assert gpu.run_chains(rec, np.array([0]), np.zeros((0, 4)), 2, 10, True, T)[0].shape == (0, 4)
 
 
+def test_empty_receptor_and_oversized_ligand(gpu, orc, ddd):
+    # an empty protein: every energy is 0, nothing is ever downhill, the chain still consumes its draws (AcceptMove :141-149)
+    lig = mock_ligand()
+    with gpu.Receptor(np.zeros((0, 4))) as rec:
+        for prm in (gpu.default_params(), _p64(gpu)):
+            poses, stats, trace = gpu.run_chains(rec, np.array([0, 2]), lig, 2, 30, True, T, prm, seed=3, want_trace=True)
+            pose_o, st_o, tr_o, _ = orc.chain(np.zeros((0, 4)), lig, 30, True, T, orc.philox_stream(3, 0), want_trace=True)
+            assert np.array_equal(trace[0], tr_o) and stats[0]["draws"] == st_o["draws"] and stats[0]["final_energy"] == 0.0
+            assert np.allclose(gpu.chain_pose(np.array([0, 2]), 2, poses, 0, 0), pose_o, atol=1e-9)
+    # a ligand too large for a slot of the SM-persistent engine falls back to one CTA per chain, same results
+    prot = ddd.synth.make_receptor(300, seed=1)
+    rng = np.random.default_rng(0)
+    big = np.concatenate([rng.uniform(-60, 60, size=(1800, 3)) * np.array([1.0, 1.0, 1.0]) + 200.0, rng.normal(0, 0.2, size=(1800, 1))], axis=1)
+    with gpu.Receptor(prot) as rec:
+        scr = gpu.Screen(rec, np.array([0, 1800]), big, 1)
+        scr.run(3, True, T, _p64(gpu), seed=2)
+        poses, stats = scr.download()
+        assert scr.chain_slots() == 0 and stats[0]["steps"] == 3
+        scr.close()
+    pose_o, st_o = orc.chain(prot, big, 3, True, T, orc.philox_stream(2, 0))
+    assert stats[0]["draws"] == st_o["draws"] and stats[0]["accepted"] == st_o["accepted"]
+    assert np.allclose(poses, pose_o, rtol=0, atol=1e-8)
+
+
 def test_f32_chains_match_oracle_statistics(gpu, orc, ddd):
     # production precision: trajectories may differ after an fp32 near-tie, statistics must not
     prot = ddd.synth.make_receptor(1500, seed=2)
