@@ -271,8 +271,9 @@ def main():
     my_steps = float(st["steps"].sum()) * 1.0         # steps of the LAST bench step, all chains of this rank
     n_bailed = int(np.count_nonzero(st["status"] & capi.STATUS_RETRY_LIMIT))
     assert not np.any(st["status"] & ~capi.STATUS_RETRY_LIMIT), "chain status flags set"
-    if args.config != 5:                              # the sweep's 20..80-atom ligands may exhaust the retry bound (reported below)
-        assert my_steps == n_lig * replicas * args.chain_steps and n_bailed == 0, "chains stopped early"
+    # a chain that needs more than max_retries (1024) collision retries in ONE step stops there (the reference would spin,
+    # metropolis.go:173): counted below, and only the steps really executed enter the metric
+    assert my_steps >= 0.99 * n_lig * replicas * args.chain_steps, "too many chains stopped early"
     width, slots = scr.chain_threads(), scr.chain_slots()
     scr.close()
     dev_s = max_over_ranks(kernel_ms * 1e-3)          # max over ranks of the device time of K steps
@@ -304,7 +305,7 @@ def main():
         out_pose, out_energy, picked = call(400 + k)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = sum_over_ranks(n_lig * replicas * args.chain_steps) * n_e2e / e2e_s
+    e2e_value = sum_over_ranks(n_lig * replicas * args.chain_steps) * n_e2e / e2e_s * (my_steps / max(1.0, n_lig * replicas * args.chain_steps))
     h2d = int(h_lig.nbytes + off.nbytes) * world
     d2h = int(h_lig.nbytes * replicas + n_lig * replicas * capi.STATS_DTYPE.itemsize) * world
 
@@ -352,7 +353,7 @@ def main():
                    "parallelism": f"{world} x independent chain shards, no collective"},
         "wall_ms_per_step": wall_s * 1e3 / args.steps,
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                     "traffic": 1.7e6 if args.config == 2 else None, "traffic_source": "profiles/r01_sm_engine_ncu.md (dram__bytes_read+write of one launch; config 2 shape)", "peak_source": f"SMs*128 lanes*2*sm_max_mhz ({peaks['sm_max_mhz']:.0f} MHz from {peaks_src})",
+                     "traffic": 2.43e7 if args.config == 2 else None, "traffic_source": "profiles/r01_sm_engine_ncu.md (dram__bytes_read+write of one launch; config 2 shape)", "peak_source": f"SMs*128 lanes*2*sm_max_mhz ({peaks['sm_max_mhz']:.0f} MHz from {peaks_src})",
                      "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": work_pairs / args.steps / world,
                      "kernel_ms_per_launch": dev_s * 1e3 / args.steps,
                      "mufu_bound_frac_of_peak": 0.75, "frac_of_mufu_bound": achieved / fp32_peak / 0.75},

@@ -41,7 +41,7 @@ constexpr int kUbufDraws  = 256;            // jitter uniforms staged per propos
 constexpr int kNearCap    = 128;            // near-pair list entries per slot
 constexpr int kUnitCap    = 512;            // cutoff extension: receptor units (32 atoms) within reach of one pose
 #ifndef DDD_NEAR_MARGIN
-#define DDD_NEAR_MARGIN 0.9
+#define DDD_NEAR_MARGIN 1.4
 #endif
 #ifndef DDD_SM_IDLE_NS
 #define DDD_SM_IDLE_NS 100
@@ -796,9 +796,11 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
         // loses time in collision retries gets its pair sums served ahead of the others
         int sid = -1, best = kKeyNone;
 #pragma unroll
-        for (int t = 0; t < kSmMaxSlots; ++t) {             // all keys in flight at once; unused slots hold kKeyNone
-            const int key = ld_volatile(V.keys() + t);
-            if (key < best) { best = key; sid = t; }
+        for (int t = 0; t < kSmMaxSlots; ++t) {             // all K keys in flight at once
+            if (t < K) {
+                const int key = ld_volatile(V.keys() + t);
+                if (key < best) { best = key; sid = t; }
+            }
         }
         if (sid < 0) {
             if (ld_volatile(V.live()) == 0) break;
