@@ -1018,15 +1018,17 @@ int ddd_chain_kernel_info(int32_t precision, int32_t *threads, int32_t *regs, in
     CUDA_TRY(cudaSetDevice(g_devs[0].id));
     cudaFuncAttributes fa;
     int blocks = 0;
-    const size_t smem = chain_smem_bytes(40, 128);
+    const size_t smem = sm_smem_bytes(40, 7);            // the SM-persistent engine at config 2's shape: 7 chains of 40 atoms per SM
     if (precision == DDD_PRECISION_F64) {
-        CUDA_TRY(cudaFuncGetAttributes(&fa, mc_chain_kernel<128, true>));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, mc_chain_kernel<128, true>, 128, smem));
+        if (int rc = set_smem(mc_sm_kernel<true>, smem)) return rc;
+        CUDA_TRY(cudaFuncGetAttributes(&fa, mc_sm_kernel<true>));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, mc_sm_kernel<true>, kSmThreads, smem));
     } else {
-        CUDA_TRY(cudaFuncGetAttributes(&fa, mc_chain_kernel<128, false>));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, mc_chain_kernel<128, false>, 128, smem));
+        if (int rc = set_smem(mc_sm_kernel<false>, smem)) return rc;
+        CUDA_TRY(cudaFuncGetAttributes(&fa, mc_sm_kernel<false>));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, mc_sm_kernel<false>, kSmThreads, smem));
     }
-    if (threads) *threads = 128;
+    if (threads) *threads = kSmThreads;
     if (regs) *regs = fa.numRegs;
     if (static_smem) *static_smem = (int32_t)fa.sharedSizeBytes;
     if (max_blocks_per_sm_at_nl40) *max_blocks_per_sm_at_nl40 = blocks;

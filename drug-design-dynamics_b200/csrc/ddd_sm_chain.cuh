@@ -339,8 +339,9 @@ __device__ __forceinline__ void warp_write_lf(const SmArgs &A, const SlotView &s
 
 // Cutoff extension, the cell-list query of one pose: the ligand's fp32 bounding box against the box of every receptor
 // unit (32 Morton-ordered atoms); a unit whose box is farther than the cutoff from the ligand's box cannot hold a pair
-// inside the cutoff and is dropped.  The survivors' ids go to the pose buffer's list in ascending order (deterministic);
-// more than kUnitCap survivors: -1, the sums then run over every unit.  One warp, 32 units per step.
+// inside the cutoff and is dropped.  Two levels: first the boxes of the groups of 4 units, then the unit boxes of the
+// surviving groups.  The survivors' ids go to the pose buffer's list in ascending order (deterministic); more than
+// kUnitCap survivors: -1, the sums then run over every unit.  One warp, 32 boxes per step.
 __device__ __noinline__ void warp_build_unit_list(const SmArgs &A, const SlotView &s, SmSlotCtl *c, int buf, int nl) {
     const int lane = threadIdx.x & 31;
     const float lo[3] = {c->lbox[buf][0], c->lbox[buf][1], c->lbox[buf][2]}, hi[3] = {c->lbox[buf][4], c->lbox[buf][5], c->lbox[buf][6]};
@@ -348,23 +349,47 @@ __device__ __noinline__ void warp_build_unit_list(const SmArgs &A, const SlotVie
     const float rc2 = rc * rc * 1.0001f + 1e-3f;                      // conservative: fp32 boxes, fp32 pose
     unsigned short *ul = s.units(buf);
     const int n_units = A.c.rec.n_units_s;
-    int count = 0;
-    for (int b = 0; b < n_units; b += 32) {
-        const int u = b + lane;
-        bool keep = false;
-        if (u < n_units && nl > 0) {
-            const float4 bmin = __ldg(A.c.rec.ubox + 2 * u), bmax = __ldg(A.c.rec.ubox + 2 * u + 1);
-            const float gx = fmaxf(0.f, fmaxf(bmin.x - hi[0], lo[0] - bmax.x));
-            const float gy = fmaxf(0.f, fmaxf(bmin.y - hi[1], lo[1] - bmax.y));
-            const float gz = fmaxf(0.f, fmaxf(bmin.z - hi[2], lo[2] - bmax.z));
-            keep = gx * gx + gy * gy + gz * gz < rc2;
-        }
+    auto within = [&](const float4 bmin, const float4 bmax) {
+        const float gx = fmaxf(0.f, fmaxf(bmin.x - hi[0], lo[0] - bmax.x));
+        const float gy = fmaxf(0.f, fmaxf(bmin.y - hi[1], lo[1] - bmax.y));
+        const float gz = fmaxf(0.f, fmaxf(bmin.z - hi[2], lo[2] - bmax.z));
+        return gx * gx + gy * gy + gz * gz < rc2;
+    };
+    // level 1: the boxes of the groups of 4 units; the survivors' ids are staged in the (idle) dynamic near-pair list
+    unsigned short *grp = reinterpret_cast<unsigned short *>(s.dyn_list());
+    constexpr int kGroupCap = kNearCap * 2;                               // ushort entries in that list
+    const int n_groups = (n_units + 3) >> 2;
+    int n_g = 0;
+    for (int b = 0; b < n_groups; b += 32) {
+        const int g = b + lane;
+        const bool keep = g < n_groups && nl > 0 && within(__ldg(A.c.rec.gbox + 2 * g), __ldg(A.c.rec.gbox + 2 * g + 1));
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         if (keep) {
-            const int idx = count + __popc(m & ((1u << lane) - 1));
-            if (idx < kUnitCap) ul[idx] = (unsigned short)u;
+            const int idx = n_g + __popc(m & ((1u << lane) - 1));
+            if (idx < kGroupCap) grp[idx] = (unsigned short)g;
         }
-        count += __popc(m);
+        n_g += __popc(m);
+    }
+    __syncwarp();
+    // level 2: the 4 unit boxes of every surviving group, 8 groups per step; ascending ids are preserved
+    int count = 0;
+    if (n_g > kGroupCap) count = kUnitCap + 1;                            // more than 1024 units in reach: overflow
+    else {
+        for (int b = 0; b < 4 * n_g; b += 32) {
+            const int e = b + lane;
+            bool keep = false;
+            int u = 0;
+            if (e < 4 * n_g) {
+                u = 4 * (int)grp[e >> 2] + (e & 3);
+                keep = u < n_units && within(__ldg(A.c.rec.ubox + 2 * u), __ldg(A.c.rec.ubox + 2 * u + 1));
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int idx = count + __popc(m & ((1u << lane) - 1));
+                if (idx < kUnitCap) ul[idx] = (unsigned short)u;
+            }
+            count += __popc(m);
+        }
     }
     __syncwarp();
     if (lane == 0) c->n_surv[buf] = count <= kUnitCap ? count : -1;

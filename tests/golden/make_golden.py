@@ -87,6 +87,21 @@ def main():
     s["minimize_jitter"] = {"energy": en.tolist(), "accepted": st["accepted"].tolist(), "pose_checksum": float(out[:, :3].sum())}
     g["synth600"] = s
 
+    # cutoff extension (no reference row; pins the builder's own restatement): shipped data, 10 A shifted-Coulomb cutoff
+    pc = orc.params(cutoff=10.0)
+    c = {"cutoff": 10.0, "energy": {}, "chains": []}
+    for l in ligs:
+        e, a = orc.energy(arrays["223l_protein"], arrays[l + "_ligand"], pc, with_abs=True)
+        c["energy"][l] = {"energy": e, "abs_sum": a}
+    for lig, rotate, steps, seed, cid in (("223l", True, 300, 5, 1), ("421p", False, 300, 7, 0)):
+        pose, st, tr, et = orc.chain(arrays["223l_protein"], arrays[lig + "_ligand"], steps, rotate, 310.15,
+                                     orc.philox_stream(seed, cid), pc, want_trace=True)
+        c["chains"].append({"ligand": lig, "rotate": rotate, "steps": steps, "seed": seed, "chain_id": cid,
+                            "accept_trace": "".join(map(str, tr.tolist())), "accepted": int(st["accepted"]),
+                            "retries": int(st["retries"]), "draws": int(st["draws"]), "final_energy": float(st["final_energy"]),
+                            "pose_checksum": float(pose[:, :3].sum())})
+    g["cutoff10"] = c
+
     (HERE / "oracle_golden.json").write_text(json.dumps(g, indent=1))
     print("wrote", HERE / "sample_mol2.npz", HERE / "oracle_golden.json")
 

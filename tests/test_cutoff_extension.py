@@ -42,7 +42,43 @@ def test_oracle_cutoff_matches_numpy_and_defaults_off(orc, ddd):
     assert st["final_energy"] <= st["start_energy"] and st["steps"] == 150
 
 
+def test_oracle_cutoff_golden(orc, sample):
+    import json
+    from conftest import GOLDEN
+    g = json.loads((GOLDEN / "oracle_golden.json").read_text())["cutoff10"]
+    pc = orc.params(cutoff=g["cutoff"])
+    for l, v in g["energy"].items():
+        e, a = orc.energy(sample["223l_protein"], sample[l + "_ligand"], pc, with_abs=True)
+        assert e == v["energy"] and a == v["abs_sum"]
+    for c in g["chains"]:
+        pose, st, tr, _ = orc.chain(sample["223l_protein"], sample[c["ligand"] + "_ligand"], c["steps"], c["rotate"], T,
+                                    orc.philox_stream(c["seed"], c["chain_id"]), pc, want_trace=True)
+        assert "".join(map(str, tr.tolist())) == c["accept_trace"] and st["draws"] == c["draws"] and st["final_energy"] == c["final_energy"]
+
+
 # ------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_cutoff_golden_on_shipped_data(gpu, sample):
+    # the committed restatement outputs, reproduced on the GPU box without the CPU oracle in the loop
+    import json
+    from conftest import GOLDEN
+    g = json.loads((GOLDEN / "oracle_golden.json").read_text())["cutoff10"]
+    p64 = gpu.default_params(precision=gpu.PRECISION_F64, cutoff=g["cutoff"])
+    with gpu.Receptor(sample["223l_protein"]) as rec:
+        for l, v in g["energy"].items():
+            lig = sample[l + "_ligand"]
+            e, a = gpu.energy_batch(rec, np.array([0, len(lig)]), lig, p64, with_abs=True)
+            assert abs(e[0] - v["energy"]) <= 1e-13 * v["abs_sum"] and a[0] == pytest.approx(v["abs_sum"], rel=1e-12)
+        for c in g["chains"]:
+            lig = sample[c["ligand"] + "_ligand"]
+            poses, stats, trace = gpu.run_chains(rec, np.array([0, len(lig)]), lig, 1, c["steps"], c["rotate"], T, p64, seed=c["seed"],
+                                                 first_chain_id=c["chain_id"], want_trace=True)
+            assert "".join(map(str, trace[0].tolist())) == c["accept_trace"]
+            assert stats[0]["draws"] == c["draws"] and stats[0]["retries"] == c["retries"] and stats[0]["accepted"] == c["accepted"]
+            assert stats[0]["final_energy"] == pytest.approx(c["final_energy"], rel=1e-10)
+            assert float(poses[:, :3].sum()) == pytest.approx(c["pose_checksum"], abs=1e-7)
+
+
 @pytest.mark.gpu
 def test_energy_batch_with_cutoff_matches_the_restatement(gpu, orc, ddd):
     prot = ddd.synth.make_receptor(3000, seed=4)
