@@ -193,7 +193,7 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
 // units can be within the clamp distance of the ligand (their boxes are apart), so min(1/d, 1/clamp) == 1/d bit for bit.
 template <int A, bool CUT, bool CLAMP = true>
 __device__ __forceinline__ float warp_atoms_sum_f32(const float4 (&P)[A], const ulonglong2 *__restrict__ lf2, int n_pairs,
-                                                    float rinv_max, float rc_inv) {
+                                                    float rinv_max, float rc_inv, float *t_lo = nullptr) {
     f32x2 px[A], py[A], pz[A], s[A];
 #pragma unroll
     for (int a = 0; a < A; ++a) {
@@ -201,7 +201,8 @@ __device__ __forceinline__ float warp_atoms_sum_f32(const float4 (&P)[A], const 
         s[a] = pack2(0.f, 0.f);
     }
     const f32x2 m_rc = pack2(-rc_inv, -rc_inv);
-#pragma unroll 2
+    constexpr int kPairUnroll = A >= 8 ? 1 : 2;          // measured: 8 atoms per lane already fill the pipes
+#pragma unroll kPairUnroll
     for (int k = 0; k < n_pairs; ++k) {
         const ulonglong2 Lxy = lf2[2 * k], Lzq = lf2[2 * k + 1];
 #pragma unroll
@@ -221,18 +222,22 @@ __device__ __forceinline__ float warp_atoms_sum_f32(const float4 (&P)[A], const 
     }
     float t = 0.f;                       // fp32 within the lane's A * nl terms, fp64 beyond
 #pragma unroll
-    for (int a = 0; a < A; ++a) { float sa, sb; unpack2(s[a], sa, sb); t = fmaf(P[a].w, sa + sb, t); }
+    for (int a = 0; a < A; ++a) {
+        if (A == 8 && a == 4 && t_lo) { *t_lo = t; t = 0.f; }           // 8 atoms per lane = two groups of 4, summed separately
+        float sa, sb; unpack2(s[a], sa, sb); t = fmaf(P[a].w, sa + sb, t);
+    }
     return t;
 }
 
 template <int A, bool CUT, bool CLAMP = true>
 __device__ __forceinline__ float warp_units_sum_f32(const float4 *__restrict__ rec, const int (&ubase)[A],
-                                                    const ulonglong2 *__restrict__ lf2, int n_pairs, float rinv_max, float rc_inv) {
+                                                    const ulonglong2 *__restrict__ lf2, int n_pairs, float rinv_max, float rc_inv,
+                                                    float *t_lo = nullptr) {
     float4 P[A];
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int a = 0; a < A; ++a) P[a] = __ldg(rec + ubase[a] + lane);
-    return warp_atoms_sum_f32<A, CUT, CLAMP>(P, lf2, n_pairs, rinv_max, rc_inv);
+    return warp_atoms_sum_f32<A, CUT, CLAMP>(P, lf2, n_pairs, rinv_max, rc_inv, t_lo);
 }
 
 template <int A, bool CUT = false>

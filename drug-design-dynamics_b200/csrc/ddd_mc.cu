@@ -337,7 +337,9 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
         a.nl_cap = d.nl_cap;
         const bool precise = p->precision == DDD_PRECISION_F64;
         const bool cut = p->cutoff > 0;
-        const int ulb = cut ? 3 * kUnitCap * (int)sizeof(unsigned short) : 0;
+        const int n_groups4 = (int)((s->rec->n_units_s + 3) / 4);
+        const int gsum_bytes = (!cut && n_groups4 <= kMaxLaneSumGroups && s->rec->n_units_s >= 4 * kSmWarps) ? n_groups4 * 128 : 0;
+        const int ulb = (cut ? 3 * kUnitCap * (int)sizeof(unsigned short) : 0) + gsum_bytes;
         const bool fits_sm_engine = sm_smem_bytes(d.nl_cap, 1, ulb) <= dev.max_smem;      // very large ligands: one CTA per chain
         if (cut && (s->threads_override > 0 || !fits_sm_engine))
             return fail(DDD_EINVAL, "params.cutoff needs the SM-persistent engine (chain_threads 0 and a ligand that fits one SM's shared memory)");
@@ -363,7 +365,7 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
                 A.upi = 4 * std::max(DDD_SM_ITEM_QUADS, (quads + kSmMaxItems - 1) / kSmMaxItems);
             } else A.upi = std::max(1, (A.n_units + kSmWarps - 1) / kSmWarps);
             A.n_items = (A.n_units + A.upi - 1) / A.upi;
-            A.cut = cut ? 1 : 0; A.unit_list_bytes = ulb; A.out_units = nullptr;
+            A.cut = cut ? 1 : 0; A.unit_list_bytes = ulb - gsum_bytes; A.gsum_bytes = gsum_bytes; A.n_groups4 = n_groups4; A.out_units = nullptr;
             if (cut) {
                 if (!d.d_units) { if (int rc = dev_alloc(&d.d_units, (size_t)n_local)) return rc; }
                 A.out_units = d.d_units;
@@ -586,7 +588,7 @@ int ddd_receptor_create(const double *xyzq, int64_t n_atoms, ddd_receptor **out)
         }
         std::sort(key.begin(), key.end());
         r->n_units_s = (n_atoms + 31) / 32;
-        const int64_t n_pad_s = (r->n_units_s + 3) / 4 * 4 * 32;            // whole A=4 groups may be read
+        const int64_t n_pad_s = (r->n_units_s + 7) / 8 * 8 * 32;            // whole groups of 8 units may be read
         h32s.assign((size_t)std::max<int64_t>(n_pad_s, 1), make_float4(kPadCoord, kPadCoord, kPadCoord, 0.f));
         hbox.assign((size_t)std::max<int64_t>(2 * r->n_units_s, 1), make_float4(0, 0, 0, 0));
         h64s.resize((size_t)std::max<int64_t>(n_atoms, 1));
@@ -605,7 +607,8 @@ int ddd_receptor_create(const double *xyzq, int64_t n_atoms, ddd_receptor **out)
             hbox[(size_t)(2 * u + 1)] = make_float4(hi[0], hi[1], hi[2], 0.f);
         }
         const int64_t n_groups = (r->n_units_s + 3) / 4;
-        hgbox.assign((size_t)std::max<int64_t>(2 * n_groups, 1), make_float4(0, 0, 0, 0));
+        // boxes of 4-unit groups, padded to an even count with far-away boxes (a group of padding atoms only)
+        hgbox.assign((size_t)std::max<int64_t>(2 * ((n_groups + 1) / 2 * 2), 2), make_float4(kPadCoord, kPadCoord, kPadCoord, 0.f));
         for (int64_t g = 0; g < n_groups; ++g) {
             float4 lo = make_float4(3e38f, 3e38f, 3e38f, 0.f), hi = make_float4(-3e38f, -3e38f, -3e38f, 0.f);
             for (int64_t u = 4 * g; u < std::min<int64_t>(4 * g + 4, r->n_units_s); ++u) {

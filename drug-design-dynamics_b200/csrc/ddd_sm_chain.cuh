@@ -96,11 +96,15 @@ struct SmArgs {
     int upi, n_items;        // units per item; items per energy evaluation (<= kSmMaxItems)
     int cut;                 // cutoff extension on: fp32 sums run over the per-pose unit lists of the sorted receptor
     int unit_list_bytes;     // per slot: 3 * kUnitCap * 2 when cut, else 0
+    int gsum_bytes;          // per slot: 128 B per group of 4 units when the fp32 sums are kept per group and lane (see
+                             // sm_item_f32_groups), else 0
+    int n_groups4;           // groups of 4 units (128 receptor atoms)
     long long *out_units;    // nullable: per-chain count of receptor units evaluated (ddd_screen_pair_units)
 };
 
-__host__ __device__ inline size_t sm_smem_bytes(int nl_cap, int slots, int unit_list_bytes = 0) {
-    return kCtaHeaderBytes + (size_t)slots * (kSlotFixedBytes + (size_t)nl_cap * kAtomBytes + unit_list_bytes);
+constexpr int kMaxLaneSumGroups = 64;       // receptors up to 8 192 atoms keep per-group, per-lane fp32 sums
+__host__ __device__ inline size_t sm_smem_bytes(int nl_cap, int slots, int extra_bytes = 0) {
+    return kCtaHeaderBytes + (size_t)slots * (kSlotFixedBytes + (size_t)nl_cap * kAtomBytes + extra_bytes);
 }
 
 // Views into the CTA's shared memory: [live 16][keys 64] then per slot [ctl][item sums][uniform staging][base list][dyn list]
@@ -119,6 +123,8 @@ struct SlotView {
     __device__ __forceinline__ float4 *lf(int buf) const { return reinterpret_cast<float4 *>(pose + (size_t)cap * kAtomRecBytes) + (size_t)buf * cap; }
     // cutoff extension: ids of the receptor units within reach of pose buffer `buf`, ascending
     __device__ __forceinline__ unsigned short *units(int buf) const { return reinterpret_cast<unsigned short *>(pose + (size_t)cap * kAtomBytes) + buf * kUnitCap; }
+    // per-group, per-lane fp32 partial sums of the evaluation in flight (follows the unit lists)
+    __device__ __forceinline__ float *gsum(int ulb) const { return reinterpret_cast<float *>(pose + (size_t)cap * kAtomBytes + ulb); }
 };
 
 struct SmView {
@@ -127,7 +133,7 @@ struct SmView {
     __device__ __forceinline__ int *live() const { return reinterpret_cast<int *>(raw); }
     // scheduling key of a slot: the chain's step count while it has work to hand out, kKeyNone otherwise
     __device__ __forceinline__ int *keys() const { return reinterpret_cast<int *>(raw + 16); }
-    __device__ __forceinline__ unsigned char *block(int s) const { return raw + kCtaHeaderBytes + (size_t)s * (kSlotFixedBytes + cap * kAtomBytes + ulb); }
+    __device__ __forceinline__ unsigned char *block(int s) const { return raw + kCtaHeaderBytes + (size_t)s * (kSlotFixedBytes + cap * kAtomBytes + ulb); }   // ulb: all per-slot extras
     __device__ __forceinline__ SmSlotCtl *ctl(int s) const { return reinterpret_cast<SmSlotCtl *>(block(s)); }
     __device__ __forceinline__ double *items(int s) const { return reinterpret_cast<double *>(block(s) + sizeof(SmSlotCtl)); }
     __device__ __forceinline__ SlotView slot(int s) const {
@@ -154,23 +160,60 @@ __device__ __forceinline__ int ld_volatile(const int *p) { return *reinterpret_c
 __device__ __forceinline__ void st_volatile(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
 
 // ------------------------------------------------------------------ energy work items
+__device__ __forceinline__ bool boxes_apart(const float4 gmin, const float4 gmax, const float *lbox) {
+    return gmin.x - lbox[4] > 1e-3f || lbox[0] - gmax.x > 1e-3f || gmin.y - lbox[5] > 1e-3f ||
+           lbox[1] - gmax.y > 1e-3f || gmin.z - lbox[6] > 1e-3f || lbox[2] - gmax.z > 1e-3f;
+}
+
+// Receptors up to 8 192 atoms: the fp32 sum is kept PER GROUP (4 units = 128 atoms, 4 per lane) AND PER LANE in shared
+// memory -- gsum[g][lane] = the lane's fp32 sum over its 4 atoms x nL ligand atoms -- and added in (group, lane) order by
+// the serial phase.  No reduction on the item path, and the result does not depend on how the groups were cut into
+// items, so the item size is free to follow the load: long items (8 groups) while several chains share the SM, single
+// groups when one chain has it to itself.  Two adjacent groups go through the loop together (8 atoms per lane share every
+// ligand load) but keep separate sums.  The clamp d >= 1e-6 (:255-257) can only matter where a group's box touches the
+// pose's box; everywhere else min(1/d, 1e6) == 1/d exactly and the loop without the two FMNMX gives the same bits.
+__device__ __forceinline__ void sm_item_f32_groups(const SmArgs &A, const float4 *lf, const float *lbox, float *gsum, int nl, int g, int g1) {
+    const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
+    const int n_pairs = (nl + 1) >> 1;
+    const float rmax = A.c.prm.rinv_max;
+    const float4 *rec = A.c.rec.f32s;                 // Morton order: a group is spatially compact
+    const int lane = threadIdx.x & 31;
+    for (; g + 2 <= g1; g += 2) {
+        const bool apart = boxes_apart(__ldg(A.c.rec.gbox + 2 * g), __ldg(A.c.rec.gbox + 2 * g + 1), lbox) &&
+                           boxes_apart(__ldg(A.c.rec.gbox + 2 * g + 2), __ldg(A.c.rec.gbox + 2 * g + 3), lbox);
+        int ub[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) ub[a] = (4 * g + a) * 32;
+        float lo, hi;
+        if (apart) hi = warp_units_sum_f32<8, false, false>(rec, ub, lf2, n_pairs, rmax, 0.f, &lo);
+        else hi = warp_units_sum_f32<8, false, true>(rec, ub, lf2, n_pairs, rmax, 0.f, &lo);
+        gsum[g * 32 + lane] = lo;
+        gsum[(g + 1) * 32 + lane] = hi;
+    }
+    if (g < g1) {
+        const bool apart = boxes_apart(__ldg(A.c.rec.gbox + 2 * g), __ldg(A.c.rec.gbox + 2 * g + 1), lbox);
+        int ub[4] = {4 * g * 32, 4 * g * 32 + 32, 4 * g * 32 + 64, 4 * g * 32 + 96};
+        float t;
+        if (apart) t = warp_units_sum_f32<4, false, false>(rec, ub, lf2, n_pairs, rmax, 0.f);
+        else t = warp_units_sum_f32<4, false, true>(rec, ub, lf2, n_pairs, rmax, 0.f);
+        gsum[g * 32 + lane] = t;
+    }
+}
+
+// larger receptors: static items (runs of A.upi units), one fp64 sum per item
 __device__ __forceinline__ double sm_item_f32(const SmArgs &A, const float4 *lf, const float *lbox, int nl, int it) {
     const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
     const int n_pairs = (nl + 1) >> 1;
     int u = it * A.upi;
     const int u1 = min(u + A.upi, A.n_units);
     const float rmax = A.c.prm.rinv_max;
-    const float4 *rec = A.c.rec.f32s;                 // Morton order: a group of 4 units is spatially compact
+    const float4 *rec = A.c.rec.f32s;
     double acc = 0.0;
     if ((A.upi & 3) == 0) {
         for (; u + 4 <= u1; u += 4) {
-            // The clamp d >= 1e-6 (:255-257) can only matter where the group's box touches the ligand's box; everywhere
-            // else min(1/d, 1e6) == 1/d exactly and the loop without the two FMNMX gives the same bits.
             const float4 gmin = __ldg(A.c.rec.gbox + (u >> 1)), gmax = __ldg(A.c.rec.gbox + (u >> 1) + 1);
-            const bool apart = gmin.x - lbox[4] > 1e-3f || lbox[0] - gmax.x > 1e-3f || gmin.y - lbox[5] > 1e-3f ||
-                               lbox[1] - gmax.y > 1e-3f || gmin.z - lbox[6] > 1e-3f || lbox[2] - gmax.z > 1e-3f;
             int ub[4] = {u * 32, u * 32 + 32, u * 32 + 64, u * 32 + 96};
-            if (apart) acc += (double)warp_units_sum_f32<4, false, false>(rec, ub, lf2, n_pairs, rmax, 0.f);
+            if (boxes_apart(gmin, gmax, lbox)) acc += (double)warp_units_sum_f32<4, false, false>(rec, ub, lf2, n_pairs, rmax, 0.f);
             else acc += (double)warp_units_sum_f32<4, false, true>(rec, ub, lf2, n_pairs, rmax, 0.f);
         }
     } else {
@@ -594,6 +637,12 @@ __device__ __forceinline__ bool sm_publish(const SmArgs &A, const SmView &V, int
     // pair-sum items of this evaluation: the static cut of the receptor, or (cutoff extension, fp32 sums) runs of the
     // trial pose's unit list, 4*m units per item with m as small as the item-sum array allows
     int n_e = A.n_items, upi_e = A.upi;
+    if (A.gsum_bytes && mode == 0 && !A.cut) {          // per-group sums: items are scheduling granules only
+        const int live = ld_volatile(V.live());
+        const int gpi = live >= 4 ? 8 : live >= 2 ? 2 : 1;     // groups per item
+        upi_e = 4 * gpi;
+        n_e = (A.n_groups4 + gpi - 1) / gpi;
+    }
     if (A.cut) {
         const int ns = c->n_surv[c->i_trial];
         const int nu = ns >= 0 ? ns : A.c.rec.n_units_s;
@@ -637,8 +686,13 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
         stage = c->stage;
         spec_ready = c->has_spec != 0;
         const double *items = V.items(slot_id);
-        const int n_e = c->n_e;
-        for (int it = lane; it < n_e; it += 32) e += items[it];             // fixed order: independent of who computed what
+        if (A.gsum_bytes && c->mode == 0 && !A.cut) {                       // (group, lane) order: independent of the item cut
+            const float *gs = s.gsum(A.unit_list_bytes);
+            for (int g = 0; g < A.n_groups4; ++g) e += (double)gs[g * 32 + lane];
+        } else {
+            const int n_e = c->n_e;
+            for (int it = lane; it < n_e; it += 32) e += items[it];         // fixed order: independent of who computed what
+        }
         e = warp_sum(e);
     }
     for (;;) {
@@ -807,7 +861,7 @@ template <bool PRECISE>
 __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_constant__ SmArgs A) {
     extern __shared__ __align__(16) unsigned char ddd_sm_smem[];
     SmView V;
-    V.raw = ddd_sm_smem; V.slots = A.slots; V.cap = A.c.nl_cap; V.ulb = A.unit_list_bytes;
+    V.raw = ddd_sm_smem; V.slots = A.slots; V.cap = A.c.nl_cap; V.ulb = A.unit_list_bytes + A.gsum_bytes;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = A.slots;
     if (threadIdx.x == 0) *V.live() = K;
@@ -847,9 +901,14 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
             const int e_it = it - has_spec;
             const SlotView s = V.slot(sid);
             const int nl = c->nl, buf = c->i_trial;
-            const double sum = c->mode ? sm_item_f64(A, s, c, buf, nl, e_it)
-                             : A.cut ? sm_item_f32_cut(A, s, c, buf, nl, e_it) : sm_item_f32(A, s.lf(buf), c->lbox[buf], nl, e_it);
-            if (lane == 0) V.items(sid)[e_it] = sum;
+            if (c->mode == 0 && A.gsum_bytes && !A.cut) {
+                const int gpi = c->upi_e >> 2;
+                sm_item_f32_groups(A, s.lf(buf), c->lbox[buf], s.gsum(A.unit_list_bytes), nl, e_it * gpi, min((e_it + 1) * gpi, A.n_groups4));
+            } else {
+                const double sum = c->mode ? sm_item_f64(A, s, c, buf, nl, e_it)
+                                 : A.cut ? sm_item_f32_cut(A, s, c, buf, nl, e_it) : sm_item_f32(A, s.lf(buf), c->lbox[buf], nl, e_it);
+                if (lane == 0) V.items(sid)[e_it] = sum;
+            }
         }
         cta_fence();
         int d = 0;
