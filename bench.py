@@ -349,11 +349,11 @@ def main():
                    "pair_precision": "fp32 terms, fp64 accumulation", "chain_cta_threads": width, "chains_per_sm": slots, "chains_stopped_at_retry_bound": n_bailed,
                    "engine": "SM-persistent (one CTA per SM, speculative proposals)" if slots else "one CTA per chain",
                    "l2": f"receptor ({NP * 16 // 1024} KB fp32) and poses are L1/L2-resident by design; the kernel is FP32/MUFU-bound, HBM traffic ~0 "
-                         "(ncu: 1.7 MB read per launch), so no L2 flush applies",
+                         "(ncu: 1.9 MB per launch), so no L2 flush applies",
                    "parallelism": f"{world} x independent chain shards, no collective"},
         "wall_ms_per_step": wall_s * 1e3 / args.steps,
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                     "traffic": 2.43e7 if args.config == 2 else None, "traffic_source": "profiles/r01_sm_engine_ncu.md (dram__bytes_read+write of one launch; config 2 shape)", "peak_source": f"SMs*128 lanes*2*sm_max_mhz ({peaks['sm_max_mhz']:.0f} MHz from {peaks_src})",
+                     "traffic": 1.86e6 if args.config == 2 else None, "traffic_source": "profiles/r01_sm_engine_ncu.md (dram__bytes_read+write of one launch; config 2 shape)", "peak_source": f"SMs*128 lanes*2*sm_max_mhz ({peaks['sm_max_mhz']:.0f} MHz from {peaks_src})",
                      "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": work_pairs / args.steps / world,
                      "kernel_ms_per_launch": dev_s * 1e3 / args.steps,
                      "mufu_bound_frac_of_peak": 0.75, "frac_of_mufu_bound": achieved / fp32_peak / 0.75},

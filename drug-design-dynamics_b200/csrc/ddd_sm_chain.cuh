@@ -43,6 +43,9 @@ constexpr int kUnitCap    = 512;            // cutoff extension: receptor units 
 #ifndef DDD_NEAR_MARGIN
 #define DDD_NEAR_MARGIN 1.4
 #endif
+#ifndef DDD_GPI_BUSY
+#define DDD_GPI_BUSY 10
+#endif
 #ifndef DDD_SM_IDLE_NS
 #define DDD_SM_IDLE_NS 100
 #endif
@@ -639,7 +642,7 @@ __device__ __forceinline__ bool sm_publish(const SmArgs &A, const SmView &V, int
     int n_e = A.n_items, upi_e = A.upi;
     if (A.gsum_bytes && mode == 0 && !A.cut) {          // per-group sums: items are scheduling granules only
         const int live = ld_volatile(V.live());
-        const int gpi = live >= 4 ? 8 : live >= 2 ? 2 : 1;     // groups per item
+        const int gpi = live >= 4 ? DDD_GPI_BUSY : live >= 2 ? 2 : 1;     // groups per item
         upi_e = 4 * gpi;
         n_e = (A.n_groups4 + gpi - 1) / gpi;
     }
