@@ -43,14 +43,9 @@ constexpr int kUnitCap    = 512;            // cutoff extension: receptor units 
 #ifndef DDD_NEAR_MARGIN
 #define DDD_NEAR_MARGIN 1.4
 #endif
-#ifndef DDD_GPI_BUSY
-#define DDD_GPI_BUSY 10
-#endif
+constexpr int kGroupsPerItemBusy = 10;     // 128-atom groups per item while >= 4 chains share the SM (measured: 4/8/10/14/20 -> 54.9/55.8/56.1/56.3/52.8 %)
 #ifndef DDD_SM_IDLE_NS
 #define DDD_SM_IDLE_NS 100
-#endif
-#ifndef DDD_SM_PRIO
-#define DDD_SM_PRIO 1
 #endif
 constexpr double kNearMargin = DDD_NEAR_MARGIN;         // a near-pair list holds every ligand pair closer than MINDISTANCE + this
 
@@ -150,14 +145,8 @@ struct SmView {
 
 // Idle warps poll the scheduling keys with a short nanosleep in between.  (Blocking them on an mbarrier that flips on
 // every hand-out was measured slower on B200: the wake-up of try_wait costs more than the poll.)
-// CTA-scope acquire/release fence (the default __threadfence_block() is the sequentially-consistent MEMBAR.SC.CTA)
-#ifndef DDD_SM_FENCE_SC
-#define DDD_SM_FENCE_SC 0
-#endif
-__device__ __forceinline__ void cta_fence() {
-    if (DDD_SM_FENCE_SC) __threadfence_block();
-    else asm volatile("fence.acq_rel.cta;" ::: "memory");
-}
+// CTA-scope acquire/release fence (__threadfence_block() would be the sequentially-consistent MEMBAR.SC.CTA)
+__device__ __forceinline__ void cta_fence() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 
 __device__ __forceinline__ int ld_volatile(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 __device__ __forceinline__ void st_volatile(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
@@ -642,7 +631,7 @@ __device__ __forceinline__ bool sm_publish(const SmArgs &A, const SmView &V, int
     int n_e = A.n_items, upi_e = A.upi;
     if (A.gsum_bytes && mode == 0 && !A.cut) {          // per-group sums: items are scheduling granules only
         const int live = ld_volatile(V.live());
-        const int gpi = live >= 4 ? DDD_GPI_BUSY : live >= 2 ? 2 : 1;     // groups per item
+        const int gpi = live >= 4 ? kGroupsPerItemBusy : live >= 2 ? 2 : 1;     // groups per item
         upi_e = 4 * gpi;
         n_e = (A.n_groups4 + gpi - 1) / gpi;
     }
