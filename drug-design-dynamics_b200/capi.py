@@ -21,7 +21,7 @@ SYMBOLS = [
     "ddd_closest_atom_batch", "ddd_shift_closer_batch", "ddd_randomize_pose_batch",
     "ddd_screen_create", "ddd_screen_run", "ddd_screen_sync", "ddd_screen_last_kernel_ms",
     "ddd_screen_download", "ddd_screen_destroy", "ddd_screen_set_chain_threads", "ddd_screen_chain_threads",
-    "ddd_screen_set_chain_slots", "ddd_screen_chain_slots", "ddd_screen_rmsd", "ddd_screen_pair_units",
+    "ddd_screen_set_chain_slots", "ddd_screen_chain_slots", "ddd_screen_rmsd", "ddd_screen_pair_units", "ddd_screen_set_lj", "ddd_receptor_set_lj",
     "ddd_shard_plan", "ddd_device_info",
     "ddd_chain_kernel_info",
 ]
@@ -48,7 +48,7 @@ class Params(C.Structure):
         ("max_angle", C.c_double), ("jitter_width", C.c_double), ("clamp_distance", C.c_double),
         ("rigid_translation", C.c_double), ("rigid_angle", C.c_double),
         ("max_retries", C.c_int64), ("precision", C.c_int32), ("move_mode", C.c_int32),
-        ("cutoff", C.c_double),
+        ("cutoff", C.c_double), ("lj_scale", C.c_double), ("lj_cap", C.c_double),
     ]
 
 
@@ -110,6 +110,8 @@ def lib() -> C.CDLL:
         "ddd_screen_chain_slots": (i32, [vp]),
         "ddd_screen_rmsd": (C.c_int, [vp, vp, C.POINTER(dbl)]),
         "ddd_screen_pair_units": (C.c_int, [vp, vp]),
+        "ddd_screen_set_lj": (C.c_int, [vp, vp, vp]),
+        "ddd_receptor_set_lj": (C.c_int, [vp, vp, vp]),
         "ddd_screen_last_kernel_ms": (dbl, [vp]),
         "ddd_screen_download": (C.c_int, [vp, vp, vp]),
         "ddd_screen_destroy": (C.c_int, [vp]),
@@ -208,6 +210,12 @@ class Receptor:
         if not self._h:
             raise DddError(DDD_EINVAL, "receptor already destroyed")
         return self._h
+
+    def set_lj(self, sigma, epsilon):
+        """LJ extension: per-atom sigma / epsilon of the receptor"""
+        sg, ep = np.ascontiguousarray(sigma, dtype=np.float64), np.ascontiguousarray(epsilon, dtype=np.float64)
+        assert len(sg) == len(ep) == self.n_atoms
+        _check(lib().ddd_receptor_set_lj(self.handle, _ptr(sg), _ptr(ep)))
 
     def close(self):
         if self._h:
@@ -364,6 +372,12 @@ class Screen:
         stats = np.zeros(self.n_chains, dtype=STATS_DTYPE)
         _check(lib().ddd_screen_download(self._h, _ptr(out), _ptr(stats)))
         return out, stats
+
+    def set_lj(self, sigma, epsilon):
+        """LJ extension: per-atom sigma / epsilon of the ligands (CSR order)"""
+        sg, ep = np.ascontiguousarray(sigma, dtype=np.float64), np.ascontiguousarray(epsilon, dtype=np.float64)
+        assert len(sg) == len(ep) == int(self.offsets[-1])
+        _check(lib().ddd_screen_set_lj(self._h, _ptr(sg), _ptr(ep)))
 
     def pair_units(self):
         """cutoff extension: receptor atoms visited by each chain's pair sums, summed over its evaluations"""

@@ -32,6 +32,8 @@ struct DevParams {
     int move_mode, rotate;
     double cutoff;               // EXTENSION: > 0 = shifted-Coulomb cutoff radius (0: the reference's untruncated sum)
     float rc_inv;                // 1 / cutoff (0 when off)
+    double lj_scale, lj_cap;     // EXTENSION: Lennard-Jones 12-6 on top of the Coulomb term (lj_scale == 0: off)
+    float lj_c32, lj_cap32;      // 4 lj_scale / K (the fp32 sums are multiplied by K at the end), the cap on (sigma/d)^2
 };
 
 struct RecView {
@@ -46,6 +48,9 @@ struct RecView {
     const float4 *ubox;
     const float4 *gbox;          // (min xyz, max xyz) of every group of 4 consecutive units (128 atoms)
     int n_units_s;
+    // LJ extension: (sigma/2, sqrt(eps)) per atom; fp64 in input order and in Morton order, fp32 in Morton order
+    const double2 *lj64, *lj64s;
+    const float2 *lj32s;
 };
 
 // ------------------------------------------------------------------ Philox4x32-10
@@ -225,6 +230,62 @@ __device__ __forceinline__ float warp_atoms_sum_f32(const float4 (&P)[A], const 
     for (int a = 0; a < A; ++a) {
         if (A == 8 && a == 4 && t_lo) { *t_lo = t; t = 0.f; }           // 8 atoms per lane = two groups of 4, summed separately
         float sa, sb; unpack2(s[a], sa, sb); t = fmaf(P[a].w, sa + sb, t);
+    }
+    return t;
+}
+
+// LJ extension: Coulomb + Lennard-Jones 12-6 for A receptor atoms per lane.  Per ligand pair and receptor atom, on top of
+// the Coulomb ops: s = sigma_p/2 + sigma_l/2, x = min((s / d)^2, cap), x3 = x^3, lj += sqrt(eps_l) (x3^2 - x3):
+// FADD2, 4 FMUL2, 2 FFMA2, 2 FMNMX.  Returns  sum_p [ q_p sum_l q_l/d  +  c_lj sqrt(eps_p) sum_l sqrt(eps_l)(x^6 - x^3) ].
+// lj2[k] = (sigma0/2, sigma1/2, sqrt(eps0), sqrt(eps1)) of ligand pair k.
+template <int A, bool CUT>
+__device__ __forceinline__ float warp_units_sum_lj_f32(const float4 *__restrict__ rec, const float2 *__restrict__ rec_lj, const int (&ubase)[A],
+                                                       const ulonglong2 *__restrict__ lf2, const ulonglong2 *__restrict__ lj2, int n_pairs,
+                                                       float rinv_max, float rc_inv, float c_lj, float cap) {
+    f32x2 px[A], py[A], pz[A], hs[A], s[A], l[A];
+    float q[A], se[A];
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        const float4 P = __ldg(rec + ubase[a] + lane);
+        const float2 J = __ldg(rec_lj + ubase[a] + lane);
+        px[a] = pack2(P.x, P.x); py[a] = pack2(P.y, P.y); pz[a] = pack2(P.z, P.z); hs[a] = pack2(J.x, J.x);
+        q[a] = P.w; se[a] = J.y; s[a] = pack2(0.f, 0.f); l[a] = pack2(0.f, 0.f);
+    }
+    const f32x2 m_rc = pack2(-rc_inv, -rc_inv);
+    for (int k = 0; k < n_pairs; ++k) {
+        const ulonglong2 Lxy = lf2[2 * k], Lzq = lf2[2 * k + 1], Lj = lj2[k];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            const f32x2 dx = add2(px[a], Lxy.x), dy = add2(py[a], Lxy.y), dz = add2(pz[a], Lzq.x);
+            const f32x2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+            float d2a, d2b;
+            unpack2(d2, d2a, d2b);
+            const float ua = rsqrt_approx(d2a), ub = rsqrt_approx(d2b);          // 1/d, unclamped: the LJ core has its own cap
+            float ra = fminf(ua, rinv_max), rb = fminf(ub, rinv_max);
+            const f32x2 t = mul2(add2(hs[a], Lj.x), pack2(ua, ub));              // sigma_pl / d
+            float xa, xb;
+            unpack2(mul2(t, t), xa, xb);
+            xa = fminf(xa, cap); xb = fminf(xb, cap);
+            if (CUT) {
+                unpack2(add2(pack2(ra, rb), m_rc), ra, rb);
+                if (!(ra > 0.f)) xa = 0.f;                                       // beyond the cutoff: no LJ either
+                if (!(rb > 0.f)) xb = 0.f;
+                ra = fmaxf(ra, 0.f); rb = fmaxf(rb, 0.f);
+            }
+            const f32x2 x = pack2(xa, xb);
+            const f32x2 x3 = mul2(mul2(x, x), x);
+            l[a] = fma2(Lj.y, fma2(x3, x3, mul2(x3, pack2(-1.f, -1.f))), l[a]);
+            s[a] = fma2(Lzq.y, pack2(ra, rb), s[a]);
+        }
+    }
+    float t = 0.f;
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        float sa, sb, la, lb;
+        unpack2(s[a], sa, sb); unpack2(l[a], la, lb);
+        t = fmaf(q[a], sa + sb, t);
+        t = fmaf(c_lj * se[a], la + lb, t);
     }
     return t;
 }

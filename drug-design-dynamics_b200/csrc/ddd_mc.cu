@@ -72,6 +72,9 @@ DevParams make_dev_params(const ddd_params &p, int rotate, double temperature) {
     d.move_mode = p.move_mode; d.rotate = rotate ? 1 : 0;
     d.cutoff = p.cutoff > 0 ? p.cutoff : 0.0;
     d.rc_inv = p.cutoff > 0 ? (float)(1.0 / p.cutoff) : 0.f;
+    d.lj_scale = p.lj_scale; d.lj_cap = p.lj_cap;
+    d.lj_c32 = p.k_coulomb != 0.0 ? (float)(4.0 * p.lj_scale / p.k_coulomb) : 0.f;   // the fp32 sums are multiplied by K at the end
+    d.lj_cap32 = (float)p.lj_cap;
     return d;
 }
 
@@ -82,6 +85,8 @@ int check_params(const ddd_params *p) {
     if (p->move_mode != DDD_MOVE_REFERENCE && p->move_mode != DDD_MOVE_RIGID)
         return fail(DDD_EINVAL, "params.move_mode %d unknown", p->move_mode);
     if (!(p->cutoff >= 0.0) || std::isinf(p->cutoff)) return fail(DDD_EINVAL, "params.cutoff must be 0 (off) or a finite radius");
+    if (p->lj_scale != 0.0 && !(p->lj_cap > 0.0)) return fail(DDD_EINVAL, "params.lj_cap must be positive");
+    if (p->lj_scale != 0.0 && p->k_coulomb == 0.0) return fail(DDD_EINVAL, "params.lj_scale needs a non-zero k_coulomb");
     return DDD_OK;
 }
 
@@ -121,10 +126,16 @@ struct ddd_receptor {
     std::vector<Atom64 *> f64;
     std::vector<float4 *> f32s, ubox, gbox;   // Morton-sorted atoms, unit boxes, boxes of groups of 4 units
     std::vector<Atom64 *> f64s;
+    std::vector<int64_t> perm;               // sorted position -> input index (host)
+    // LJ extension: (sigma/2, sqrt(eps)) per atom, fp64 in input order and in Morton order, fp32 in Morton order
+    std::vector<double2 *> lj64, lj64s;
+    std::vector<float2 *> lj32s;
+    bool has_lj = false;
     int64_t n_units_s = 0;
     RecView view(size_t di) const {
         RecView v; v.f32 = f32[di]; v.f64 = f64[di]; v.n = (int)n; v.n_pad = (int)n_pad; v.cx = cx; v.cy = cy; v.cz = cz;
         v.f32s = f32s[di]; v.f64s = f64s[di]; v.ubox = ubox[di]; v.gbox = gbox[di]; v.n_units_s = (int)n_units_s;
+        v.lj64 = has_lj ? lj64[di] : nullptr; v.lj64s = has_lj ? lj64s[di] : nullptr; v.lj32s = has_lj ? lj32s[di] : nullptr;
         return v;
     }
 };
@@ -151,6 +162,7 @@ struct ScreenDev {
     int *d_queue = nullptr;                // SM-persistent engine: dynamic chain counter
     double *d_rmsd = nullptr;              // per-chain RMSD (ddd_screen_rmsd)
     long long *d_units = nullptr;          // per-chain receptor units evaluated (cutoff extension)
+    double2 *d_lig_lj = nullptr;           // LJ extension: (sigma/2, sqrt(eps)) of this device's slice of the ligand atoms
     float rmsd_ms = 0.f;
 };
 
@@ -165,6 +177,7 @@ struct ddd_screen {
     int threads_override = 0;              // > 0: one-CTA-per-chain engine with this CTA width
     int slots_override = 0;                // > 0: SM-persistent engine with this many chains per SM; both 0: automatic
     bool last_cut = false;                 // the last run used the cutoff extension
+    bool has_lj = false;                   // ddd_screen_set_lj was called
 };
 
 namespace {
@@ -213,7 +226,7 @@ void plan_shards(const int64_t *offsets, int64_t n_lig, int replicas, int n_shar
 void free_screen_dev(ScreenDev &sd) {
     cudaSetDevice(g_devs[sd.di].id);
     cudaFree(sd.d_offsets); cudaFree(sd.d_lig); cudaFree(sd.d_order); cudaFree(sd.d_out);
-    cudaFree(sd.d_stats); cudaFree(sd.d_trace); cudaFree(sd.d_rec); cudaFree(sd.d_rec_off); cudaFree(sd.d_queue); cudaFree(sd.d_rmsd); cudaFree(sd.d_units);
+    cudaFree(sd.d_stats); cudaFree(sd.d_trace); cudaFree(sd.d_rec); cudaFree(sd.d_rec_off); cudaFree(sd.d_queue); cudaFree(sd.d_rmsd); cudaFree(sd.d_units); cudaFree(sd.d_lig_lj);
     sd = ScreenDev();
 }
 
@@ -337,10 +350,16 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
         a.nl_cap = d.nl_cap;
         const bool precise = p->precision == DDD_PRECISION_F64;
         const bool cut = p->cutoff > 0;
+        const bool lj = p->lj_scale != 0.0;
+        if (lj && (!s->has_lj || !s->rec->has_lj))
+            return fail(DDD_EINVAL, "params.lj_scale != 0 needs ddd_receptor_set_lj and ddd_screen_set_lj");
+        if (lj && s->threads_override > 0) return fail(DDD_EINVAL, "params.lj_scale needs the SM-persistent engine");
         const int n_groups4 = (int)((s->rec->n_units_s + 3) / 4);
         const int gsum_bytes = (!cut && n_groups4 <= kMaxLaneSumGroups && s->rec->n_units_s >= 4 * kSmWarps) ? n_groups4 * 128 : 0;
-        const int ulb = (cut ? 3 * kUnitCap * (int)sizeof(unsigned short) : 0) + gsum_bytes;
+        const int lj_bytes = lj ? d.nl_cap * 24 : 0;                          // per ligand atom: (sigma/2, sqrt eps) fp64 + packed fp32
+        const int ulb = (cut ? 3 * kUnitCap * (int)sizeof(unsigned short) : 0) + gsum_bytes + lj_bytes;
         const bool fits_sm_engine = sm_smem_bytes(d.nl_cap, 1, ulb) <= dev.max_smem;      // very large ligands: one CTA per chain
+        if (lj && !fits_sm_engine) return fail(DDD_ELIMIT, "params.lj_scale: the ligand does not fit one SM's shared memory");
         if (cut && (s->threads_override > 0 || !fits_sm_engine))
             return fail(DDD_EINVAL, "params.cutoff needs the SM-persistent engine (chain_threads 0 and a ligand that fits one SM's shared memory)");
         if (cut && s->rec->n_units_s > 65535) return fail(DDD_ELIMIT, "params.cutoff supports receptors up to 2097120 atoms");
@@ -365,7 +384,7 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
                 A.upi = 4 * std::max(DDD_SM_ITEM_QUADS, (quads + kSmMaxItems - 1) / kSmMaxItems);
             } else A.upi = std::max(1, (A.n_units + kSmWarps - 1) / kSmWarps);
             A.n_items = (A.n_units + A.upi - 1) / A.upi;
-            A.cut = cut ? 1 : 0; A.unit_list_bytes = ulb - gsum_bytes; A.gsum_bytes = gsum_bytes; A.n_groups4 = n_groups4; A.out_units = nullptr;
+            A.cut = cut ? 1 : 0; A.unit_list_bytes = ulb - gsum_bytes - lj_bytes; A.gsum_bytes = gsum_bytes; A.lj_bytes = lj_bytes; A.lig_lj = d.d_lig_lj; A.n_groups4 = n_groups4; A.out_units = nullptr;
             if (cut) {
                 if (!d.d_units) { if (int rc = dev_alloc(&d.d_units, (size_t)n_local)) return rc; }
                 A.out_units = d.d_units;
@@ -529,6 +548,8 @@ void ddd_params_default(ddd_params *p) {
     p->precision = DDD_PRECISION_F32;
     p->move_mode = DDD_MOVE_REFERENCE;
     p->cutoff = 0.0;               // extension, off: every pair is summed (metropolis.go:249-259)
+    p->lj_scale = 0.0;             // extension, off: Coulomb only (metropolis.go:258)
+    p->lj_cap = 4.0;
 }
 
 // pure host logic, usable without a device: chains [out_begin[k], out_begin[k+1]) -> shard k
@@ -592,8 +613,10 @@ int ddd_receptor_create(const double *xyzq, int64_t n_atoms, ddd_receptor **out)
         h32s.assign((size_t)std::max<int64_t>(n_pad_s, 1), make_float4(kPadCoord, kPadCoord, kPadCoord, 0.f));
         hbox.assign((size_t)std::max<int64_t>(2 * r->n_units_s, 1), make_float4(0, 0, 0, 0));
         h64s.resize((size_t)std::max<int64_t>(n_atoms, 1));
+        r->perm.resize((size_t)n_atoms);
         for (int64_t i = 0; i < n_atoms; ++i) {
             const int64_t src = key[(size_t)i].second;
+            r->perm[(size_t)i] = src;
             h32s[(size_t)i] = h32[(size_t)src];
             h64s[(size_t)i] = Atom64{xyzq[4 * src], xyzq[4 * src + 1], xyzq[4 * src + 2], xyzq[4 * src + 3]};
         }
@@ -625,6 +648,7 @@ int ddd_receptor_create(const double *xyzq, int64_t n_atoms, ddd_receptor **out)
     r->ubox.assign(g_devs.size(), nullptr);
     r->f64s.assign(g_devs.size(), nullptr);
     r->gbox.assign(g_devs.size(), nullptr);
+    r->lj64.assign(g_devs.size(), nullptr); r->lj64s.assign(g_devs.size(), nullptr); r->lj32s.assign(g_devs.size(), nullptr);
     int rc = DDD_OK;
     for (size_t di = 0; di < g_devs.size() && !rc; ++di) {
         cudaError_t ce = cudaSetDevice(g_devs[di].id);
@@ -651,13 +675,47 @@ int ddd_receptor_destroy(ddd_receptor *r) {
     for (size_t di = 0; di < r->f32.size() && di < g_devs.size(); ++di) {
         cudaSetDevice(g_devs[di].id);
         cudaFree(r->f32[di]); cudaFree(r->f64[di]);
-        if (di < r->f32s.size()) { cudaFree(r->f32s[di]); cudaFree(r->ubox[di]); cudaFree(r->f64s[di]); cudaFree(r->gbox[di]); }
+        if (di < r->f32s.size()) { cudaFree(r->f32s[di]); cudaFree(r->ubox[di]); cudaFree(r->f64s[di]); cudaFree(r->gbox[di]);
+                                    cudaFree(r->lj64[di]); cudaFree(r->lj64s[di]); cudaFree(r->lj32s[di]); }
     }
     delete r;
     return DDD_OK;
 }
 
 int64_t ddd_receptor_num_atoms(const ddd_receptor *r) { return r ? r->n : -1; }
+
+int ddd_receptor_set_lj(ddd_receptor *r, const double *sigma, const double *epsilon) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    REQUIRE_INIT();
+    if (!r) return fail(DDD_EINVAL, "receptor is NULL");
+    if ((sigma == nullptr) != (epsilon == nullptr)) return fail(DDD_EINVAL, "sigma and epsilon must be given together");
+    if (!sigma) { r->has_lj = false; return DDD_OK; }
+    const int64_t n = r->n;
+    const size_t n_pad = (size_t)((r->n_units_s + 7) / 8 * 8 * 32);
+    std::vector<double2> a((size_t)std::max<int64_t>(n, 1)), as((size_t)std::max<int64_t>(n, 1));
+    std::vector<float2> fs(std::max<size_t>(n_pad, 1), make_float2(0.f, 0.f));          // padding atoms: epsilon = 0
+    for (int64_t i = 0; i < n; ++i) {
+        if (!(sigma[i] >= 0.0) || !(epsilon[i] >= 0.0)) return fail(DDD_EINVAL, "sigma/epsilon of receptor atom %lld is negative or NaN", (long long)i);
+        a[(size_t)i] = make_double2(0.5 * sigma[i], std::sqrt(epsilon[i]));
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        as[(size_t)i] = a[(size_t)r->perm[(size_t)i]];
+        fs[(size_t)i] = make_float2((float)as[(size_t)i].x, (float)as[(size_t)i].y);
+    }
+    for (size_t di = 0; di < g_devs.size(); ++di) {
+        CUDA_TRY(cudaSetDevice(g_devs[di].id));
+        if (!r->lj64[di]) {
+            if (int rc = dev_alloc(&r->lj64[di], a.size())) return rc;
+            if (int rc = dev_alloc(&r->lj64s[di], as.size())) return rc;
+            if (int rc = dev_alloc(&r->lj32s[di], fs.size())) return rc;
+        }
+        CUDA_TRY(cudaMemcpy(r->lj64[di], a.data(), sizeof(double2) * a.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(r->lj64s[di], as.data(), sizeof(double2) * as.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(r->lj32s[di], fs.data(), sizeof(float2) * fs.size(), cudaMemcpyHostToDevice));
+    }
+    r->has_lj = true;
+    return DDD_OK;
+}
 
 // ------------------------------------------------------------------ CalculateEnergy batch
 int ddd_energy_batch(const ddd_receptor *r, const int64_t *offsets, const double *lig_xyzq, int64_t n_lig,
@@ -666,6 +724,7 @@ int ddd_energy_batch(const ddd_receptor *r, const int64_t *offsets, const double
     REQUIRE_INIT();
     if (!r) return fail(DDD_EINVAL, "receptor is NULL");
     if (int rc = check_params(p)) return rc;
+    if (p->lj_scale != 0.0) return fail(DDD_EINVAL, "params.lj_scale: ligand LJ parameters travel with a screen (run it with 0 steps for energies)");
     int64_t max_nl = 0;
     if (int rc = check_csr(offsets, n_lig, lig_xyzq, &max_nl)) return rc;
     if (n_lig == 0) return DDD_OK;
@@ -715,6 +774,7 @@ int ddd_run_chains(const ddd_receptor *r, const int64_t *offsets, const double *
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     REQUIRE_INIT();
     if (int rc = check_params(p)) return rc;
+    if (p->lj_scale != 0.0) return fail(DDD_EINVAL, "params.lj_scale: ligand LJ parameters travel with a screen (ddd_screen_create + ddd_screen_set_lj)");
     ddd_screen *s = nullptr;
     if (int rc = screen_create_impl(r, offsets, lig_xyzq, n_lig, replicas, first_chain_id, &s)) return rc;
     int rc = screen_run_impl(s, steps_per_chain, rotate, temperature, p, seed, recorded, recorded_offsets, out_accept_trace != nullptr);
@@ -988,6 +1048,26 @@ int ddd_screen_pair_units(ddd_screen *s, int64_t *out_receptor_atoms) {
         CUDA_TRY(cudaMemcpy(out_receptor_atoms + d.c0, d.d_units, sizeof(int64_t) * (size_t)n_local, cudaMemcpyDeviceToHost));
         for (int64_t i = d.c0; i < d.c1; ++i) out_receptor_atoms[i] *= 32;
     }
+    return DDD_OK;
+}
+
+int ddd_screen_set_lj(ddd_screen *s, const double *sigma, const double *epsilon) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    REQUIRE_INIT();
+    if (!s) return fail(DDD_EINVAL, "screen is NULL");
+    if (!sigma || !epsilon) return fail(DDD_EINVAL, "sigma/epsilon is NULL");
+    for (auto &d : s->devs) {
+        std::vector<double2> h((size_t)std::max<int64_t>(d.n_atoms_in, 1));
+        for (int64_t i = 0; i < d.n_atoms_in; ++i) {
+            const double sg = sigma[d.atom_base + i], ep = epsilon[d.atom_base + i];
+            if (!(sg >= 0.0) || !(ep >= 0.0)) return fail(DDD_EINVAL, "sigma/epsilon of ligand atom %lld is negative or NaN", (long long)(d.atom_base + i));
+            h[(size_t)i] = make_double2(0.5 * sg, std::sqrt(ep));
+        }
+        CUDA_TRY(cudaSetDevice(g_devs[d.di].id));
+        if (!d.d_lig_lj) { if (int rc = dev_alloc(&d.d_lig_lj, h.size())) return rc; }
+        CUDA_TRY(cudaMemcpy(d.d_lig_lj, h.data(), sizeof(double2) * h.size(), cudaMemcpyHostToDevice));
+    }
+    s->has_lj = true;
     return DDD_OK;
 }
 

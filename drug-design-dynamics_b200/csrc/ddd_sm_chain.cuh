@@ -97,6 +97,8 @@ struct SmArgs {
     int gsum_bytes;          // per slot: 128 B per group of 4 units when the fp32 sums are kept per group and lane (see
                              // sm_item_f32_groups), else 0
     int n_groups4;           // groups of 4 units (128 receptor atoms)
+    int lj_bytes;            // LJ extension: per slot 24 B per ligand atom ((sigma/2, sqrt eps) fp64 + pair-packed fp32), else 0
+    const double2 *lig_lj;   // LJ extension: (sigma/2, sqrt eps) of the ligand atoms of this launch (atom_base-relative)
     long long *out_units;    // nullable: per-chain count of receptor units evaluated (ddd_screen_pair_units)
 };
 
@@ -123,6 +125,10 @@ struct SlotView {
     __device__ __forceinline__ unsigned short *units(int buf) const { return reinterpret_cast<unsigned short *>(pose + (size_t)cap * kAtomBytes) + buf * kUnitCap; }
     // per-group, per-lane fp32 partial sums of the evaluation in flight (follows the unit lists)
     __device__ __forceinline__ float *gsum(int ulb) const { return reinterpret_cast<float *>(pose + (size_t)cap * kAtomBytes + ulb); }
+    // LJ extension (follows the group sums): (sigma/2, sqrt eps) per ligand atom in fp64, then pair-packed fp32
+    // (sigma0/2, sigma1/2, sqrt eps0, sqrt eps1) per ligand pair
+    __device__ __forceinline__ double2 *lj64(int off) const { return reinterpret_cast<double2 *>(pose + (size_t)cap * kAtomBytes + off); }
+    __device__ __forceinline__ float4 *ljf(int off) const { return reinterpret_cast<float4 *>(pose + (size_t)cap * kAtomBytes + off + (size_t)cap * 16); }
 };
 
 struct SmView {
@@ -164,12 +170,20 @@ __device__ __forceinline__ bool boxes_apart(const float4 gmin, const float4 gmax
 // groups when one chain has it to itself.  Two adjacent groups go through the loop together (8 atoms per lane share every
 // ligand load) but keep separate sums.  The clamp d >= 1e-6 (:255-257) can only matter where a group's box touches the
 // pose's box; everywhere else min(1/d, 1e6) == 1/d exactly and the loop without the two FMNMX gives the same bits.
-__device__ __forceinline__ void sm_item_f32_groups(const SmArgs &A, const float4 *lf, const float *lbox, float *gsum, int nl, int g, int g1) {
+__device__ __forceinline__ void sm_item_f32_groups(const SmArgs &A, const float4 *lf, const float4 *ljf, const float *lbox, float *gsum, int nl, int g, int g1) {
     const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
+    const ulonglong2 *ljp = reinterpret_cast<const ulonglong2 *>(ljf);
     const int n_pairs = (nl + 1) >> 1;
     const float rmax = A.c.prm.rinv_max;
     const float4 *rec = A.c.rec.f32s;                 // Morton order: a group is spatially compact
     const int lane = threadIdx.x & 31;
+    if (A.lj_bytes) {                                   // LJ extension: one group at a time, Coulomb + 12-6
+        for (; g < g1; ++g) {
+            int ub[4] = {4 * g * 32, 4 * g * 32 + 32, 4 * g * 32 + 64, 4 * g * 32 + 96};
+            gsum[g * 32 + lane] = warp_units_sum_lj_f32<4, false>(rec, A.c.rec.lj32s, ub, lf2, ljp, n_pairs, rmax, 0.f, A.c.prm.lj_c32, A.c.prm.lj_cap32);
+        }
+        return;
+    }
     for (; g + 2 <= g1; g += 2) {
         const bool apart = boxes_apart(__ldg(A.c.rec.gbox + 2 * g), __ldg(A.c.rec.gbox + 2 * g + 1), lbox) &&
                            boxes_apart(__ldg(A.c.rec.gbox + 2 * g + 2), __ldg(A.c.rec.gbox + 2 * g + 3), lbox);
@@ -193,7 +207,7 @@ __device__ __forceinline__ void sm_item_f32_groups(const SmArgs &A, const float4
 }
 
 // larger receptors: static items (runs of A.upi units), one fp64 sum per item
-__device__ __forceinline__ double sm_item_f32(const SmArgs &A, const float4 *lf, const float *lbox, int nl, int it) {
+__device__ __forceinline__ double sm_item_f32(const SmArgs &A, const float4 *lf, const float4 *ljf, const float *lbox, int nl, int it) {
     const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
     const int n_pairs = (nl + 1) >> 1;
     int u = it * A.upi;
@@ -201,6 +215,18 @@ __device__ __forceinline__ double sm_item_f32(const SmArgs &A, const float4 *lf,
     const float rmax = A.c.prm.rinv_max;
     const float4 *rec = A.c.rec.f32s;
     double acc = 0.0;
+    if (A.lj_bytes) {                                   // LJ extension
+        const ulonglong2 *ljp = reinterpret_cast<const ulonglong2 *>(ljf);
+        for (; u + 4 <= u1; u += 4) {
+            int ub[4] = {u * 32, u * 32 + 32, u * 32 + 64, u * 32 + 96};
+            acc += (double)warp_units_sum_lj_f32<4, false>(rec, A.c.rec.lj32s, ub, lf2, ljp, n_pairs, rmax, 0.f, A.c.prm.lj_c32, A.c.prm.lj_cap32);
+        }
+        for (; u < u1; ++u) {
+            int ub[1] = {u * 32};
+            acc += (double)warp_units_sum_lj_f32<1, false>(rec, A.c.rec.lj32s, ub, lf2, ljp, n_pairs, rmax, 0.f, A.c.prm.lj_c32, A.c.prm.lj_cap32);
+        }
+        return warp_sum(acc);
+    }
     if ((A.upi & 3) == 0) {
         for (; u + 4 <= u1; u += 4) {
             const float4 gmin = __ldg(A.c.rec.gbox + (u >> 1)), gmax = __ldg(A.c.rec.gbox + (u >> 1) + 1);
@@ -230,6 +256,20 @@ __device__ __forceinline__ double sm_item_f32_cut(const SmArgs &A, const SlotVie
     const float rmax = A.c.prm.rinv_max, rci = A.c.prm.rc_inv;
     const float4 *rec = A.c.rec.f32s;
     double acc = 0.0;
+    if (A.lj_bytes) {                                   // LJ extension
+        const ulonglong2 *ljp = reinterpret_cast<const ulonglong2 *>(s.ljf(A.unit_list_bytes + A.gsum_bytes));
+        for (; j + 4 <= j1; j += 4) {
+            int ub[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) ub[a] = 32 * (ns >= 0 ? (int)ul[j + a] : j + a);
+            acc += (double)warp_units_sum_lj_f32<4, true>(rec, A.c.rec.lj32s, ub, lf2, ljp, n_pairs, rmax, rci, A.c.prm.lj_c32, A.c.prm.lj_cap32);
+        }
+        for (; j < j1; ++j) {
+            int ub[1] = {32 * (ns >= 0 ? (int)ul[j] : j)};
+            acc += (double)warp_units_sum_lj_f32<1, true>(rec, A.c.rec.lj32s, ub, lf2, ljp, n_pairs, rmax, rci, A.c.prm.lj_c32, A.c.prm.lj_cap32);
+        }
+        return warp_sum(acc);
+    }
     // the sorted receptor of a large complex lives in L2, not L1: the next group's atoms are prefetched into L1 while
     // this group's pairs are summed
     const int lane = threadIdx.x & 31;
@@ -251,9 +291,20 @@ __device__ __forceinline__ double sm_item_f32_cut(const SmArgs &A, const SlotVie
     return warp_sum(acc);
 }
 
+// LJ extension, one pair in fp64, in the CPU restatement's expression order: pj / lj = (sigma/2, sqrt eps)
+__device__ __forceinline__ double lj_term(const DevParams &P, const double2 pj, const double2 lj, double d2) {
+    const double sg = pj.x + lj.x;
+    double x = d2 > 0 ? sg * sg / d2 : P.lj_cap;
+    if (!(x < P.lj_cap)) x = P.lj_cap;
+    const double x3 = x * x * x;
+    return P.lj_scale * 4.0 * (pj.y * lj.y) * (x3 * x3 - x3);
+}
+
 // the reference's per-term fp64 arithmetic (:253-258) for the receptor atoms of one item
 __device__ __forceinline__ double sm_item_f64(const SmArgs &A, const SlotView &s, const SmSlotCtl *c, int buf, int nl, int it) {
     const double K = A.c.prm.k_coulomb, clampd = A.c.prm.clamp_distance, cutoff = A.c.prm.cutoff;
+    const bool lj = A.lj_bytes != 0;
+    const double2 *ljl = s.lj64(A.unit_list_bytes + A.gsum_bytes);
     double e = 0.0;
     if (A.cut) {                                                          // the pose's cell-list units, exact per-pair test
         const int ns = c->n_surv[buf];
@@ -264,13 +315,17 @@ __device__ __forceinline__ double sm_item_f64(const SmArgs &A, const SlotView &s
             const int p = 32 * (ns >= 0 ? (int)ul[j] : j) + (int)(threadIdx.x & 31);
             if (p >= A.c.rec.n) continue;
             const Atom64 P = A.c.rec.f64s[p];
+            const double2 PJ = lj ? A.c.rec.lj64s[p] : make_double2(0.0, 0.0);
             for (int l = 0; l < nl; ++l) {
                 const double *L = s.xyz(buf, l);
                 const double ddx = P.x - L[0], ddy = P.y - L[1], ddz = P.z - L[2];
-                double d = sqrt(ddx * ddx + ddy * ddy + ddz * ddz);
+                const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+                double d = sqrt(d2);
                 if (!(d < cutoff)) continue;
                 if (d < clampd) d = clampd;
-                e += K * (P.q * s.q(l)) / d - K * (P.q * s.q(l)) / cutoff;
+                double term = K * (P.q * s.q(l)) / d - K * (P.q * s.q(l)) / cutoff;
+                if (lj) term += lj_term(A.c.prm, PJ, ljl[l], d2);
+                e += term;
             }
         }
         return warp_sum(e);
@@ -278,14 +333,17 @@ __device__ __forceinline__ double sm_item_f64(const SmArgs &A, const SlotView &s
     const int p0 = it * A.upi * 32, p1 = min((it + 1) * A.upi * 32, A.c.rec.n);
     for (int p = p0 + (int)(threadIdx.x & 31); p < p1; p += 32) {
         const Atom64 P = A.c.rec.f64[p];
+        const double2 PJ = lj ? A.c.rec.lj64[p] : make_double2(0.0, 0.0);
         for (int l = 0; l < nl; ++l) {
             const double *L = s.xyz(buf, l);
             const double ddx = P.x - L[0], ddy = P.y - L[1], ddz = P.z - L[2];
-            double d = sqrt(ddx * ddx + ddy * ddy + ddz * ddz);          // :253 (Pow(x,2) == x*x)
+            const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
+            double d = sqrt(d2);                                          // :253 (Pow(x,2) == x*x)
             if (cutoff > 0 && !(d < cutoff)) continue;                    // EXTENSION: shifted-Coulomb cutoff
             if (d < clampd) d = clampd;                                   // :255-257
             double term = K * (P.q * s.q(l)) / d;                         // :258
             if (cutoff > 0) term -= K * (P.q * s.q(l)) / cutoff;
+            if (lj) term += lj_term(A.c.prm, PJ, ljl[l], d2);
             e += term;
         }
     }
@@ -710,6 +768,17 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 o[0] = src[4 * i]; o[1] = src[4 * i + 1]; o[2] = src[4 * i + 2];
                 s.q(i) = src[4 * i + 3];
             }
+            if (A.lj_bytes) {                                                   // LJ extension: the ligand's (sigma/2, sqrt eps)
+                const int lo = A.unit_list_bytes + A.gsum_bytes;
+                const double2 *lsrc = A.lig_lj + (off - a.atom_base);
+                float *lf4 = reinterpret_cast<float *>(s.ljf(lo));
+                for (int i = lane; i < nl + (nl & 1); i += 32) {
+                    const double2 v = i < nl ? lsrc[i] : make_double2(0.0, 0.0);
+                    if (i < nl) s.lj64(lo)[i] = v;
+                    lf4[4 * (i >> 1) + (i & 1)] = (float)v.x;
+                    lf4[4 * (i >> 1) + 2 + (i & 1)] = (float)v.y;
+                }
+            }
             if (lane == 0) {
                 c->nl = nl; c->status = 0; c->rep = (int)(chain - lig * a.replicas); c->bailed = 0;
                 c->i_cur = 0; c->i_trial = 0; c->i_spec = 1; c->has_spec = 0;
@@ -853,7 +922,7 @@ template <bool PRECISE>
 __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_constant__ SmArgs A) {
     extern __shared__ __align__(16) unsigned char ddd_sm_smem[];
     SmView V;
-    V.raw = ddd_sm_smem; V.slots = A.slots; V.cap = A.c.nl_cap; V.ulb = A.unit_list_bytes + A.gsum_bytes;
+    V.raw = ddd_sm_smem; V.slots = A.slots; V.cap = A.c.nl_cap; V.ulb = A.unit_list_bytes + A.gsum_bytes + A.lj_bytes;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = A.slots;
     if (threadIdx.x == 0) *V.live() = K;
@@ -895,10 +964,12 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
             const int nl = c->nl, buf = c->i_trial;
             if (c->mode == 0 && A.gsum_bytes && !A.cut) {
                 const int gpi = c->upi_e >> 2;
-                sm_item_f32_groups(A, s.lf(buf), c->lbox[buf], s.gsum(A.unit_list_bytes), nl, e_it * gpi, min((e_it + 1) * gpi, A.n_groups4));
+                sm_item_f32_groups(A, s.lf(buf), s.ljf(A.unit_list_bytes + A.gsum_bytes), c->lbox[buf], s.gsum(A.unit_list_bytes), nl,
+                                   e_it * gpi, min((e_it + 1) * gpi, A.n_groups4));
             } else {
                 const double sum = c->mode ? sm_item_f64(A, s, c, buf, nl, e_it)
-                                 : A.cut ? sm_item_f32_cut(A, s, c, buf, nl, e_it) : sm_item_f32(A, s.lf(buf), c->lbox[buf], nl, e_it);
+                                 : A.cut ? sm_item_f32_cut(A, s, c, buf, nl, e_it)
+                                         : sm_item_f32(A, s.lf(buf), s.ljf(A.unit_list_bytes + A.gsum_bytes), c->lbox[buf], nl, e_it);
                 if (lane == 0) V.items(sid)[e_it] = sum;
             }
         }

@@ -74,6 +74,11 @@ typedef struct ddd_params {
                                    K q_p q_l (1/max(d, clamp) - 1/cutoff), a pair beyond it nothing.  The chains then
                                    evaluate only the receptor cells within reach of the pose (uniform-grid cell list
                                    built at ddd_receptor_create); needs the SM-persistent engine. */
+    double  lj_scale;           /* EXTENSION, default 0 = off (the reference has no Lennard-Jones term).  != 0: every pair
+                                   of the Coulomb sum also adds lj_scale * 4 sqrt(eps_p eps_l) (x^6 - x^3),
+                                   x = min(((sigma_p + sigma_l)/2)^2 / d^2, lj_cap).  Needs ddd_receptor_set_lj and
+                                   ddd_screen_set_lj (the Go data model carries no atom types: datatypes.go:18-21). */
+    double  lj_cap;             /* cap on (sigma/d)^2 (4: the 12-6 core is frozen below d = sigma/2) */
 } ddd_params;
 
 /* per-chain counters returned by ddd_run_chains (no reference counterpart; SURVEY 5 "metrics") */
@@ -104,6 +109,8 @@ void        ddd_params_default(ddd_params *p);
 int     ddd_receptor_create(const double *xyzq, int64_t n_atoms, ddd_receptor **out);
 int     ddd_receptor_destroy(ddd_receptor *r);
 int64_t ddd_receptor_num_atoms(const ddd_receptor *r);
+/* LJ extension: per-atom sigma (A) and epsilon of the receptor (n_atoms entries each); NULL, NULL clears them */
+int     ddd_receptor_set_lj(ddd_receptor *r, const double *sigma, const double *epsilon);
 
 /* ---- CalculateEnergy (metropolis.go:247-262), batched over ligand poses ----
  * out_energy[n_lig]; out_abs_sum (nullable) receives sum|term| (fp64) for conditioning reports. */
@@ -184,6 +191,9 @@ int    ddd_screen_download(ddd_screen *s, double *out_xyzq, ddd_chain_stats *out
  * out_rmsd[c] = CalculateRMSD(final pose of chain c, start pose of its ligand) (validateResults.go:50-65).
  * out_kernel_ms (nullable): CUDA-event time of the RMSD kernel, max over devices. */
 int    ddd_screen_rmsd(ddd_screen *s, double *out_rmsd, double *out_kernel_ms);
+/* LJ extension: per-atom sigma / epsilon of the screen's ligands, in the CSR order of ddd_screen_create
+ * (offsets[n_lig] entries each); used by runs whose params.lj_scale != 0 */
+int    ddd_screen_set_lj(ddd_screen *s, const double *sigma, const double *epsilon);
 /* Cutoff extension (params.cutoff > 0): out[c] = receptor atoms that chain c's pair sums visited, summed over its
  * evaluations (what the cell-list queries of its poses returned); x nL(c) = pair terms evaluated.  Zeros without cutoff. */
 int    ddd_screen_pair_units(ddd_screen *s, int64_t *out_receptor_atoms);

@@ -36,6 +36,9 @@ void orc_params_default(orc_params *p) {
     p->rigid_angle = 0.79;
     p->max_retries = 1024;
     p->cutoff = 0.0;             /* extension, off: the reference sums every pair */
+    p->lj_scale = 0.0;           /* extension, off: the reference has no Lennard-Jones term */
+    p->lj_cap = 4.0;
+    p->prot_lj = NULL; p->lig_lj = NULL;
 }
 
 /* ------------------------------------------------------------------ philox */
@@ -277,6 +280,7 @@ double orc_calculate_energy_abs(const orc_atom *prot, int64_t np, const orc_atom
                                 const orc_params *p, double *abs_sum) {
     double energy = 0.0, asum = 0.0;
     const double K = p->k_coulomb, clampd = p->clamp_distance, cutoff = p->cutoff;
+    const int lj = p->lj_scale != 0.0 && p->prot_lj && p->lig_lj;
     for (int64_t i = 0; i < np; ++i) {
         for (int64_t j = 0; j < nl; ++j) {
             double ddx = prot[i].x - lig[j].x;
@@ -287,6 +291,14 @@ double orc_calculate_energy_abs(const orc_atom *prot, int64_t np, const orc_atom
             if (distance < clampd) distance = clampd;                             /* :255-257 */
             double term = K * (prot[i].q * lig[j].q) / distance;                  /* :258 */
             if (cutoff > 0) term -= K * (prot[i].q * lig[j].q) / cutoff;          /* shifted: continuous at the cutoff */
+            if (lj) {                                                             /* EXTENSION: Lennard-Jones 12-6 */
+                const double sg = 0.5 * (p->prot_lj[2 * i] + p->lig_lj[2 * j]);
+                const double d2 = ORC_SQ(ddx) + ORC_SQ(ddy) + ORC_SQ(ddz);
+                double x = d2 > 0 ? sg * sg / d2 : p->lj_cap;
+                if (!(x < p->lj_cap)) x = p->lj_cap;
+                const double x3 = x * x * x;
+                term += p->lj_scale * 4.0 * (sqrt(p->prot_lj[2 * i + 1]) * sqrt(p->lig_lj[2 * j + 1])) * (x3 * x3 - x3);
+            }
             energy += term;
             asum += fabs(term);
         }
@@ -297,7 +309,7 @@ double orc_calculate_energy_abs(const orc_atom *prot, int64_t np, const orc_atom
 
 double orc_calculate_energy(const orc_atom *prot, int64_t np, const orc_atom *lig, int64_t nl,
                             const orc_params *p) {
-    if (p->cutoff > 0) return orc_calculate_energy_abs(prot, np, lig, nl, p, NULL);   /* EXTENSION: shifted-Coulomb cutoff */
+    if (p->cutoff > 0 || p->lj_scale != 0.0) return orc_calculate_energy_abs(prot, np, lig, nl, p, NULL);   /* EXTENSIONS */
     double energy = 0.0;
     const double K = p->k_coulomb, clampd = p->clamp_distance;
     for (int64_t i = 0; i < np; ++i) {

@@ -52,6 +52,12 @@ typedef struct {
     double cutoff;           /* EXTENSION (no reference row, parity unpinned): > 0 = shifted-Coulomb cutoff in A:
                                 pairs with d < cutoff add K q q (1/max(d,clamp) - 1/cutoff), the others nothing.
                                 0 (default) = the reference's sum over every pair */
+    /* EXTENSION (no reference row, parity unpinned): Lennard-Jones 12-6 on top of the Coulomb term, off when lj_scale == 0.
+       Every pair that enters the Coulomb sum also adds lj_scale * 4 sqrt(eps_p eps_l) (x^6 - x^3) with
+       x = min(((sigma_p + sigma_l) / 2)^2 / d^2, lj_cap) (Lorentz-Berthelot mixing; the cap keeps the core finite).
+       prot_lj / lig_lj: (sigma, epsilon) per atom, interleaved; lig_lj belongs to the ligand passed with these params. */
+    double lj_scale, lj_cap;
+    const double *prot_lj, *lig_lj;
 } orc_params;
 
 void orc_params_default(orc_params *p);

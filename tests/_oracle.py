@@ -23,6 +23,7 @@ class OrcParams(C.Structure):
         ("max_angle", C.c_double), ("jitter_width", C.c_double), ("clamp_distance", C.c_double),
         ("move_mode", C.c_int), ("rigid_translation", C.c_double), ("rigid_angle", C.c_double),
         ("max_retries", C.c_int64), ("cutoff", C.c_double),
+        ("lj_scale", C.c_double), ("lj_cap", C.c_double), ("prot_lj", C.c_void_p), ("lig_lj", C.c_void_p),
     ]
 
 
@@ -104,9 +105,13 @@ class Oracle:
             fn.restype, fn.argtypes = res, args
 
     # ---- params / streams
-    def params(self, **kw) -> OrcParams:
+    def params(self, prot_lj=None, lig_lj=None, **kw) -> OrcParams:
+        """prot_lj / lig_lj: (n, 2) arrays of (sigma, epsilon) for the LJ extension; kept alive on the returned struct"""
         p = OrcParams()
         self.L.orc_params_default(C.byref(p))
+        if prot_lj is not None:
+            p._keep = (np.ascontiguousarray(prot_lj, dtype=np.float64), np.ascontiguousarray(lig_lj, dtype=np.float64))
+            p.prot_lj, p.lig_lj = p._keep[0].ctypes.data, p._keep[1].ctypes.data
         for k, v in kw.items():
             if not hasattr(p, k):
                 raise AttributeError(k)

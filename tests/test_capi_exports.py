@@ -32,13 +32,13 @@ def test_library_contains_sm100a_code_only(capi):
 
 
 def test_struct_layouts(capi):
-    assert ctypes.sizeof(capi.Params) == 88
+    assert ctypes.sizeof(capi.Params) == 104
     assert ctypes.sizeof(capi.ChainStats) == 72 == capi.STATS_DTYPE.itemsize
     p = capi.default_params()
     assert (p.k_coulomb, p.threshold, p.min_distance, p.max_angle, p.jitter_width, p.clamp_distance) == \
         (9e9, 5.0, 0.5, 0.79, 0.1, 1e-6)                  # datatypes.go:6-12, metropolis.go:158,255
     assert p.precision == capi.PRECISION_F32 and p.move_mode == capi.MOVE_REFERENCE and p.max_retries == 1024
-    assert p.cutoff == 0.0                                # extensions are off by default: the reference sums every pair
+    assert p.cutoff == 0.0 and p.lj_scale == 0.0          # extensions are off by default: every pair, Coulomb only
 
 
 def test_no_device_means_loud_failure_not_fallback(capi):
