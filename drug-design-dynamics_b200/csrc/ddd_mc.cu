@@ -10,6 +10,8 @@
 #include "../../include/ddd_mc.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -54,11 +56,33 @@ int fail(int code, const char *fmt, ...) {
 #define REQUIRE_INIT()                                                                         \
     do { if (g_devs.empty()) return fail(DDD_ENODEVICE, "no CUDA device in use: call ddd_init() first (there is no CPU fallback)"); } while (0)
 
+// Long-lived allocations (the receptor): plain cudaMalloc / cudaFree.
 template <typename T>
-int dev_alloc(T **p, size_t count) {
+int dev_alloc_sync(T **p, size_t count) {
     *p = nullptr;
     CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(count, 1) * sizeof(T)));
     return DDD_OK;
+}
+
+// Per-call buffers come from the device's stream-ordered memory pool on the library's own stream: cudaMalloc / cudaFree
+// per call stalled ddd_minimize_batch by up to 300 ms on a busy host (measured), the pool keeps its memory
+// (release threshold = max, ddd_init) and costs microseconds.  Every use of such a buffer is on the same stream.
+cudaStream_t current_stream() {
+    int id = 0;
+    cudaGetDevice(&id);
+    for (auto &d : g_devs) if (d.id == id) return d.stream;
+    return nullptr;
+}
+
+template <typename T>
+int dev_alloc(T **p, size_t count) {
+    *p = nullptr;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(p), std::max<size_t>(count, 1) * sizeof(T), current_stream()));
+    return DDD_OK;
+}
+
+void dev_free(void *p) {
+    if (p) cudaFreeAsync(p, current_stream());
 }
 
 DevParams make_dev_params(const ddd_params &p, int rotate, double temperature) {
@@ -225,8 +249,8 @@ void plan_shards(const int64_t *offsets, int64_t n_lig, int replicas, int n_shar
 
 void free_screen_dev(ScreenDev &sd) {
     cudaSetDevice(g_devs[sd.di].id);
-    cudaFree(sd.d_offsets); cudaFree(sd.d_lig); cudaFree(sd.d_order); cudaFree(sd.d_out);
-    cudaFree(sd.d_stats); cudaFree(sd.d_trace); cudaFree(sd.d_rec); cudaFree(sd.d_rec_off); cudaFree(sd.d_queue); cudaFree(sd.d_rmsd); cudaFree(sd.d_units); cudaFree(sd.d_lig_lj);
+    dev_free(sd.d_offsets); dev_free(sd.d_lig); dev_free(sd.d_order); dev_free(sd.d_out);
+    dev_free(sd.d_stats); dev_free(sd.d_trace); dev_free(sd.d_rec); dev_free(sd.d_rec_off); dev_free(sd.d_queue); dev_free(sd.d_rmsd); dev_free(sd.d_units); dev_free(sd.d_lig_lj);
     sd = ScreenDev();
 }
 
@@ -291,7 +315,8 @@ int screen_create_impl(const ddd_receptor *r, const int64_t *offsets, const doub
             });
             guard(dev_alloc(&d.d_order, order.size()));
             if (!rc) {
-                ce = cudaMemcpy(d.d_order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice);
+                ce = cudaMemcpyAsync(d.d_order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, g_devs[di].stream);
+                if (ce == cudaSuccess) ce = cudaStreamSynchronize(g_devs[di].stream);      // `order` goes out of scope
                 if (ce != cudaSuccess) guard(fail(DDD_ECUDA, "H2D copy of chain order: %s", cudaGetErrorString(ce)));
             }
         }
@@ -323,9 +348,9 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
         const Dev &dev = g_devs[d.di];
         CUDA_TRY(cudaSetDevice(dev.id));
         const int64_t n_local = d.c1 - d.c0;
-        cudaFree(d.d_trace); d.d_trace = nullptr;
-        cudaFree(d.d_rec); d.d_rec = nullptr;
-        cudaFree(d.d_rec_off); d.d_rec_off = nullptr;
+        dev_free(d.d_trace); d.d_trace = nullptr;
+        dev_free(d.d_rec); d.d_rec = nullptr;
+        dev_free(d.d_rec_off); d.d_rec_off = nullptr;
         if (want_trace) {
             if (int rc = dev_alloc(&d.d_trace, (size_t)(n_local * steps))) return rc;
             CUDA_TRY(cudaMemsetAsync(d.d_trace, 0, std::max<size_t>(1, (size_t)(n_local * steps)), dev.stream));
@@ -506,6 +531,10 @@ int ddd_init(const int *devices, int n_devices) {
         d.max_smem = prop.sharedMemPerBlockOptin;
         CUDA_TRY(cudaSetDevice(id));
         CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+        cudaMemPool_t pool = nullptr;
+        CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, id));
+        unsigned long long keep = ~0ull;                                  // never hand pool memory back between calls
+        CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         CUDA_TRY(cudaEventCreate(&d.ev0));
         CUDA_TRY(cudaEventCreate(&d.ev1));
         g_devs.push_back(d);
@@ -652,15 +681,15 @@ int ddd_receptor_create(const double *xyzq, int64_t n_atoms, ddd_receptor **out)
     int rc = DDD_OK;
     for (size_t di = 0; di < g_devs.size() && !rc; ++di) {
         cudaError_t ce = cudaSetDevice(g_devs[di].id);
-        if (ce == cudaSuccess) { rc = dev_alloc(&r->f32[di], (size_t)r->n_pad); if (rc) break; rc = dev_alloc(&r->f64[di], (size_t)n_atoms); if (rc) break; }
+        if (ce == cudaSuccess) { rc = dev_alloc_sync(&r->f32[di], (size_t)r->n_pad); if (rc) break; rc = dev_alloc_sync(&r->f64[di], (size_t)n_atoms); if (rc) break; }
         if (ce == cudaSuccess && r->n_pad > 0) ce = cudaMemcpy(r->f32[di], h32.data(), sizeof(float4) * (size_t)r->n_pad, cudaMemcpyHostToDevice);
         if (ce == cudaSuccess && n_atoms > 0) ce = cudaMemcpy(r->f64[di], xyzq, sizeof(Atom64) * (size_t)n_atoms, cudaMemcpyHostToDevice);
-        if (ce == cudaSuccess) { rc = dev_alloc(&r->f32s[di], h32s.size()); if (rc) break; rc = dev_alloc(&r->ubox[di], hbox.size()); if (rc) break; }
+        if (ce == cudaSuccess) { rc = dev_alloc_sync(&r->f32s[di], h32s.size()); if (rc) break; rc = dev_alloc_sync(&r->ubox[di], hbox.size()); if (rc) break; }
         if (ce == cudaSuccess) ce = cudaMemcpy(r->f32s[di], h32s.data(), sizeof(float4) * h32s.size(), cudaMemcpyHostToDevice);
         if (ce == cudaSuccess) ce = cudaMemcpy(r->ubox[di], hbox.data(), sizeof(float4) * hbox.size(), cudaMemcpyHostToDevice);
-        if (ce == cudaSuccess) { rc = dev_alloc(&r->gbox[di], hgbox.size()); if (rc) break; }
+        if (ce == cudaSuccess) { rc = dev_alloc_sync(&r->gbox[di], hgbox.size()); if (rc) break; }
         if (ce == cudaSuccess) ce = cudaMemcpy(r->gbox[di], hgbox.data(), sizeof(float4) * hgbox.size(), cudaMemcpyHostToDevice);
-        if (ce == cudaSuccess) { rc = dev_alloc(&r->f64s[di], h64s.size()); if (rc) break; }
+        if (ce == cudaSuccess) { rc = dev_alloc_sync(&r->f64s[di], h64s.size()); if (rc) break; }
         if (ce == cudaSuccess) ce = cudaMemcpy(r->f64s[di], h64s.data(), sizeof(Atom64) * h64s.size(), cudaMemcpyHostToDevice);
         if (ce != cudaSuccess) rc = fail(DDD_ECUDA, "receptor upload on device %d: %s", g_devs[di].id, cudaGetErrorString(ce));
     }
@@ -705,9 +734,9 @@ int ddd_receptor_set_lj(ddd_receptor *r, const double *sigma, const double *epsi
     for (size_t di = 0; di < g_devs.size(); ++di) {
         CUDA_TRY(cudaSetDevice(g_devs[di].id));
         if (!r->lj64[di]) {
-            if (int rc = dev_alloc(&r->lj64[di], a.size())) return rc;
-            if (int rc = dev_alloc(&r->lj64s[di], as.size())) return rc;
-            if (int rc = dev_alloc(&r->lj32s[di], fs.size())) return rc;
+            if (int rc = dev_alloc_sync(&r->lj64[di], a.size())) return rc;
+            if (int rc = dev_alloc_sync(&r->lj64s[di], as.size())) return rc;
+            if (int rc = dev_alloc_sync(&r->lj32s[di], fs.size())) return rc;
         }
         CUDA_TRY(cudaMemcpy(r->lj64[di], a.data(), sizeof(double2) * a.size(), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(r->lj64s[di], as.data(), sizeof(double2) * as.size(), cudaMemcpyHostToDevice));
@@ -733,7 +762,7 @@ int ddd_energy_batch(const ddd_receptor *r, const int64_t *offsets, const double
     CUDA_TRY(cudaSetDevice(dev.id));
     long long *d_off = nullptr; double *d_lig = nullptr, *d_e = nullptr, *d_abs = nullptr;
     int rc = DDD_OK;
-    auto cleanup = [&]() { cudaFree(d_off); cudaFree(d_lig); cudaFree(d_e); cudaFree(d_abs); };
+    auto cleanup = [&]() { dev_free(d_off); dev_free(d_lig); dev_free(d_e); dev_free(d_abs); };
     if ((rc = dev_alloc(&d_off, (size_t)n_lig + 1)) || (rc = dev_alloc(&d_lig, (size_t)offsets[n_lig] * 4)) ||
         (rc = dev_alloc(&d_e, (size_t)n_lig)) || (out_abs_sum && (rc = dev_alloc(&d_abs, (size_t)n_lig)))) { cleanup(); return rc; }
     auto run = [&]() -> int {
@@ -803,10 +832,20 @@ int ddd_minimize_batch(const ddd_receptor *r, const int64_t *offsets, const doub
     // ligand list split over several calls (or ranks) sees the same streams as one call
     ddd_screen *s = nullptr;
     if (int rc = check_params(p)) return rc;
+    const bool dbg = std::getenv("DDD_DEBUG_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     if (int rc = screen_create_impl(r, offsets, lig_xyzq, n_lig, num_procs, first_ligand_index * (uint64_t)num_procs, &s)) return rc;
+    const double t1 = now();
     int rc = screen_run_impl(s, width, rotate, temperature, p, seed, nullptr, nullptr, false);
+    const double t2 = now();
     if (!rc) rc = screen_download_impl(s, chain_pose.data(), stats.data(), nullptr);
+    const double t3 = now();
+    const double kms = ddd_screen_last_kernel_ms(s);
     screen_destroy_impl(s);
+    const double t4 = now();
+    if (dbg) fprintf(stderr, "[ddd_minimize_batch] create %.2f ms, launch %.2f ms, sync+download %.2f ms (kernel %.2f ms), destroy %.2f ms\n",
+                     t1 - t0, t2 - t1, t3 - t2, kms, t4 - t3);
     if (rc) return rc;
     for (int64_t i = 0; i < n_lig; ++i) {
         const int64_t nl = offsets[i + 1] - offsets[i];
@@ -845,7 +884,7 @@ int ddd_rmsd_batch(const int64_t *offsets, const double *sim, const double *ref,
     const Dev &dev = g_devs[0];
     CUDA_TRY(cudaSetDevice(dev.id));
     long long *d_off = nullptr; double *d_s = nullptr, *d_r = nullptr, *d_o = nullptr;
-    auto cleanup = [&]() { cudaFree(d_off); cudaFree(d_s); cudaFree(d_r); cudaFree(d_o); };
+    auto cleanup = [&]() { dev_free(d_off); dev_free(d_s); dev_free(d_r); dev_free(d_o); };
     int rc;
     if ((rc = dev_alloc(&d_off, (size_t)n_pairs + 1)) || (rc = dev_alloc(&d_s, (size_t)n_atoms * atom_stride)) ||
         (rc = dev_alloc(&d_r, (size_t)n_atoms * atom_stride)) || (rc = dev_alloc(&d_o, (size_t)n_pairs))) { cleanup(); return rc; }
@@ -878,7 +917,7 @@ static int closest_impl(const ddd_receptor *r, const int64_t *offsets, double *l
     CUDA_TRY(cudaSetDevice(dev.id));
     const int64_t n_atoms = offsets[n_lig];
     long long *d_off = nullptr, *d_li = nullptr, *d_pj = nullptr; double *d_lig = nullptr, *d_d = nullptr;
-    auto cleanup = [&]() { cudaFree(d_off); cudaFree(d_li); cudaFree(d_pj); cudaFree(d_lig); cudaFree(d_d); };
+    auto cleanup = [&]() { dev_free(d_off); dev_free(d_li); dev_free(d_pj); dev_free(d_lig); dev_free(d_d); };
     int rc;
     if ((rc = dev_alloc(&d_off, (size_t)n_lig + 1)) || (rc = dev_alloc(&d_lig, (size_t)n_atoms * 4)) ||
         (rc = dev_alloc(&d_d, (size_t)n_lig)) || (rc = dev_alloc(&d_li, (size_t)n_lig)) || (rc = dev_alloc(&d_pj, (size_t)n_lig))) { cleanup(); return rc; }
@@ -922,7 +961,7 @@ int ddd_randomize_pose_batch(const int64_t *offsets, double *lig_xyzq_inout, int
     CUDA_TRY(cudaSetDevice(dev.id));
     const int64_t n_atoms = offsets[n_lig];
     long long *d_off = nullptr; double *d_lig = nullptr;
-    auto cleanup = [&]() { cudaFree(d_off); cudaFree(d_lig); };
+    auto cleanup = [&]() { dev_free(d_off); dev_free(d_lig); };
     int rc;
     if ((rc = dev_alloc(&d_off, (size_t)n_lig + 1)) || (rc = dev_alloc(&d_lig, (size_t)n_atoms * 4))) { cleanup(); return rc; }
     auto run = [&]() -> int {
@@ -1045,7 +1084,8 @@ int ddd_screen_pair_units(ddd_screen *s, int64_t *out_receptor_atoms) {
         const int64_t n_local = d.c1 - d.c0;
         if (!d.d_units || !s->last_cut) { std::fill(out_receptor_atoms + d.c0, out_receptor_atoms + d.c1, (int64_t)0); continue; }
         CUDA_TRY(cudaSetDevice(g_devs[d.di].id));
-        CUDA_TRY(cudaMemcpy(out_receptor_atoms + d.c0, d.d_units, sizeof(int64_t) * (size_t)n_local, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpyAsync(out_receptor_atoms + d.c0, d.d_units, sizeof(int64_t) * (size_t)n_local, cudaMemcpyDeviceToHost, g_devs[d.di].stream));
+        CUDA_TRY(cudaStreamSynchronize(g_devs[d.di].stream));
         for (int64_t i = d.c0; i < d.c1; ++i) out_receptor_atoms[i] *= 32;
     }
     return DDD_OK;
@@ -1065,7 +1105,8 @@ int ddd_screen_set_lj(ddd_screen *s, const double *sigma, const double *epsilon)
         }
         CUDA_TRY(cudaSetDevice(g_devs[d.di].id));
         if (!d.d_lig_lj) { if (int rc = dev_alloc(&d.d_lig_lj, h.size())) return rc; }
-        CUDA_TRY(cudaMemcpy(d.d_lig_lj, h.data(), sizeof(double2) * h.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpyAsync(d.d_lig_lj, h.data(), sizeof(double2) * h.size(), cudaMemcpyHostToDevice, g_devs[d.di].stream));
+        CUDA_TRY(cudaStreamSynchronize(g_devs[d.di].stream));
     }
     s->has_lj = true;
     return DDD_OK;

@@ -75,8 +75,10 @@ struct __align__(16) SmSlotCtl {
     long long units_done;                             // cutoff extension: receptor units evaluated by the chain's fp32 sums
     long long pad3;
     float lbox[3][8];                                 // fp32 bounding box of pose buffer b: (min xyz, -, max xyz, -)
+    unsigned apart[3][2];                             // bit g: receptor group g's box is apart from pose buffer b's box (clamp-free)
+    unsigned pad4, pad5;
 };
-static_assert(sizeof(SmSlotCtl) == 320, "SmSlotCtl is laid out as twenty 16-byte words");
+static_assert(sizeof(SmSlotCtl) == 352, "SmSlotCtl is laid out as twenty-two 16-byte words");
 constexpr int kSlotFixedBytes = (int)sizeof(SmSlotCtl) + kSmMaxItems * 8 + kUbufDraws * 8 + 2 * kNearCap * 4;
 constexpr int kAtomRecBytes = 88;                     // fp64 record per atom: 3 poses x (x,y,z), q, pad
 constexpr int kAtomBytes = kAtomRecBytes + 3 * 16;    // + three pair-packed fp32 poses
@@ -157,12 +159,12 @@ __device__ __forceinline__ void cta_fence() { asm volatile("fence.acq_rel.cta;" 
 __device__ __forceinline__ int ld_volatile(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 __device__ __forceinline__ void st_volatile(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
 
-// ------------------------------------------------------------------ energy work items
 __device__ __forceinline__ bool boxes_apart(const float4 gmin, const float4 gmax, const float *lbox) {
     return gmin.x - lbox[4] > 1e-3f || lbox[0] - gmax.x > 1e-3f || gmin.y - lbox[5] > 1e-3f ||
            lbox[1] - gmax.y > 1e-3f || gmin.z - lbox[6] > 1e-3f || lbox[2] - gmax.z > 1e-3f;
 }
 
+// ------------------------------------------------------------------ energy work items
 // Receptors up to 8 192 atoms: the fp32 sum is kept PER GROUP (4 units = 128 atoms, 4 per lane) AND PER LANE in shared
 // memory -- gsum[g][lane] = the lane's fp32 sum over its 4 atoms x nL ligand atoms -- and added in (group, lane) order by
 // the serial phase.  No reduction on the item path, and the result does not depend on how the groups were cut into
@@ -170,7 +172,7 @@ __device__ __forceinline__ bool boxes_apart(const float4 gmin, const float4 gmax
 // groups when one chain has it to itself.  Two adjacent groups go through the loop together (8 atoms per lane share every
 // ligand load) but keep separate sums.  The clamp d >= 1e-6 (:255-257) can only matter where a group's box touches the
 // pose's box; everywhere else min(1/d, 1e6) == 1/d exactly and the loop without the two FMNMX gives the same bits.
-__device__ __forceinline__ void sm_item_f32_groups(const SmArgs &A, const float4 *lf, const float4 *ljf, const float *lbox, float *gsum, int nl, int g, int g1) {
+__device__ __forceinline__ void sm_item_f32_groups(const SmArgs &A, const float4 *lf, const float4 *ljf, const unsigned *apart_mask, float *gsum, int nl, int g, int g1) {
     const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
     const ulonglong2 *ljp = reinterpret_cast<const ulonglong2 *>(ljf);
     const int n_pairs = (nl + 1) >> 1;
@@ -184,9 +186,9 @@ __device__ __forceinline__ void sm_item_f32_groups(const SmArgs &A, const float4
         }
         return;
     }
+    const unsigned long long am = (unsigned long long)apart_mask[0] | (unsigned long long)apart_mask[1] << 32;   // computed with the pose
     for (; g + 2 <= g1; g += 2) {
-        const bool apart = boxes_apart(__ldg(A.c.rec.gbox + 2 * g), __ldg(A.c.rec.gbox + 2 * g + 1), lbox) &&
-                           boxes_apart(__ldg(A.c.rec.gbox + 2 * g + 2), __ldg(A.c.rec.gbox + 2 * g + 3), lbox);
+        const bool apart = ((am >> g) & 3ull) == 3ull;
         int ub[8];
 #pragma unroll
         for (int a = 0; a < 8; ++a) ub[a] = (4 * g + a) * 32;
@@ -197,7 +199,7 @@ __device__ __forceinline__ void sm_item_f32_groups(const SmArgs &A, const float4
         gsum[(g + 1) * 32 + lane] = hi;
     }
     if (g < g1) {
-        const bool apart = boxes_apart(__ldg(A.c.rec.gbox + 2 * g), __ldg(A.c.rec.gbox + 2 * g + 1), lbox);
+        const bool apart = (am >> g) & 1ull;
         int ub[4] = {4 * g * 32, 4 * g * 32 + 32, 4 * g * 32 + 64, 4 * g * 32 + 96};
         float t;
         if (apart) t = warp_units_sum_f32<4, false, false>(rec, ub, lf2, n_pairs, rmax, 0.f);
@@ -427,6 +429,16 @@ __device__ __forceinline__ void warp_write_lf(const SmArgs &A, const SlotView &s
             hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
         }
     if (lane < 3) { c->lbox[buf][lane] = lo[lane]; c->lbox[buf][4 + lane] = hi[lane]; }
+    if (A.gsum_bytes) {                                 // which 128-atom groups can skip the clamp for this pose (<= 64 groups)
+        const float lb[8] = {lo[0], lo[1], lo[2], 0.f, hi[0], hi[1], hi[2], 0.f};
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const int g = 32 * w + lane;
+            const bool ap = g < A.n_groups4 && boxes_apart(__ldg(A.c.rec.gbox + 2 * g), __ldg(A.c.rec.gbox + 2 * g + 1), lb);
+            const unsigned m = __ballot_sync(0xffffffffu, ap);
+            if (lane == 0) c->apart[buf][w] = m;
+        }
+    }
     __syncwarp();
 }
 
@@ -964,7 +976,7 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
             const int nl = c->nl, buf = c->i_trial;
             if (c->mode == 0 && A.gsum_bytes && !A.cut) {
                 const int gpi = c->upi_e >> 2;
-                sm_item_f32_groups(A, s.lf(buf), s.ljf(A.unit_list_bytes + A.gsum_bytes), c->lbox[buf], s.gsum(A.unit_list_bytes), nl,
+                sm_item_f32_groups(A, s.lf(buf), s.ljf(A.unit_list_bytes + A.gsum_bytes), c->apart[buf], s.gsum(A.unit_list_bytes), nl,
                                    e_it * gpi, min((e_it + 1) * gpi, A.n_groups4));
             } else {
                 const double sum = c->mode ? sm_item_f64(A, s, c, buf, nl, e_it)
