@@ -202,7 +202,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU restatement)")
     torch.cuda.set_device(local_rank)
-    os.environ["NCCL_DEBUG"] = os.environ.get("DDD_NCCL_DEBUG", "WARN")      # NCCL's version banner goes to stdout: keep the one JSON line clean
+    # NCCL's version banner goes to stdout at any NCCL_DEBUG level: keep stdout to the one JSON line
+    if "DDD_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["DDD_NCCL_DEBUG"]
+    else:
+        os.environ.pop("NCCL_DEBUG", None)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     capi.init([local_rank])
