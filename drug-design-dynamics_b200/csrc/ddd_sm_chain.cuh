@@ -408,6 +408,17 @@ __device__ __noinline__ bool warp_collision_exact(const SlotView &s, int buf, in
 }
 
 // fp32 pose of every atom from the fp64 master copy (the pair-packed layout the pair loop and the list scan read)
+// the same without the bounding box: enough for the near-pair scan of a pose that has just failed its collision test
+__device__ __forceinline__ void warp_write_lf_only(const SmArgs &A, const SlotView &s, int buf, int nl) {
+    float4 *lf = s.lf(buf);
+    for (int i = threadIdx.x & 31; i < nl; i += 32) {
+        const double *a = s.xyz(buf, i);
+        store_lig_f32(lf, i, (float)(a[0] - A.c.rec.cx), (float)(a[1] - A.c.rec.cy), (float)(a[2] - A.c.rec.cz), (float)s.q(i));
+    }
+    if ((nl & 1) && (threadIdx.x & 31) == 0) store_lig_f32(lf, nl, -kPadCoord, -kPadCoord, -kPadCoord, 0.f);   // q = 0 pad atom
+    __syncwarp();
+}
+
 __device__ __forceinline__ void warp_write_lf(const SmArgs &A, const SlotView &s, SmSlotCtl *c, int buf, int nl) {
     float4 *lf = s.lf(buf);
     const int lane = threadIdx.x & 31;
@@ -667,12 +678,11 @@ __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotVie
         }
         from = dst;                                                       // retries are cumulative
         __syncwarp();
-        bool collided, lf_fresh = false;
+        bool collided;
         if (lists_ok && base_n <= kNearCap && k <= k_max) collided = warp_check_near_list(s, dst, s.base_list(), base_n, P.min_distance);
         else if (lists_ok && dyn_n >= 0 && k - dyn_kb <= k_max) collided = warp_check_near_list(s, dst, s.dyn_list(), dyn_n, P.min_distance);
         else {
-            warp_write_lf(A, s, c, dst, nl);
-            lf_fresh = true;
+            warp_write_lf_only(A, s, dst, nl);
             const int n = warp_build_near_list(s.lf(dst), c, s.dyn_list(), nl, r2_near);
             if (n <= kNearCap) { dyn_n = n; dyn_kb = k; collided = warp_check_near_list(s, dst, s.dyn_list(), n, P.min_distance); }
             else {                                                        // list overflow: screen every pair
@@ -683,7 +693,7 @@ __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotVie
                     collided = __any_sync(0xffffffffu, warp_collision_exact(s, dst, nl, P.min_distance)) != 0;
             }
         }
-        if (!collided) { if (!lf_fresh) warp_write_lf(A, s, c, dst, nl); break; }
+        if (!collided) { warp_write_lf(A, s, c, dst, nl); break; }     // fp32 pose + bounding box of the pose that will be evaluated
         ++R.rej;
         if (R.rej >= P.max_retries) { bail = true; break; }                // the reference would spin forever here
     }
