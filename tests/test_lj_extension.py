@@ -98,3 +98,30 @@ def test_lj_energies_and_chains_match_the_restatement(gpu, orc, ddd):
             gpu.energy_batch(rec, off, lig, gpu.default_params(lj_scale=SCALE))
         with pytest.raises(gpu.DddError):
             gpu.run_chains(rec, off, lig, 1, 5, True, T, gpu.default_params(lj_scale=SCALE))
+
+
+@pytest.mark.gpu
+def test_mode_combinations_are_reproducible_and_engine_independent(gpu, ddd):
+    # every extension x precision x slot count on a mixed batch with more chains than slots: same seed -> same bits,
+    # and the number of resident chains per SM never changes a result
+    prot = ddd.synth.make_receptor(2300, seed=3)
+    sizes = [3 + (7 * i) % 38 for i in range(40)]
+    off, lig = ddd.synth.make_ligands(sizes, prot)
+    plj, llj = _lj_params(len(prot), 5), _lj_params(len(lig), 6)
+    with gpu.Receptor(prot) as rec:
+        rec.set_lj(plj[:, 0], plj[:, 1])
+        for kw in ({}, {"precision": gpu.PRECISION_F64}, {"cutoff": 9.0}, {"lj_scale": SCALE},
+                   {"cutoff": 9.0, "lj_scale": SCALE, "precision": gpu.PRECISION_F64}):
+            ref = None
+            for slots in (0, 1, 3, 0):
+                scr = gpu.Screen(rec, off, lig, 6)
+                scr.set_lj(llj[:, 0], llj[:, 1])
+                scr.set_chain_slots(slots)
+                scr.run(15, True, T, gpu.default_params(**kw), seed=1)
+                p, st = scr.download()
+                scr.close()
+                assert np.all(st["status"] == 0) and np.all(st["steps"] == 15)
+                if ref is None:
+                    ref = (p, st)
+                else:
+                    assert np.array_equal(ref[0], p) and np.array_equal(ref[1], st), (kw, slots)
