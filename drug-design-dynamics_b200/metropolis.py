@@ -360,6 +360,46 @@ def ParseMol2(filename) -> Molecule:
     return Molecule(xyzq=np.array(rows, dtype=np.float64).reshape(-1, 4))
 
 
+def ParseMol2Types(filename) -> list:
+    """EXTENSION (LJ): the SYBYL atom-type column (field 5) that parsing.go:84-96 reads past.  Same line filter as ParseMol2,
+    so ParseMol2Types(f)[i] is the type of ParseMol2(f).atoms[i]."""
+    types = []
+    in_atoms = False
+    with open(filename, "r") as fh:
+        for line in fh:
+            line = line.rstrip("\r\n")
+            if line.startswith("@<TRIPOS>ATOM"):
+                in_atoms = True
+                continue
+            if in_atoms and line.startswith("@<TRIPOS>"):
+                break
+            if not in_atoms:
+                continue
+            fields = line.split()
+            if len(fields) < 9:
+                continue
+            types.append(fields[5])
+    return types
+
+
+# EXTENSION (LJ): 12-6 parameters per SYBYL element (sigma in A, epsilon in kcal/mol; OPLS-AA-like united values).  The
+# reference has no such table -- it has no Lennard-Jones term (SURVEY F2); this only makes ddd_receptor_set_lj /
+# ddd_screen_set_lj usable from mol2 files.  Keyed by the element part of the type ("C.ar" -> "C").
+LJ_BY_ELEMENT = {
+    "C": (3.50, 0.066), "N": (3.25, 0.170), "O": (3.00, 0.170), "S": (3.55, 0.250), "P": (3.74, 0.200), "H": (2.50, 0.030),
+    "F": (2.95, 0.053), "Cl": (3.40, 0.300), "Br": (3.47, 0.470), "I": (3.80, 0.600), "Mg": (1.64, 0.875),
+    "Zn": (1.96, 0.250), "Ca": (2.41, 0.450), "Na": (3.33, 0.003), "K": (4.93, 0.0003), "Fe": (2.59, 0.013),
+}
+LJ_DEFAULT = (3.40, 0.100)
+
+
+def lj_parameters(types):
+    """(sigma[n], epsilon[n]) float64 for a list of SYBYL atom types; unknown elements get LJ_DEFAULT."""
+    out = np.array([LJ_BY_ELEMENT.get(t.split(".")[0].capitalize() if len(t.split(".")[0]) > 1 else t.split(".")[0].upper(), LJ_DEFAULT)
+                    for t in types], dtype=np.float64).reshape(-1, 2)
+    return np.ascontiguousarray(out[:, 0]), np.ascontiguousarray(out[:, 1])
+
+
 def findFilesWithSubstring(rootDir, searchString):
     """parsing.go:142-160: filepath.Walk order (lexical), files whose NAME contains the substring."""
     out = []

@@ -36,7 +36,12 @@ def main():
     for f in sorted(MOL2.glob("*.mol2")):
         arrays[f.stem] = orc.parse_mol2(f)
     arrays["1a4h_protein"] = orc.parse_mol2(REF / "Rshiny" / "MCdata" / "1a4h_protein.mol2")
-    np.savez_compressed(HERE / "sample_mol2.npz", **arrays)
+    # SYBYL atom types of the same atoms (LJ extension; the reference's parser reads past this column)
+    M = ddd_loader.load().metropolis
+    types = {f.stem + "_types": np.array(M.ParseMol2Types(f)) for f in sorted(MOL2.glob("*.mol2"))}
+    for k, v in types.items():
+        assert len(v) == len(arrays[k[:-6]])
+    np.savez_compressed(HERE / "sample_mol2.npz", **arrays, **types)
 
     g = {"note": "float64 outputs of oracle/ddd_oracle.c (C restatement, NOT Go); see make_golden.py"}
     ligs = ["1a0i", "223l", "227l", "421p", "6tol", "721p", "7loc", "821p"]
