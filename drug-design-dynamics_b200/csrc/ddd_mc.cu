@@ -380,7 +380,7 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
             return fail(DDD_EINVAL, "params.lj_scale != 0 needs ddd_receptor_set_lj and ddd_screen_set_lj");
         if (lj && s->threads_override > 0) return fail(DDD_EINVAL, "params.lj_scale needs the SM-persistent engine");
         const int n_groups4 = (int)((s->rec->n_units_s + 3) / 4);
-        const int gsum_bytes = (!cut && n_groups4 <= kMaxLaneSumGroups && s->rec->n_units_s >= 4 * kSmWarps) ? n_groups4 * 128 : 0;
+        const int gsum_bytes = (!cut && n_groups4 >= 1 && n_groups4 <= kMaxLaneSumGroups) ? n_groups4 * 128 : 0;
         const int lj_bytes = lj ? d.nl_cap * 24 : 0;                          // per ligand atom: (sigma/2, sqrt eps) fp64 + packed fp32
         const int ulb = (cut ? 3 * kUnitCap * (int)sizeof(unsigned short) : 0) + gsum_bytes + lj_bytes;
         const bool fits_sm_engine = sm_smem_bytes(d.nl_cap, 1, ulb) <= dev.max_smem;      // very large ligands: one CTA per chain

@@ -49,7 +49,14 @@ def gpu(ddd):
 def sample():
     """Shipped sample data (223l/227l proteins + 8 ligands) as xyzq arrays; see golden/make_golden.py."""
     z = np.load(GOLDEN / "sample_mol2.npz")
-    return {k: z[k] for k in z.files}
+    return {k: z[k] for k in z.files if not k.endswith("_types")}
+
+
+@pytest.fixture(scope="session")
+def sample_types():
+    """SYBYL atom types of the same atoms (LJ extension), keyed like `sample`."""
+    z = np.load(GOLDEN / "sample_mol2.npz")
+    return {k[:-6]: z[k] for k in z.files if k.endswith("_types")}
 
 
 @pytest.fixture(scope="session")

@@ -188,6 +188,26 @@ def test_empty_receptor_and_oversized_ligand(gpu, orc, ddd):
     assert np.allclose(poses, pose_o, rtol=0, atol=1e-8)
 
 
+def test_receptor_sizes_cover_both_sum_layouts(gpu, ddd):
+    # <= 8192 receptor atoms: per-group per-lane sums; above: one fp64 sum per static item.  Either way the chain's own
+    # fp32-summed energy must agree with the fp64 energy of the same pose, and the run must be bit-reproducible.
+    for n_rec in (130, 1288, 9000):
+        prot = ddd.synth.make_receptor(n_rec, seed=8)
+        off, lig = ddd.synth.make_ligands([40, 17, 33, 8] * 6, prot)
+        with gpu.Receptor(prot) as rec:
+            scr = gpu.Screen(rec, off, lig, 1)
+            scr.run(60, True, T, gpu.default_params(), seed=5)
+            poses, stats = scr.download()
+            scr.run(60, True, T, gpu.default_params(), seed=5)
+            poses2, stats2 = scr.download()
+            scr.close()
+            e64, ab = gpu.energy_batch(rec, off, poses, gpu.default_params(precision=gpu.PRECISION_F64), with_abs=True)
+        assert np.array_equal(poses, poses2) and np.array_equal(stats, stats2), n_rec
+        assert np.all(stats["status"] == 0) and np.all(stats["final_energy"] <= stats["start_energy"])
+        assert np.all(np.abs(stats["final_energy"] - e64) <= 1e-13 * ab + 1e-300), n_rec
+        assert np.all(np.abs(stats["chain_energy"] - e64) <= 1e-6 * ab + 1e-300), n_rec
+
+
 def test_f32_chains_match_oracle_statistics(gpu, orc, ddd):
     # production precision: trajectories may differ after an fp32 near-tie, statistics must not
     prot = ddd.synth.make_receptor(1500, seed=2)

@@ -127,9 +127,9 @@ def test_mode_combinations_are_reproducible_and_engine_independent(gpu, ddd):
                     assert np.array_equal(ref[0], p) and np.array_equal(ref[1], st), (kw, slots)
 
 
-def test_lj_parameters_from_mol2_types(ddd, sample):
+def test_lj_parameters_from_mol2_types(ddd, sample, sample_types):
     M = ddd.metropolis
-    t = sample["223l_ligand_types"].tolist()
+    t = sample_types["223l_ligand"].tolist()
     assert t[:6] == ["Cl", "C.3", "C.3", "O.3", "S.3", "C.3"] and len(t) == len(sample["223l_ligand"])
     sg, ep = M.lj_parameters(t)
     assert (sg[0], ep[0]) == M.LJ_BY_ELEMENT["Cl"] and (sg[1], ep[1]) == M.LJ_BY_ELEMENT["C"] and (sg[4], ep[4]) == M.LJ_BY_ELEMENT["S"]
@@ -142,14 +142,14 @@ def test_lj_parameters_from_mol2_types(ddd, sample):
 
 
 @pytest.mark.gpu
-def test_lj_on_shipped_data_with_typed_parameters(gpu, orc, ddd, sample):
+def test_lj_on_shipped_data_with_typed_parameters(gpu, orc, ddd, sample, sample_types):
     # 223l protein x shipped ligands, sigma / epsilon from the mol2 atom types: fp64 energies and a chain vs the restatement
     M = ddd.metropolis
     prot = sample["223l_protein"]
-    psg, pep = M.lj_parameters(sample["223l_protein_types"].tolist())
+    psg, pep = M.lj_parameters(sample_types["223l_protein"].tolist())
     names = ["1a0i", "223l", "421p", "6tol"]
     off, lig = gpu.pack_ligands([sample[n + "_ligand"] for n in names])
-    lsg, lep = M.lj_parameters(np.concatenate([sample[n + "_ligand_types"] for n in names]).tolist())
+    lsg, lep = M.lj_parameters(np.concatenate([sample_types[n + "_ligand"] for n in names]).tolist())
     scale = 1.0e6
     with gpu.Receptor(prot) as rec:
         rec.set_lj(psg, pep)
