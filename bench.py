@@ -337,7 +337,7 @@ def main():
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_s * 1e3 / args.steps, "higher_is_better": True,
-        "scaling": "weak" if args.config == 2 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak" if args.config in (2, 4) else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         **({"rmsd": {"pairs": rmsd_info["pairs"], "kernel_ms": rmsd_info["kernel_ms"], "algorithmic_bytes": rmsd_info["bytes"],
                      "achieved_gbs": rmsd_info["bytes"] / (rmsd_info["kernel_ms"] * 1e-3) / 1e9 / world, "peak_gbs": peaks.get("hbm_gbs"),
                      "frac": rmsd_info["bytes"] / (rmsd_info["kernel_ms"] * 1e-3) / 1e9 / world / peaks.get("hbm_gbs", 6540.8),

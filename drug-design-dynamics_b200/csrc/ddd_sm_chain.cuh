@@ -209,7 +209,7 @@ __device__ __forceinline__ void sm_item_f32_groups(const SmArgs &A, const float4
 }
 
 // larger receptors: static items (runs of A.upi units), one fp64 sum per item
-__device__ __forceinline__ double sm_item_f32(const SmArgs &A, const float4 *lf, const float4 *ljf, const float *lbox, int nl, int it) {
+__device__ __noinline__ double sm_item_f32(const SmArgs &A, const float4 *lf, const float4 *ljf, const float *lbox, int nl, int it) {
     const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
     const int n_pairs = (nl + 1) >> 1;
     int u = it * A.upi;
@@ -303,7 +303,7 @@ __device__ __forceinline__ double lj_term(const DevParams &P, const double2 pj, 
 }
 
 // the reference's per-term fp64 arithmetic (:253-258) for the receptor atoms of one item
-__device__ __forceinline__ double sm_item_f64(const SmArgs &A, const SlotView &s, const SmSlotCtl *c, int buf, int nl, int it) {
+__device__ __noinline__ double sm_item_f64(const SmArgs &A, const SlotView &s, const SmSlotCtl *c, int buf, int nl, int it) {
     const double K = A.c.prm.k_coulomb, clampd = A.c.prm.clamp_distance, cutoff = A.c.prm.cutoff;
     const bool lj = A.lj_bytes != 0;
     const double2 *ljl = s.lj64(A.unit_list_bytes + A.gsum_bytes);
