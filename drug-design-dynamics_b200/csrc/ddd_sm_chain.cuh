@@ -409,7 +409,7 @@ __device__ __noinline__ bool warp_collision_exact(const SlotView &s, int buf, in
 
 // fp32 pose of every atom from the fp64 master copy (the pair-packed layout the pair loop and the list scan read)
 // the same without the bounding box: enough for the near-pair scan of a pose that has just failed its collision test
-__device__ __forceinline__ void warp_write_lf_only(const SmArgs &A, const SlotView &s, int buf, int nl) {
+__device__ __noinline__ void warp_write_lf_only(const SmArgs &A, const SlotView &s, int buf, int nl) {
     float4 *lf = s.lf(buf);
     for (int i = threadIdx.x & 31; i < nl; i += 32) {
         const double *a = s.xyz(buf, i);
@@ -419,7 +419,7 @@ __device__ __forceinline__ void warp_write_lf_only(const SmArgs &A, const SlotVi
     __syncwarp();
 }
 
-__device__ __forceinline__ void warp_write_lf(const SmArgs &A, const SlotView &s, SmSlotCtl *c, int buf, int nl) {
+__device__ __noinline__ void warp_write_lf(const SmArgs &A, const SlotView &s, SmSlotCtl *c, int buf, int nl) {
     float4 *lf = s.lf(buf);
     const int lane = threadIdx.x & 31;
     float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
@@ -551,7 +551,7 @@ __device__ __noinline__ int warp_build_near_list(const float4 *lf, SmSlotCtl *c,
 }
 
 // IsCollisionFree (:229-242) restricted to the listed pairs, in the reference's fp64 arithmetic; true = some pair collides
-__device__ __forceinline__ bool warp_check_near_list(const SlotView &s, int buf, const ushort2 *list, int n, double min_distance) {
+__device__ __noinline__ bool warp_check_near_list(const SlotView &s, int buf, const ushort2 *list, int n, double min_distance) {
     const double m2 = min_distance * min_distance, m2_lo = m2 * (1.0 - 1e-9), m2_hi = m2 * (1.0 + 1e-9);
     bool hit = false;
     for (int e = threadIdx.x & 31; e < n; e += 32) {
