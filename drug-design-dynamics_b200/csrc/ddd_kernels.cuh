@@ -57,15 +57,13 @@ struct RecView {
 // Salmon et al. SC'11 (Random123).  Same counter/key convention as the host side:
 // counter = (index/2 lo, index/2 hi, stream lo, stream hi), key = (seed lo, seed hi);
 // words (0,1) -> draw 2k, words (2,3) -> draw 2k+1, 53-bit mantissa, [0,1).
-// DDD_PHILOX_UNROLL: the SM-persistent engine keeps the ten rounds rolled -- its serial phase is run by one
-// warp at a time and is bound by instruction fetch (L0 I-cache ~6 KB), not by issue slots.
-#ifndef DDD_PHILOX_UNROLL
-#define DDD_PHILOX_UNROLL 10
-#endif
-constexpr int kPhiloxUnroll = DDD_PHILOX_UNROLL;
-__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                       uint32_t k0, uint32_t k1, uint32_t out[4]) {
-#pragma unroll kPhiloxUnroll
+// UNROLL: the ten rounds are kept rolled where the call is off the hot path (accept draw, axis batch, per-atom draws of
+// oversized ligands): the chain kernels are large and a warp in its serial phase is bound by instruction fetch
+// (ncu: no_instruction), not by issue slots.  The staged jitter draws of the proposal use the unrolled form.
+template <int UNROLL>
+__host__ __device__ __forceinline__ void philox4x32_10_t(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                         uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll UNROLL
     for (int r = 0; r < 10; ++r) {
 #ifdef __CUDA_ARCH__
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -80,6 +78,13 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+#ifndef DDD_PHILOX_UNROLL
+#define DDD_PHILOX_UNROLL 1
+#endif
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                       uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    philox4x32_10_t<DDD_PHILOX_UNROLL>(c0, c1, c2, c3, k0, k1, out);
 }
 
 __host__ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {

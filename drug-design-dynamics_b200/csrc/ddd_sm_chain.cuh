@@ -656,8 +656,8 @@ __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotVie
             for (int b = lane; b < nb; b += 32) {
                 const uint64_t blk = b_first + (uint64_t)b;
                 uint32_t o[4];
-                philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)st.id, (uint32_t)(st.id >> 32),
-                              (uint32_t)st.seed, (uint32_t)(st.seed >> 32), o);
+                philox4x32_10_t<10>((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)st.id, (uint32_t)(st.id >> 32),
+                                    (uint32_t)st.seed, (uint32_t)(st.seed >> 32), o);
                 ub[b] = make_double2(u53(o[0], o[1]), u53(o[2], o[3]));
             }
             __syncwarp();
