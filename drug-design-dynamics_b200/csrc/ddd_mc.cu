@@ -561,7 +561,7 @@ int ddd_num_devices(void) {
 
 const char *ddd_last_error(void) { return g_err.c_str(); }
 
-const char *ddd_version(void) { return "ddd_mc 0.2 (sm_100a; SM-persistent chain engine: 16 warps per SM, speculative proposals, 384-atom pair-sum items)"; }
+const char *ddd_version(void) { return "ddd_mc 0.2 (sm_100a; SM-persistent chain engine: 16 warps per SM, speculative proposals, per-group pair sums)"; }
 
 void ddd_params_default(ddd_params *p) {
     if (!p) return;
