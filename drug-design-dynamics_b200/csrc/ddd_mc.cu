@@ -248,6 +248,7 @@ void plan_shards(const int64_t *offsets, int64_t n_lig, int replicas, int n_shar
 }
 
 void free_screen_dev(ScreenDev &sd) {
+    if (sd.di >= g_devs.size()) { sd = ScreenDev(); return; }      // the library was shut down: the context owns what is left
     cudaSetDevice(g_devs[sd.di].id);
     dev_free(sd.d_offsets); dev_free(sd.d_lig); dev_free(sd.d_order); dev_free(sd.d_out);
     dev_free(sd.d_stats); dev_free(sd.d_trace); dev_free(sd.d_rec); dev_free(sd.d_rec_off); dev_free(sd.d_queue); dev_free(sd.d_rmsd); dev_free(sd.d_units); dev_free(sd.d_lig_lj);
