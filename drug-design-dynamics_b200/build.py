@@ -27,7 +27,8 @@ def nvcc_path() -> str:
 
 
 def sources() -> list[Path]:
-    return [CSRC / "ddd_mc.cu", CSRC / "ddd_kernels.cuh", ROOT / "include" / "ddd_mc.h"]
+    """Everything ddd_mc.cu includes: every .cu/.cuh under csrc/ and every header under include/."""
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted((ROOT / "include").glob("*.h"))
 
 
 def is_stale() -> bool:

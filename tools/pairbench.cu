@@ -195,6 +195,147 @@ __global__ void __launch_bounds__(THREADS, MINB) k_packed_lig(const float4 *__re
     out[(size_t)blockIdx.x * THREADS + threadIdx.x] = e;
 }
 
+
+// ---------------------------------------------------------------- V4: packed, ligand-pair packing, EXPANDED form in the ligand-centred frame:
+// d2 = |p'|^2 + |l'|^2 - 2 p'.l' with p' = p - c, l' = l - c (c = ligand centroid).  Per receptor atom and ligand PAIR:
+// 3 FFMA2 + FADD2 (d2), 2 MUFU.RSQ, FFMA2 = 7 issue slots, 5 FMA-pipe ops (vs 9 / 7 in the direct clamp-free form).
+// ligand smem per pair: (-2x0,-2x1,-2y0,-2y1), (-2z0,-2z1,l2_0,l2_1), (q0,q1)
+template <int THREADS, int A, int UNROLL, int MODE = 0>
+__global__ void __launch_bounds__(THREADS, (A > 8 && THREADS == 128) ? 4 : 1) k_plig_exp(const float4 *__restrict__ rec, int n_pad, const float4 *__restrict__ lig,
+                                                        int nl, int reps, float rinv_max, double *out, Timing *tm) {
+    extern __shared__ float4 lf[];
+    const int nl2 = nl / 2;
+    float2 *lq = reinterpret_cast<float2 *>(lf + 2 * nl2);
+    __shared__ float cen[3];
+    if (threadIdx.x == 0) {
+        float cx = 0, cy = 0, cz = 0;
+        for (int i = 0; i < nl; ++i) { const float4 L = lig[(size_t)blockIdx.x % 64 * nl + i]; cx += L.x; cy += L.y; cz += L.z; }
+        cen[0] = cx / nl; cen[1] = cy / nl; cen[2] = cz / nl;
+    }
+    __syncthreads();
+    const float cx = cen[0], cy = cen[1], cz = cen[2];
+    for (int i = threadIdx.x; i < nl2; i += THREADS) {
+        float4 L0 = lig[(size_t)blockIdx.x % 64 * nl + 2 * i], L1 = lig[(size_t)blockIdx.x % 64 * nl + 2 * i + 1];
+        L0.x -= cx; L0.y -= cy; L0.z -= cz; L1.x -= cx; L1.y -= cy; L1.z -= cz;
+        lf[2 * i] = make_float4(-2.f * L0.x, -2.f * L1.x, -2.f * L0.y, -2.f * L1.y);
+        lf[2 * i + 1] = make_float4(-2.f * L0.z, -2.f * L1.z, L0.x * L0.x + L0.y * L0.y + L0.z * L0.z, L1.x * L1.x + L1.y * L1.y + L1.z * L1.z);
+        lq[i] = make_float2(L0.w, L1.w);
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) { tm->clk0 = clock64(); tm->ns0 = gtime(); }
+    double e = 0.0;
+    const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
+    const u64 *lq2 = reinterpret_cast<const u64 *>(lq);
+    for (int rep = 0; rep < reps; ++rep) {
+        for (int base = 0; base + THREADS * A <= n_pad; base += THREADS * A) {
+            u64 px[A], py[A], pz[A], pp[A], s[A]; float q[A];
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                const float4 P = __ldg(rec + base + a * THREADS + threadIdx.x);
+                const float x = P.x - cx, y = P.y - cy, z = P.z - cz;
+                const float p2 = fmaf(z, z, fmaf(y, y, x * x));
+                px[a] = pack2(x, x); py[a] = pack2(y, y); pz[a] = pack2(z, z); pp[a] = pack2(p2, p2); q[a] = P.w; s[a] = pack2(0.f, 0.f);
+            }
+            ulonglong2 Lxy = lf2[0], Lzl = lf2[1];
+            u64 Lq = lq2[0];
+#pragma unroll UNROLL
+            for (int l = 0; l < nl2; ++l) {
+                if (MODE != 2) { Lxy = lf2[2 * l]; Lzl = lf2[2 * l + 1]; Lq = lq2[l]; }
+                else { Lxy.x = add2(Lxy.x, Lq); }     // diagnostic: no LDS inside the loop (one extra FADD2 keeps the iterations distinct)
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    u64 d2;
+                    if (MODE == 1) d2 = fma2(px[a], Lxy.x, fma2(py[a], Lxy.y, fma2(pz[a], Lzl.x, add2(pp[a], Lzl.y))));
+                    else d2 = add2(fma2(px[a], Lxy.x, fma2(py[a], Lxy.y, fma2(pz[a], Lzl.x, Lzl.y))), pp[a]);
+                    float d2a, d2b; unpack2(d2, d2a, d2b);
+                    const float ra = rsq(d2a), rb = rsq(d2b);
+                    s[a] = fma2(Lq, pack2(ra, rb), s[a]);
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < A; ++a) { float sa, sb; unpack2(s[a], sa, sb); e = fma((double)q[a], (double)(sa + sb), e); }
+        }
+        if (rep + 1 < reps) { __syncthreads(); if (threadIdx.x < nl2) lf[2 * threadIdx.x].x += 1e-3f; __syncthreads(); }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { tm->clk1 = clock64(); tm->ns1 = gtime(); }
+    out[(size_t)blockIdx.x * THREADS + threadIdx.x] = e;
+}
+
+
+// ---------------------------------------------------------------- V5: V4 with the rsqrt of the last NN of the A atoms per lane done on the FMA pipe
+// (integer seed + tuned Newton step + one plain Newton step, max rel. error 7.6e-7): MUFU.RSQ is the binding pipe, the
+// expanded form leaves the FMA pipe half idle, so a fraction of the rsqrt's moves over.
+__device__ __forceinline__ u64 rsq2_fma(u64 d2) {
+    float a, b; unpack2(d2, a, b);
+    const float ya = __uint_as_float(0x5F1FFFF9u - (__float_as_uint(a) >> 1)), yb = __uint_as_float(0x5F1FFFF9u - (__float_as_uint(b) >> 1));
+    u64 y = pack2(ya, yb);
+    const u64 hk = mul2(d2, pack2(-0.703952253f, -0.703952253f)), h = mul2(d2, pack2(-0.5f, -0.5f));
+    u64 t = mul2(y, y);
+    t = fma2(hk, t, pack2(1.68191391f, 1.68191391f));
+    y = mul2(y, t);
+    t = mul2(y, y);
+    t = fma2(h, t, pack2(1.5f, 1.5f));
+    return mul2(y, t);
+}
+template <int THREADS, int A, int NN, int UNROLL>
+__global__ void __launch_bounds__(THREADS, 1) k_plig_mix(const float4 *__restrict__ rec, int n_pad, const float4 *__restrict__ lig,
+                                                        int nl, int reps, float rinv_max, double *out, Timing *tm) {
+    extern __shared__ float4 lf[];
+    const int nl2 = nl / 2;
+    float2 *lq = reinterpret_cast<float2 *>(lf + 2 * nl2);
+    __shared__ float cen[3];
+    if (threadIdx.x == 0) {
+        float cx = 0, cy = 0, cz = 0;
+        for (int i = 0; i < nl; ++i) { const float4 L = lig[(size_t)blockIdx.x % 64 * nl + i]; cx += L.x; cy += L.y; cz += L.z; }
+        cen[0] = cx / nl; cen[1] = cy / nl; cen[2] = cz / nl;
+    }
+    __syncthreads();
+    const float cx = cen[0], cy = cen[1], cz = cen[2];
+    for (int i = threadIdx.x; i < nl2; i += THREADS) {
+        float4 L0 = lig[(size_t)blockIdx.x % 64 * nl + 2 * i], L1 = lig[(size_t)blockIdx.x % 64 * nl + 2 * i + 1];
+        L0.x -= cx; L0.y -= cy; L0.z -= cz; L1.x -= cx; L1.y -= cy; L1.z -= cz;
+        lf[2 * i] = make_float4(-2.f * L0.x, -2.f * L1.x, -2.f * L0.y, -2.f * L1.y);
+        lf[2 * i + 1] = make_float4(-2.f * L0.z, -2.f * L1.z, L0.x * L0.x + L0.y * L0.y + L0.z * L0.z, L1.x * L1.x + L1.y * L1.y + L1.z * L1.z);
+        lq[i] = make_float2(L0.w, L1.w);
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) { tm->clk0 = clock64(); tm->ns0 = gtime(); }
+    double e = 0.0;
+    const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
+    const u64 *lq2 = reinterpret_cast<const u64 *>(lq);
+    for (int rep = 0; rep < reps; ++rep) {
+        for (int base = 0; base + THREADS * A <= n_pad; base += THREADS * A) {
+            u64 px[A], py[A], pz[A], pp[A], s[A]; float q[A];
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                const float4 P = __ldg(rec + base + a * THREADS + threadIdx.x);
+                const float x = P.x - cx, y = P.y - cy, z = P.z - cz;
+                const float p2 = fmaf(z, z, fmaf(y, y, x * x));
+                px[a] = pack2(x, x); py[a] = pack2(y, y); pz[a] = pack2(z, z); pp[a] = pack2(p2, p2); q[a] = P.w; s[a] = pack2(0.f, 0.f);
+            }
+#pragma unroll UNROLL
+            for (int l = 0; l < nl2; ++l) {
+                const ulonglong2 Lxy = lf2[2 * l], Lzl = lf2[2 * l + 1];
+                const u64 Lq = lq2[l];
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    const u64 d2 = add2(fma2(px[a], Lxy.x, fma2(py[a], Lxy.y, fma2(pz[a], Lzl.x, Lzl.y))), pp[a]);
+                    if (a < A - NN) {
+                        float d2a, d2b; unpack2(d2, d2a, d2b);
+                        const float ra = rsq(d2a), rb = rsq(d2b);
+                        s[a] = fma2(Lq, pack2(ra, rb), s[a]);
+                    } else s[a] = fma2(Lq, rsq2_fma(d2), s[a]);
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < A; ++a) { float sa, sb; unpack2(s[a], sa, sb); e = fma((double)q[a], (double)(sa + sb), e); }
+        }
+        if (rep + 1 < reps) { __syncthreads(); if (threadIdx.x < nl2) lf[2 * threadIdx.x].x += 1e-3f; __syncthreads(); }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { tm->clk1 = clock64(); tm->ns1 = gtime(); }
+    out[(size_t)blockIdx.x * THREADS + threadIdx.x] = e;
+}
+
 // pure MUFU.RSQ issue rate: 8 independent chains per thread
 __global__ void __launch_bounds__(128) k_mufu(int iters, float *out, Timing *tm) {
     float v[8];
@@ -216,7 +357,7 @@ struct Ctx {
 
 static const char *g_filter = "";
 template <typename F>
-void run(const char *name, F launch, const Ctx &c, int threads, int ctas_per_sm, int reps, size_t smem) {
+void run(const char *name, F launch, const Ctx &c, int threads, int ctas_per_sm, int reps, size_t smem, int tile = 0) {
     if (g_filter[0] && !strstr(name, g_filter)) return;
     const int grid = c.sms * ctas_per_sm;
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -233,7 +374,8 @@ void run(const char *name, F launch, const Ctx &c, int threads, int ctas_per_sm,
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         if (ms < best) { best = ms; CK(cudaMemcpy(&tm, c.tm, sizeof tm, cudaMemcpyDeviceToHost)); }
     }
-    const double pairs = (double)grid * reps * (double)c.n_pad * c.nl;
+    const double covered = tile > 0 ? (double)(c.n_pad / tile * tile) : (double)c.n_pad;     // atoms a pass really visits
+    const double pairs = (double)grid * reps * covered * c.nl;
     const double mhz = (double)(tm.clk1 - tm.clk0) / (double)(tm.ns1 - tm.ns0) * 1e3;
     const double pps = pairs / (best * 1e-3);
     const double ppc = pps / (mhz * 1e6) / c.sms;
@@ -282,11 +424,21 @@ int main(int argc, char **argv) {
     RUN_PACKED(128, 2, 2, 4); RUN_PACKED(128, 2, 2, 7); RUN_PACKED(128, 4, 1, 4); RUN_PACKED(128, 4, 1, 7); RUN_PACKED(128, 2, 4, 7);
     RUN_PLIG(128, 4, 2, 4); RUN_PLIG(128, 4, 2, 7); RUN_PLIG(128, 8, 1, 4); RUN_PLIG(128, 2, 2, 8);
     RUN_EXP(128, 4, 2, 4); RUN_EXP(128, 4, 2, 7); RUN_EXP(128, 8, 1, 4);
-#define RUN_PLIGM(T, A, U_, M, MB, OCC) run("plig-mode" #M " T" #T " A" #A " U" #U_ " minb" #MB, [&](int g, int t, size_t s, int r) { k_packed_lig<T, A, U_, M, MB><<<g, t, s>>>(c.rec, c.n_pad, c.lig, nl, r, rmax, c.out, c.tm); }, c, T, OCC, reps, sm2)
+#define RUN_PLIGM(T, A, U_, M, MB, OCC) run("plig-mode" #M " T" #T " A" #A " U" #U_ " minb" #MB, [&](int g, int t, size_t s, int r) { k_packed_lig<T, A, U_, M, MB><<<g, t, s>>>(c.rec, c.n_pad, c.lig, nl, r, rmax, c.out, c.tm); }, c, T, OCC, reps, sm2, T * A)
     RUN_PLIGM(128, 4, 2, 1, 1, 7); RUN_PLIGM(128, 4, 2, 2, 1, 7);
     RUN_PLIGM(128, 4, 2, 0, 1, 8); RUN_PLIGM(128, 4, 2, 0, 1, 9); RUN_PLIGM(128, 4, 4, 0, 1, 8);
     RUN_PLIGM(128, 2, 4, 0, 1, 12); RUN_PLIGM(128, 2, 2, 0, 1, 12); RUN_PLIGM(128, 2, 2, 0, 1, 16);
     RUN_PLIGM(256, 4, 2, 0, 1, 4); RUN_PLIGM(64, 4, 2, 0, 1, 16); RUN_PLIGM(64, 8, 1, 0, 1, 12); RUN_PLIGM(32, 8, 1, 0, 1, 28); RUN_PLIGM(32, 4, 2, 0, 1, 32);
+#define RUN_PEXP(T, A, U_, M, OCC) run("plig-exp" #M " T" #T " A" #A " U" #U_, [&](int g, int t, size_t s, int r) { k_plig_exp<T, A, U_, M><<<g, t, s>>>(c.rec, c.n_pad, c.lig, nl, r, rmax, c.out, c.tm); }, c, T, OCC, reps, sm2 + sizeof(float2) * nl, T * A)
+    RUN_PEXP(128, 4, 2, 0, 4); RUN_PEXP(128, 8, 1, 0, 4); RUN_PEXP(128, 4, 2, 0, 3); RUN_PEXP(128, 8, 1, 0, 3); RUN_PEXP(128, 8, 2, 0, 4); RUN_PEXP(128, 4, 4, 0, 4);
+    RUN_PEXP(128, 4, 2, 1, 4); RUN_PEXP(128, 8, 1, 1, 4); RUN_PEXP(128, 6, 1, 0, 4); RUN_PEXP(128, 2, 4, 0, 6); RUN_PEXP(256, 4, 2, 0, 2); RUN_PEXP(512, 4, 2, 0, 1); RUN_PEXP(512, 8, 1, 0, 1);
+    RUN_PLIGM(512, 8, 1, 2, 1, 1); RUN_PLIGM(512, 8, 1, 0, 1, 1);
+    RUN_PEXP(128, 8, 1, 2, 4); RUN_PEXP(128, 4, 2, 2, 4); RUN_PEXP(128, 10, 1, 0, 4); RUN_PEXP(128, 20, 1, 0, 4); RUN_PEXP(128, 20, 1, 0, 2); RUN_PEXP(128, 10, 1, 0, 5); RUN_PEXP(128, 8, 1, 0, 5); RUN_PEXP(128, 8, 1, 0, 6); RUN_PEXP(128, 8, 1, 0, 8);
+    RUN_PEXP(256, 10, 1, 0, 2); RUN_PEXP(512, 10, 1, 0, 1); RUN_PEXP(512, 5, 1, 0, 1); RUN_PEXP(512, 5, 2, 0, 1); RUN_PEXP(256, 20, 1, 0, 1); RUN_PEXP(256, 10, 1, 0, 1);
+#define RUN_PMIX(T, A, NN, U_, OCC) run("plig-mix T" #T " A" #A " N" #NN " U" #U_, [&](int g, int t, size_t s, int r) { k_plig_mix<T, A, NN, U_><<<g, t, s>>>(c.rec, c.n_pad, c.lig, nl, r, rmax, c.out, c.tm); }, c, T, OCC, reps, sm2 + sizeof(float2) * nl, T * A)
+    RUN_PMIX(128, 8, 0, 1, 4); RUN_PMIX(128, 8, 1, 1, 4); RUN_PMIX(128, 8, 2, 1, 4); RUN_PMIX(128, 8, 3, 1, 4); RUN_PMIX(128, 8, 8, 1, 4);
+    RUN_PMIX(128, 10, 1, 1, 4); RUN_PMIX(128, 10, 2, 1, 4); RUN_PMIX(128, 5, 1, 2, 4); RUN_PMIX(128, 4, 1, 2, 4); RUN_PMIX(128, 8, 1, 1, 8); RUN_PMIX(128, 8, 2, 1, 8);
+    RUN_PMIX(512, 10, 1, 1, 1); RUN_PMIX(512, 10, 2, 1, 1); RUN_PMIX(512, 5, 1, 1, 1); RUN_PMIX(512, 5, 1, 2, 1);
     if (!filter[0] || strstr("mufu-only", filter)) {
         cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
         float *o; CK(cudaMalloc(&o, sizeof(float) * c.sms * 16 * 128));
