@@ -85,10 +85,32 @@ def make_ligand(n_atoms: int, index: int, receptor: np.ndarray, tree: cKDTree | 
     return np.round(np.concatenate([xyz, q[:, None]], axis=1), 4)
 
 
-def make_ligands(sizes, receptor: np.ndarray, first_index: int = 0, seed0: int = LIGAND_SEED0):
-    """CSR batch: (offsets int64[n+1], xyzq float64[sum, 4]) for ligands first_index.. with the given sizes."""
-    tree = cKDTree(receptor[:, :3])
-    ligs = [make_ligand(int(n), first_index + i, receptor, tree, seed0) for i, n in enumerate(sizes)]
+_POOL_STATE = {}
+
+
+def _pool_init(receptor, seed0):
+    _POOL_STATE["rec"] = receptor
+    _POOL_STATE["tree"] = cKDTree(receptor[:, :3])
+    _POOL_STATE["seed0"] = seed0
+
+
+def _pool_make(job):
+    n, index = job
+    return make_ligand(n, index, _POOL_STATE["rec"], _POOL_STATE["tree"], _POOL_STATE["seed0"])
+
+
+def make_ligands(sizes, receptor: np.ndarray, first_index: int = 0, seed0: int = LIGAND_SEED0, workers: int = 1):
+    """CSR batch: (offsets int64[n+1], xyzq float64[sum, 4]) for ligands first_index.. with the given sizes.
+    Every ligand has its own seed, so `workers` > 1 (a process pool; call it before CUDA is initialised) gives the
+    same bits as the serial loop."""
+    sizes = [int(n) for n in sizes]
+    if workers > 1 and len(sizes) >= 256:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers, initializer=_pool_init, initargs=(receptor, seed0)) as pool:
+            ligs = pool.map(_pool_make, [(n, first_index + i) for i, n in enumerate(sizes)], chunksize=64)
+    else:
+        tree = cKDTree(receptor[:, :3])
+        ligs = [make_ligand(n, first_index + i, receptor, tree, seed0) for i, n in enumerate(sizes)]
     offsets = np.zeros(len(ligs) + 1, dtype=np.int64)
     offsets[1:] = np.cumsum([len(l) for l in ligs])
     xyzq = np.concatenate(ligs, axis=0) if ligs else np.zeros((0, 4))
