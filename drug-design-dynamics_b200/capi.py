@@ -24,10 +24,14 @@ SYMBOLS = [
     "ddd_screen_set_chain_slots", "ddd_screen_chain_slots", "ddd_screen_rmsd", "ddd_screen_pair_units", "ddd_screen_set_lj", "ddd_receptor_set_lj",
     "ddd_shard_plan", "ddd_device_info",
     "ddd_chain_kernel_info",
+    "ddd_receptor_acquire", "ddd_receptor_release", "ddd_last_chain_status",
+    "ddd_screen_fused_rmsd", "ddd_screen_randomize", "ddd_screen_shift_closer", "ddd_screen_download_start",
+    "ddd_screen_pick", "ddd_screen_argmin", "ddd_screen_set_track_best", "ddd_screen_download_best",
 ]
 
 DDD_OK, DDD_EINVAL, DDD_ENODEVICE, DDD_ECUDA, DDD_ELIMIT = 0, -1, -2, -3, -4
 PRECISION_F32, PRECISION_F64 = 0, 1
+ARGMIN_SAVE_MIN_LIGAND, ARGMIN_RSHINY = 0, 1
 MOVE_REFERENCE, MOVE_RIGID = 0, 1
 STATUS_RETRY_LIMIT, STATUS_STREAM_EXHAUSTED = 1, 2
 STREAM_PARENT_BASE = 0x4000000000000000
@@ -119,6 +123,17 @@ def lib() -> C.CDLL:
         "ddd_device_info": (C.c_int, [C.c_int, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),
                                       C.POINTER(i32), C.c_char_p, i32]),
         "ddd_chain_kernel_info": (C.c_int, [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+        "ddd_receptor_acquire": (C.c_int, [vp, i64, C.POINTER(vp)]),
+        "ddd_receptor_release": (C.c_int, [vp]),
+        "ddd_last_chain_status": (i64, [C.POINTER(i64)]),
+        "ddd_screen_fused_rmsd": (C.c_int, [vp, vp]),
+        "ddd_screen_randomize": (C.c_int, [vp, u64, u64]),
+        "ddd_screen_shift_closer": (C.c_int, [vp, dbl]),
+        "ddd_screen_download_start": (C.c_int, [vp, vp]),
+        "ddd_screen_pick": (C.c_int, [vp, dbl, u64, u64, vp, vp, vp, vp]),
+        "ddd_screen_argmin": (C.c_int, [vp, i32, C.POINTER(i64), C.POINTER(dbl)]),
+        "ddd_screen_set_track_best": (C.c_int, [vp, i32]),
+        "ddd_screen_download_best": (C.c_int, [vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -199,11 +214,16 @@ def unpack_ligands(offsets, xyzq):
 class Receptor:
     """ddd_receptor: the protein Molecule (datatypes.go:14-16) resident on every device."""
 
-    def __init__(self, xyzq):
+    def __init__(self, xyzq, cached=False):
+        """cached=True: ddd_receptor_acquire -- the library's content-keyed cache (what the scalar API mirrors use)."""
         a = _f64(xyzq).reshape(-1, 4)
         self.n_atoms = a.shape[0]
         self._h = C.c_void_p()
-        _check(lib().ddd_receptor_create(_ptr(a), a.shape[0], C.byref(self._h)))
+        self._cached = cached
+        if cached:
+            _check(lib().ddd_receptor_acquire(_ptr(a), a.shape[0], C.byref(self._h)))
+        else:
+            _check(lib().ddd_receptor_create(_ptr(a), a.shape[0], C.byref(self._h)))
 
     @property
     def handle(self):
@@ -219,7 +239,10 @@ class Receptor:
 
     def close(self):
         if self._h:
-            lib().ddd_receptor_destroy(self._h)
+            if self._cached:
+                lib().ddd_receptor_release(self._h)
+            else:
+                lib().ddd_receptor_destroy(self._h)
             self._h = C.c_void_p()
 
     def __enter__(self):
@@ -286,6 +309,13 @@ def minimize_batch(rec: Receptor, offsets, xyzq, iterations, rotate, temperature
                                     float(temperature), num_procs, C.byref(p), seed, first_ligand_index,
                                     _ptr(out), _ptr(energy), _ptr(stats), _ptr(picked)))
     return (out, energy, picked, stats) if want_stats else (out, energy, picked)
+
+
+def last_chain_status():
+    """(OR of the DDD_STATUS_* bits, chains stopped at the retry bound) of this thread's last minimize_batch / run_chains."""
+    n = C.c_int64()
+    bits = lib().ddd_last_chain_status(C.byref(n))
+    return int(bits), int(n.value)
 
 
 def rmsd_batch(offsets, sim, ref, atom_stride=4):
@@ -391,6 +421,48 @@ class Screen:
         ms = C.c_double()
         _check(lib().ddd_screen_rmsd(self._h, _ptr(out), C.byref(ms)))
         return out, ms.value
+
+    def fused_rmsd(self):
+        """the per-chain RMSD the chain kernel's epilogue computed (SM-persistent engine); same bits as rmsd()"""
+        out = np.zeros(self.n_chains)
+        _check(lib().ddd_screen_fused_rmsd(self._h, _ptr(out)))
+        return out
+
+    # ---- resident pipeline (validateResults.go:14-45, metropolis.go:14-16, plotting.go:109-121)
+    def randomize(self, seed=1, first_ligand_index=0):
+        _check(lib().ddd_screen_randomize(self._h, seed, first_ligand_index))
+
+    def shift_closer(self, threshold=5.0):
+        _check(lib().ddd_screen_shift_closer(self._h, float(threshold)))
+
+    def download_start(self):
+        out = np.zeros((int(self.offsets[-1]) if self.n_lig else 0, 4))
+        _check(lib().ddd_screen_download_start(self._h, _ptr(out)))
+        return out
+
+    def pick(self, temperature, seed=1, first_ligand_index=0, download=True):
+        """replica pick on the device -> (pose[sum nL, 4], energy[n_lig], picked[n_lig], rmsd[n_lig]) (or None when download=False)"""
+        if not download:
+            _check(lib().ddd_screen_pick(self._h, float(temperature), seed, first_ligand_index, None, None, None, None))
+            return None
+        out = np.zeros((int(self.offsets[-1]) if self.n_lig else 0, 4))
+        en = np.zeros(self.n_lig); pk = np.zeros(self.n_lig, dtype=np.int64); rm = np.zeros(self.n_lig)
+        _check(lib().ddd_screen_pick(self._h, float(temperature), seed, first_ligand_index, _ptr(out), _ptr(en), _ptr(pk), _ptr(rm)))
+        return out, en, pk, rm
+
+    def argmin(self, rule=ARGMIN_SAVE_MIN_LIGAND):
+        idx, en = C.c_int64(), C.c_double()
+        _check(lib().ddd_screen_argmin(self._h, rule, C.byref(idx), C.byref(en)))
+        return int(idx.value), float(en.value)
+
+    def set_track_best(self, on=True):
+        _check(lib().ddd_screen_set_track_best(self._h, int(bool(on))))
+
+    def download_best(self):
+        out = np.zeros((int(self.offsets[-1]) * self.replicas if self.n_lig else 0, 4))
+        en = np.zeros(self.n_chains)
+        _check(lib().ddd_screen_download_best(self._h, _ptr(out), _ptr(en)))
+        return out, en
 
     def close(self):
         if self._h:

@@ -29,6 +29,7 @@ struct DevParams {
     double rigid_translation, rigid_angle, temperature;
     long long max_retries;
     float rinv_max;              // 1 / clamp_distance: clamp d >= 1e-6  <=>  1/d <= 1e6 (:255-257)
+    float apart_gap;             // receptor-group / pose boxes farther apart than this skip the clamp: max(1e-3, 2.5 clamp_distance)
     int move_mode, rotate;
     double cutoff;               // EXTENSION: > 0 = shifted-Coulomb cutoff radius (0: the reference's untruncated sum)
     float rc_inv;                // 1 / cutoff (0 when off)
@@ -414,6 +415,11 @@ struct ChainArgs {
     void *out_stats;              // ddd_chain_stats[n_chains_local]
     uint8_t *out_trace;           // nullable: n_chains_local * steps
     int nl_cap;                   // even; shared-memory arrays are sized for nl_cap atoms
+    // SM-persistent engine only (nullable):
+    const double *ref_xyzq;       // reference poses for the fused CalculateRMSD (validateResults.go:50-65), indexed like lig_xyzq
+    double *out_rmsd;             // [n_chains_local] RMSD(final pose, reference pose) written by the chain's epilogue
+    double *out_best_xyzq;        // best-ever pose per chain, laid out like out_xyzq (EXTENSION: the reference returns the final pose)
+    double *out_best_e;           // [n_chains_local] lowest chain energy seen (start pose included)
 };
 
 // mirrors ddd_chain_stats (include/ddd_mc.h)
@@ -734,7 +740,8 @@ __global__ void __launch_bounds__(THREADS, (PRECISE ? 1 : DDD_CHAIN_WARPS_PER_SM
 struct EnergyArgs {
     RecView rec;
     DevParams prm;
-    const long long *offsets;   // local CSR (n+1), offsets[0] == 0
+    const long long *offsets;   // CSR of this launch's ligands (n+1 entries of the caller's array)
+    long long atom_base;        // atom index of lig_xyzq[0] (a device may hold only a slice of the batch)
     const double *lig_xyzq;
     double *out_energy;
     double *out_abs;            // nullable
@@ -748,7 +755,7 @@ __global__ void __launch_bounds__(kThreads) energy_batch_kernel(const EnergyArgs
     const long long lig = blockIdx.x;
     const long long off = a.offsets[lig];
     const int nl = (int)(a.offsets[lig + 1] - off);
-    const double *src = a.lig_xyzq + off * 4;
+    const double *src = a.lig_xyzq + (off - a.atom_base) * 4;
     for (int i = tid; i < nl; i += kThreads) {
         const double x = src[4 * i], y = src[4 * i + 1], z = src[4 * i + 2], q = src[4 * i + 3];
         s.cx()[i] = x; s.cy()[i] = y; s.cz()[i] = z; s.q()[i] = q;
@@ -778,7 +785,8 @@ __global__ void __launch_bounds__(kThreads) energy_batch_kernel(const EnergyArgs
 // ------------------------------------------------------------------ FindClosestAtomDistance (:290-304) + shift (:267-285)
 struct ClosestArgs {
     RecView rec;
-    const long long *offsets;
+    const long long *offsets;   // points at the first ligand of this launch
+    long long atom_base;        // atom index of lig_xyzq[0]
     double *lig_xyzq;           // in/out when do_shift
     double *out_dist;           // nullable
     long long *out_lig_atom, *out_prot_atom;   // nullable
@@ -799,7 +807,7 @@ __global__ void __launch_bounds__(kThreads) closest_atom_kernel(const ClosestArg
     const long long lig = blockIdx.x;
     const long long off = a.offsets[lig];
     const int nl = (int)(a.offsets[lig + 1] - off);
-    double *atoms = a.lig_xyzq + off * 4;
+    double *atoms = a.lig_xyzq + (off - a.atom_base) * 4;
     const int np = a.rec.n;
     double best = 1.7976931348623157e308;        // math.MaxFloat64 (:291)
     long long key = 0x7fffffffffffffffll;
@@ -852,15 +860,15 @@ __global__ void __launch_bounds__(kThreads) closest_atom_kernel(const ClosestArg
 
 // ------------------------------------------------------------------ CalculateRMSD batch (validateResults.go:50-65)
 // One warp per (simulated, reference) pair; lane-strided atoms, coalesced; memory-bound.
-__global__ void __launch_bounds__(256) rmsd_batch_kernel(const long long *__restrict__ offsets,
+__global__ void __launch_bounds__(256) rmsd_batch_kernel(const long long *__restrict__ offsets, long long atom_base,
                                                          const double *__restrict__ sim,
                                                          const double *__restrict__ ref, int stride,
                                                          long long n_pairs, double *__restrict__ out) {
     const long long pair = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (pair >= n_pairs) return;
     const int lane = threadIdx.x & 31;
-    const long long off = offsets[pair];
-    const int n = (int)(offsets[pair + 1] - off);
+    const long long off = offsets[pair] - atom_base;
+    const int n = (int)(offsets[pair + 1] - offsets[pair]);
     double acc = 0.0;
     if (stride == 4) {
         const double4 *s4 = reinterpret_cast<const double4 *>(sim) + off;
@@ -906,13 +914,100 @@ __global__ void __launch_bounds__(256) rmsd_chains_kernel(const long long *__res
     if (lane == 0) out[local] = sqrt(acc / (double)n);                    // :64 (n == 0 -> NaN)
 }
 
+// ------------------------------------------------------------------ replica pick (metropolis.go:102-109) on device
+// One thread per ligand: currentEnergy = E(start) (:96); for every replica in replica-index order (the reference's order is
+// channel arrival) newEnergy = E(result) (:104), AcceptMove (:105, :141-149) with the ligand's parent stream.
+// out_picked = the replica kept (-1: the start pose), out_energy = its energy = CalculateEnergy(minLigand) (:61).
+__global__ void __launch_bounds__(128) replica_pick_kernel(const ChainStats *__restrict__ stats, long long n_lig_local, long long lig0,
+                                                           long long chain_begin, int replicas, double temperature, uint64_t seed,
+                                                           uint64_t parent_base, double *__restrict__ out_energy, long long *__restrict__ out_picked) {
+    const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_lig_local) return;
+    const ChainStats *cs = stats + ((lig0 + l) * replicas - chain_begin);
+    double cur_e = cs[0].start_energy;                                      // :96
+    long long picked = -1;
+    uint64_t pos = 0;
+    const uint64_t parent = parent_base + (uint64_t)(lig0 + l);
+    for (int r = 0; r < replicas; ++r) {
+        const double new_e = cs[r].final_energy;                            // :104
+        bool acc = new_e < cur_e;                                           // :142
+        if (!acc) {
+            const double probability = exp(-(new_e - cur_e) / temperature); // :147
+            acc = philox_u01(seed, parent, pos++) < probability;            // :148
+        }
+        if (acc) { cur_e = new_e; picked = r; }                             // :106-107
+    }
+    out_energy[l] = cur_e;
+    out_picked[l] = picked;
+}
+
+// One warp per ligand: copy the picked replica's final pose (or the start pose when no replica was kept) into the
+// per-ligand CSR output, and CalculateRMSD (validateResults.go:50-65) of that pose against the reference pose.
+__global__ void __launch_bounds__(256) pick_gather_kernel(const long long *__restrict__ offsets, const double *__restrict__ start_xyzq,
+                                                          const double *__restrict__ ref_xyzq, long long atom_base,
+                                                          const double *__restrict__ chain_xyzq, long long out_base, int replicas,
+                                                          const long long *__restrict__ picked, long long n_lig_local, long long lig0,
+                                                          double *__restrict__ out_xyzq, double *__restrict__ out_rmsd) {
+    const long long l = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (l >= n_lig_local) return;
+    const int lane = threadIdx.x & 31;
+    const long long lig = lig0 + l;
+    const long long off = offsets[lig];
+    const int n = (int)(offsets[lig + 1] - off);
+    const long long pk = picked[l];
+    const double4 *src = pk >= 0 ? reinterpret_cast<const double4 *>(chain_xyzq) + ((long long)replicas * off + pk * n - out_base)
+                                 : reinterpret_cast<const double4 *>(start_xyzq) + (off - atom_base);
+    const double4 *r4 = reinterpret_cast<const double4 *>(ref_xyzq) + (off - atom_base);
+    double4 *dst = reinterpret_cast<double4 *>(out_xyzq) + (off - atom_base);
+    double acc = 0.0;
+    for (int i = lane; i < n; i += 32) {
+        const double4 v = src[i], ra = r4[i];
+        dst[i] = v;
+        const double dx = v.x - ra.x, dy = v.y - ra.y, dz = v.z - ra.z;
+        acc += dx * dx + dy * dy + dz * dz;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0 && out_rmsd) out_rmsd[l] = sqrt(acc / (double)n);
+}
+
+// ------------------------------------------------------------------ SaveMinimumEnergyLigand's argmin (plotting.go:109-121)
+// The reference scans the energies in order with `if energy < minEnergy` from (minIndex 0, minEnergy init): the result is the
+// FIRST index that attains the global minimum if that minimum is below `init`, else (0, init).  One CTA: (value, index) pairs
+// reduced with "smaller value, then smaller index"; NaN never satisfies `<` and is skipped like in Go.
+__global__ void __launch_bounds__(1024) argmin_first_kernel(const double *__restrict__ e, long long n, long long index_base,
+                                                            double *__restrict__ out_val, long long *__restrict__ out_idx) {
+    __shared__ double sv[32];
+    __shared__ long long si[32];
+    double best = 1.7976931348623157e308 * 2.0;                             // +inf
+    long long bi = 0x7fffffffffffffffll;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = e[i];
+        if (v < best) { best = v; bi = i; }                                 // ascending i per thread: first minimum kept
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov < best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (sv[w] < best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+        *out_val = best;
+        *out_idx = bi == 0x7fffffffffffffffll ? -1 : bi + index_base;
+    }
+}
+
 // ------------------------------------------------------------------ RandomizeLigandPose (validateResults.go:70-79)
-__global__ void __launch_bounds__(kThreads) randomize_pose_kernel(const long long *offsets, double *lig_xyzq,
+// `offsets` points at the first ligand of this launch, `lig_xyzq` at atom `atom_base` (a device may hold only a slice)
+__global__ void __launch_bounds__(kThreads) randomize_pose_kernel(const long long *offsets, double *lig_xyzq, long long atom_base,
                                                                   uint64_t seed, uint64_t first_index) {
     const long long lig = blockIdx.x;
     const long long off = offsets[lig];
     const int nl = (int)(offsets[lig + 1] - off);
-    double *atoms = lig_xyzq + off * 4;
+    double *atoms = lig_xyzq + (off - atom_base) * 4;
     Stream st; st.rec = nullptr; st.rec_len = 0; st.seed = seed;
     st.id = 0x2000000000000000ull + first_index + (uint64_t)lig;
     int status = 0;

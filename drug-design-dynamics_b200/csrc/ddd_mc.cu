@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cmath>
+#include <functional>
 #include <mutex>
 #include <numeric>
 #include <string>
@@ -29,7 +30,13 @@ static_assert(sizeof(Atom64) == 32, "Atom64 must be 4 doubles");
 namespace {
 
 thread_local std::string g_err;
+thread_local int64_t g_status_bits = 0;    // OR of the chain status bits of this thread's last ddd_minimize_batch / ddd_run_chains
+thread_local int64_t g_status_chains = 0;  // how many chains of that call carried DDD_STATUS_RETRY_LIMIT
 std::recursive_mutex g_mu;
+uint64_t g_epoch = 1;                      // bumped by ddd_shutdown: handles created before it are stale (refused by every entry
+                                           // point, freed with plain cudaFree on the device id they recorded)
+
+void purge_cache(bool everything);         // receptor cache (defined with ddd_receptor_acquire)
 
 struct Dev {
     int id = 0;
@@ -93,6 +100,7 @@ DevParams make_dev_params(const ddd_params &p, int rotate, double temperature) {
     d.temperature = temperature;
     d.max_retries = p.max_retries > 0 ? p.max_retries : (1ll << 62);
     d.rinv_max = p.clamp_distance > 0 ? (float)(1.0 / p.clamp_distance) : 3.402823466e38f;
+    d.apart_gap = (float)std::max(1e-3, 2.5 * p.clamp_distance);
     d.move_mode = p.move_mode; d.rotate = rotate ? 1 : 0;
     d.cutoff = p.cutoff > 0 ? p.cutoff : 0.0;
     d.rc_inv = p.cutoff > 0 ? (float)(1.0 / p.cutoff) : 0.f;
@@ -144,6 +152,11 @@ int set_smem(K kernel, size_t bytes) {
 
 // ------------------------------------------------------------------ opaque handles
 struct ddd_receptor {
+    uint64_t epoch = 0;                      // g_epoch at creation: a handle that outlived ddd_shutdown is stale
+    std::vector<int> dev_ids;                // CUDA ordinal of every per-device copy (for frees after a shutdown)
+    int64_t refs = 0;                        // receptor cache (ddd_receptor_acquire): users of this entry
+    uint64_t hash = 0;                       // receptor cache: content hash of the xyzq array
+    bool cached = false;
     int64_t n = 0, n_pad = 0;
     double cx = 0, cy = 0, cz = 0;
     std::vector<float4 *> f32;     // per device
@@ -166,6 +179,7 @@ struct ddd_receptor {
 
 struct ScreenDev {
     size_t di = 0;                         // index into g_devs
+    int dev_id = 0;                        // CUDA ordinal (for frees after a shutdown)
     int64_t c0 = 0, c1 = 0;                // global chain range
     int64_t lig0 = 0, lig1 = 0;            // ligands touched [lig0, lig1)
     int64_t atom_base = 0, n_atoms_in = 0; // slice of the start poses
@@ -188,9 +202,23 @@ struct ScreenDev {
     long long *d_units = nullptr;          // per-chain receptor units evaluated (cutoff extension)
     double2 *d_lig_lj = nullptr;           // LJ extension: (sigma/2, sqrt(eps)) of this device's slice of the ligand atoms
     float rmsd_ms = 0.f;
+    // resident pipeline (randomise -> shift -> chains -> pick -> RMSD -> argmin, validateResults.go:14-45 / plotting.go:109-121)
+    double *d_ref = nullptr;               // reference poses: the start poses as uploaded, kept once randomise / shift touch d_lig
+    double *d_best = nullptr;              // best-ever pose per chain (chain-major like d_out), EXTENSION
+    double *d_best_e = nullptr;            // lowest chain energy seen, per chain
+    double *d_min = nullptr;               // per-ligand picked pose (ligand CSR slice like d_lig)
+    double *d_min_e = nullptr;             // per-ligand picked energy
+    long long *d_picked = nullptr;         // per-ligand replica kept (-1: start pose)
+    double *d_min_rmsd = nullptr;          // per-ligand RMSD(picked pose, reference)
+    double *d_arg_val = nullptr;           // argmin scratch
+    long long *d_arg_idx = nullptr;
+    bool fused_rmsd = false;               // the last run's epilogue filled d_rmsd
 };
 
 struct ddd_screen {
+    uint64_t epoch = 0;
+    bool track_best = false;               // ddd_screen_set_track_best
+    bool picked = false;                   // ddd_screen_pick has run on the last run's results
     const ddd_receptor *rec = nullptr;
     int64_t n_lig = 0, n_chains = 0, steps = 0;
     int replicas = 1;
@@ -224,51 +252,67 @@ int pick_chain_slots(int64_t n_chains, int grid) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(kSlotsAuto, per_sm));
 }
 
-// chains [begin[k], begin[k+1]) go to shard k; contiguous, balanced by sum(nL + 1)
+// chains [begin[k], begin[k+1]) go to shard k; contiguous, balanced by sum(nL + 1).  A ligand's replicas stay together on one
+// shard (the cut nearest to the balanced position that falls between two ligands), so the replica pick (:102-109) and the
+// per-ligand results need no exchange between devices.
 void plan_shards(const int64_t *offsets, int64_t n_lig, int replicas, int n_shards, std::vector<int64_t> &begin) {
     begin.assign((size_t)n_shards + 1, 0);
     const int64_t n_chains = n_lig * replicas;
     begin[(size_t)n_shards] = n_chains;
     if (n_shards <= 1 || n_chains == 0) return;
-    const double total = (double)replicas * (double)(offsets[n_lig] + n_lig);
+    const double total = (double)(offsets[n_lig] + n_lig);
     int64_t lig = 0;
     for (int k = 1; k < n_shards; ++k) {
         const double target = total * (double)k / (double)n_shards;
-        while (lig < n_lig && (double)replicas * (double)(offsets[lig + 1] + lig + 1) <= target) ++lig;
-        int64_t c = lig * replicas;
+        while (lig < n_lig && (double)(offsets[lig + 1] + lig + 1) <= target) ++lig;
+        int64_t cut = lig;                                                  // ligands [0, cut) weigh <= target
         if (lig < n_lig) {
-            const double before = (double)replicas * (double)(offsets[lig] + lig);
-            const double per_chain = (double)(offsets[lig + 1] - offsets[lig] + 1);
-            int64_t r = (int64_t)std::llround((target - before) / per_chain);
-            r = std::max<int64_t>(0, std::min<int64_t>(replicas, r));
-            c += r;
+            const double before = (double)(offsets[lig] + lig), after = (double)(offsets[lig + 1] + lig + 1);
+            if (after - target < target - before) cut = lig + 1;           // the nearer ligand boundary
         }
-        begin[(size_t)k] = std::max(begin[(size_t)k - 1], std::min(c, n_chains));
+        begin[(size_t)k] = std::max(begin[(size_t)k - 1], std::min(cut * replicas, n_chains));
     }
 }
 
-void free_screen_dev(ScreenDev &sd) {
-    if (sd.di >= g_devs.size()) { sd = ScreenDev(); return; }      // the library was shut down: the context owns what is left
-    cudaSetDevice(g_devs[sd.di].id);
-    dev_free(sd.d_offsets); dev_free(sd.d_lig); dev_free(sd.d_order); dev_free(sd.d_out);
-    dev_free(sd.d_stats); dev_free(sd.d_trace); dev_free(sd.d_rec); dev_free(sd.d_rec_off); dev_free(sd.d_queue); dev_free(sd.d_rmsd); dev_free(sd.d_units); dev_free(sd.d_lig_lj);
+// `live`: the screen belongs to the current initialisation (frees go to the device's pool on the library's stream);
+// otherwise it outlived a ddd_shutdown and its buffers are released with plain cudaFree on the device they live on
+void free_screen_dev(ScreenDev &sd, bool live) {
+    void *bufs[] = {sd.d_offsets, sd.d_lig, sd.d_order, sd.d_out, sd.d_stats, sd.d_trace, sd.d_rec, sd.d_rec_off, sd.d_queue, sd.d_rmsd,
+                    sd.d_units, sd.d_lig_lj, sd.d_ref, sd.d_best, sd.d_best_e, sd.d_min, sd.d_min_e, sd.d_picked, sd.d_min_rmsd,
+                    sd.d_arg_val, sd.d_arg_idx};
+    cudaSetDevice(sd.dev_id);
+    for (void *b : bufs) { if (!b) continue; if (live) dev_free(b); else cudaFree(b); }
     sd = ScreenDev();
+}
+
+int check_receptor(const ddd_receptor *r) {
+    if (!r) return fail(DDD_EINVAL, "receptor is NULL");
+    if (r->epoch != g_epoch) return fail(DDD_EINVAL, "receptor handle is stale: it was created before the last ddd_shutdown / ddd_init");
+    return DDD_OK;
+}
+
+int check_screen(const ddd_screen *s) {
+    if (!s) return fail(DDD_EINVAL, "screen is NULL");
+    if (s->epoch != g_epoch) return fail(DDD_EINVAL, "screen handle is stale: it was created before the last ddd_shutdown / ddd_init");
+    return DDD_OK;
 }
 
 int screen_create_impl(const ddd_receptor *r, const int64_t *offsets, const double *lig_xyzq, int64_t n_lig,
                        int32_t replicas, uint64_t first_chain_id, ddd_screen **out) {
-    if (!r || !out) return fail(DDD_EINVAL, "receptor/out is NULL");
+    if (!out) return fail(DDD_EINVAL, "out is NULL");
+    if (int rc = check_receptor(r)) return rc;
     if (replicas <= 0) return fail(DDD_EINVAL, "replicas must be >= 1 (got %d)", replicas);
     int64_t max_nl = 0;
     if (int rc = check_csr(offsets, n_lig, lig_xyzq, &max_nl)) return rc;
     ddd_screen *s = new ddd_screen();
+    s->epoch = g_epoch;
     s->rec = r; s->n_lig = n_lig; s->replicas = replicas; s->n_chains = n_lig * replicas; s->chain_id_base = first_chain_id;
     s->offsets.assign(offsets ? offsets : nullptr, offsets ? offsets + n_lig + 1 : nullptr);
     if (s->offsets.empty()) s->offsets.push_back(0);
     std::vector<int64_t> begin;
     plan_shards(s->offsets.data(), n_lig, replicas, (int)g_devs.size(), begin);
     for (size_t di = 0; di < g_devs.size(); ++di) {
-        ScreenDev sd; sd.di = di; sd.c0 = begin[di]; sd.c1 = begin[di + 1];
+        ScreenDev sd; sd.di = di; sd.dev_id = g_devs[di].id; sd.c0 = begin[di]; sd.c1 = begin[di + 1];
         if (sd.c1 <= sd.c0) continue;
         sd.lig0 = sd.c0 / replicas; sd.lig1 = (sd.c1 - 1) / replicas + 1;
         sd.atom_base = s->offsets[(size_t)sd.lig0];
@@ -326,7 +370,7 @@ int screen_create_impl(const ddd_receptor *r, const int64_t *offsets, const doub
             if (ce != cudaSuccess) guard(fail(DDD_ECUDA, "sync after upload: %s", cudaGetErrorString(ce)));
         }
         if (rc) {
-            for (auto &x : s->devs) free_screen_dev(x);
+            for (auto &x : s->devs) free_screen_dev(x, true);
             delete s;
             return rc;
         }
@@ -337,7 +381,7 @@ int screen_create_impl(const ddd_receptor *r, const int64_t *offsets, const doub
 
 int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double temperature, const ddd_params *p,
                     uint64_t seed, const double *recorded, const int64_t *recorded_offsets, bool want_trace) {
-    if (!s) return fail(DDD_EINVAL, "screen is NULL");
+    if (int rc = check_screen(s)) return rc;
     if (steps < 0) return fail(DDD_EINVAL, "negative step count");
     if (int rc = check_params(p)) return rc;
     if ((recorded == nullptr) != (recorded_offsets == nullptr) && s->n_chains > 0)
@@ -374,6 +418,9 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
         a.recorded = d.d_rec; a.rec_offsets = d.d_rec_off; a.rec_base = d.rec_base;
         a.out_xyzq = d.d_out; a.out_base = d.out_base; a.out_stats = d.d_stats; a.out_trace = d.d_trace;
         a.nl_cap = d.nl_cap;
+        a.ref_xyzq = nullptr; a.out_rmsd = nullptr; a.out_best_xyzq = nullptr; a.out_best_e = nullptr;
+        d.fused_rmsd = false;
+        s->picked = false;
         const bool precise = p->precision == DDD_PRECISION_F64;
         const bool cut = p->cutoff > 0;
         const bool lj = p->lj_scale != 0.0;
@@ -389,8 +436,18 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
         if (cut && (s->threads_override > 0 || !fits_sm_engine))
             return fail(DDD_EINVAL, "params.cutoff needs the SM-persistent engine (chain_threads 0 and a ligand that fits one SM's shared memory)");
         if (cut && s->rec->n_units_s > 65535) return fail(DDD_ELIMIT, "params.cutoff supports receptors up to 2097120 atoms");
+        if (s->track_best && n_local > 0 && (s->threads_override > 0 || !fits_sm_engine))
+            return fail(DDD_EINVAL, "best-ever tracking needs the SM-persistent engine (chain_threads 0 and a ligand that fits one SM's shared memory)");
         if (s->threads_override <= 0 && n_local > 0 && fits_sm_engine) {
             // SM-persistent engine: one 32-warp CTA per SM, K resident chains each (ddd_sm_chain.cuh)
+            // its epilogue also leaves CalculateRMSD(final pose, reference pose) of every chain in d_rmsd (CompareRMSD :40-45)
+            if (!d.d_rmsd) { if (int rc = dev_alloc(&d.d_rmsd, (size_t)n_local)) return rc; }
+            a.ref_xyzq = d.d_ref ? d.d_ref : d.d_lig; a.out_rmsd = d.d_rmsd; d.fused_rmsd = true;
+            if (s->track_best) {
+                if (!d.d_best) { if (int rc = dev_alloc(&d.d_best, (size_t)d.out_atoms * 4)) return rc; }
+                if (!d.d_best_e) { if (int rc = dev_alloc(&d.d_best_e, (size_t)n_local)) return rc; }
+                a.out_best_xyzq = d.d_best; a.out_best_e = d.d_best_e;
+            }
             SmArgs A;
             A.c = a;
             const int grid = (int)std::min<int64_t>(dev.sm_count, n_local);
@@ -453,7 +510,7 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
 }
 
 int screen_sync_impl(ddd_screen *s) {
-    if (!s) return fail(DDD_EINVAL, "screen is NULL");
+    if (int rc0 = check_screen(s)) return rc0;
     for (auto &d : s->devs) {
         const Dev &dev = g_devs[d.di];
         CUDA_TRY(cudaSetDevice(dev.id));
@@ -464,7 +521,7 @@ int screen_sync_impl(ddd_screen *s) {
 }
 
 int screen_download_impl(ddd_screen *s, double *out_xyzq, ddd_chain_stats *out_stats, uint8_t *out_trace) {
-    if (!s) return fail(DDD_EINVAL, "screen is NULL");
+    if (int rc0 = check_screen(s)) return rc0;
     if (!s->launched) return fail(DDD_EINVAL, "screen has not been run");
     if (int rc = screen_sync_impl(s)) return rc;
     for (auto &d : s->devs) {
@@ -487,16 +544,93 @@ int screen_download_impl(ddd_screen *s, double *out_xyzq, ddd_chain_stats *out_s
 
 void screen_destroy_impl(ddd_screen *s) {
     if (!s) return;
-    for (auto &d : s->devs) free_screen_dev(d);
+    for (auto &d : s->devs) free_screen_dev(d, s->epoch == g_epoch);
     delete s;
 }
 
-// AcceptMove (:141-149) on the host, for the replica pick only (:105)
-bool accept_move_host(double cur_e, double new_e, double temperature, uint64_t seed, uint64_t stream, uint64_t &pos) {
-    if (new_e < cur_e) return true;
-    const double delta = new_e - cur_e;
-    const double probability = std::exp(-delta / temperature);
-    return philox_u01(seed, stream, pos++) < probability;
+// frees every per-device copy on the device it was created on (valid after a ddd_shutdown too: the CUDA context persists)
+void destroy_receptor(ddd_receptor *r) {
+    for (size_t di = 0; di < r->f32.size() && di < r->dev_ids.size(); ++di) {
+        cudaSetDevice(r->dev_ids[di]);
+        cudaFree(r->f32[di]); cudaFree(r->f64[di]);
+        if (di < r->f32s.size()) { cudaFree(r->f32s[di]); cudaFree(r->ubox[di]); cudaFree(r->f64s[di]); cudaFree(r->gbox[di]);
+                                    cudaFree(r->lj64[di]); cudaFree(r->lj64s[di]); cudaFree(r->lj32s[di]); }
+    }
+    delete r;
+}
+
+// The resident pipeline keeps the start poses as uploaded as the RMSD reference (CompareRMSD :41 takes its CopyLigand before
+// RandomizeLigandPose); the copy is made the first time randomise / shift is about to change d_lig.
+int ensure_reference(ddd_screen *s) {
+    for (auto &d : s->devs) {
+        if (d.d_ref || d.n_atoms_in == 0) continue;
+        const Dev &dev = g_devs[d.di];
+        CUDA_TRY(cudaSetDevice(dev.id));
+        if (int rc = dev_alloc(&d.d_ref, (size_t)d.n_atoms_in * 4)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d.d_ref, d.d_lig, sizeof(double) * 4 * (size_t)d.n_atoms_in, cudaMemcpyDeviceToDevice, dev.stream));
+    }
+    return DDD_OK;
+}
+
+// Replica pick of SimulateEnergyMinimizationParallel (:102-109) + gather of the picked poses + their RMSD against the
+// reference poses, per device, nothing leaves HBM.  Shards are ligand-aligned (plan_shards), so every ligand's replicas
+// are on one device.
+int screen_pick_impl(ddd_screen *s, double temperature, uint64_t seed, uint64_t first_ligand_index) {
+    if (!s->launched) return fail(DDD_EINVAL, "screen has not been run");
+    for (auto &d : s->devs) {
+        const Dev &dev = g_devs[d.di];
+        CUDA_TRY(cudaSetDevice(dev.id));
+        const int64_t n_ll = d.lig1 - d.lig0;
+        if (!d.d_min) { if (int rc = dev_alloc(&d.d_min, (size_t)d.n_atoms_in * 4)) return rc; }
+        if (!d.d_min_e) { if (int rc = dev_alloc(&d.d_min_e, (size_t)n_ll)) return rc; }
+        if (!d.d_picked) { if (int rc = dev_alloc(&d.d_picked, (size_t)n_ll)) return rc; }
+        if (!d.d_min_rmsd) { if (int rc = dev_alloc(&d.d_min_rmsd, (size_t)n_ll)) return rc; }
+        if (n_ll == 0) continue;
+        replica_pick_kernel<<<(unsigned)((n_ll + 127) / 128), 128, 0, dev.stream>>>(d.d_stats, n_ll, d.lig0, d.c0, s->replicas, temperature, seed,
+                                                                                 DDD_STREAM_PARENT_BASE + first_ligand_index, d.d_min_e, d.d_picked);
+        CUDA_TRY(cudaGetLastError());
+        pick_gather_kernel<<<(unsigned)((n_ll + 7) / 8), 256, 0, dev.stream>>>(d.d_offsets, d.d_lig, d.d_ref ? d.d_ref : d.d_lig, d.atom_base, d.d_out,
+                                                                            d.out_base, s->replicas, d.d_picked, n_ll, d.lig0, d.d_min, d.d_min_rmsd);
+        CUDA_TRY(cudaGetLastError());
+    }
+    s->picked = true;
+    return DDD_OK;
+}
+
+int screen_download_pick(ddd_screen *s, double *out_xyzq, double *out_energy, int64_t *out_picked, double *out_rmsd) {
+    for (auto &d : s->devs) {
+        const Dev &dev = g_devs[d.di];
+        CUDA_TRY(cudaSetDevice(dev.id));
+        const int64_t n_ll = d.lig1 - d.lig0;
+        if (out_xyzq && d.n_atoms_in > 0)
+            CUDA_TRY(cudaMemcpyAsync(out_xyzq + d.atom_base * 4, d.d_min, sizeof(double) * 4 * (size_t)d.n_atoms_in, cudaMemcpyDeviceToHost, dev.stream));
+        if (out_energy && n_ll > 0) CUDA_TRY(cudaMemcpyAsync(out_energy + d.lig0, d.d_min_e, sizeof(double) * (size_t)n_ll, cudaMemcpyDeviceToHost, dev.stream));
+        if (out_picked && n_ll > 0) CUDA_TRY(cudaMemcpyAsync(out_picked + d.lig0, d.d_picked, sizeof(int64_t) * (size_t)n_ll, cudaMemcpyDeviceToHost, dev.stream));
+        if (out_rmsd && n_ll > 0) CUDA_TRY(cudaMemcpyAsync(out_rmsd + d.lig0, d.d_min_rmsd, sizeof(double) * (size_t)n_ll, cudaMemcpyDeviceToHost, dev.stream));
+    }
+    for (auto &d : s->devs) {
+        CUDA_TRY(cudaSetDevice(g_devs[d.di].id));
+        CUDA_TRY(cudaStreamSynchronize(g_devs[d.di].stream));
+    }
+    return DDD_OK;
+}
+
+// contiguous ligand blocks for the one-shot batch entry points (energy / RMSD / closest / shift / randomise), one per
+// device in use, balanced by atoms; block k = ligands [b[k], b[k+1])
+std::vector<int64_t> split_ligands(const int64_t *offsets, int64_t n_lig) {
+    const int nd = (int)g_devs.size();
+    std::vector<int64_t> b((size_t)nd + 1, 0);
+    b[(size_t)nd] = n_lig;
+    // small batches stay on the first device: a second device costs more in launch + sync than it saves
+    if (nd <= 1 || n_lig < 64 * nd) { for (int k = 1; k < nd; ++k) b[(size_t)k] = n_lig; return b; }
+    int64_t lig = 0;
+    const double total = (double)(offsets[n_lig] + n_lig);
+    for (int k = 1; k < nd; ++k) {
+        const double target = total * (double)k / (double)nd;
+        while (lig < n_lig && (double)(offsets[lig + 1] + lig + 1) <= target) ++lig;
+        b[(size_t)k] = lig;
+    }
+    return b;
 }
 
 }  // namespace
@@ -506,7 +640,6 @@ extern "C" {
 
 int ddd_init(const int *devices, int n_devices) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
-    ddd_shutdown();
     int count = 0;
     cudaError_t ce = cudaGetDeviceCount(&count);
     if (ce != cudaSuccess || count <= 0) {
@@ -523,21 +656,29 @@ int ddd_init(const int *devices, int n_devices) {
             ids.push_back(devices[i]);
         }
     }
+    // Re-initialising with the device list already in use is a no-op (callers may initialise lazily from many entry
+    // points).  A different list shuts the library down first: handles of the old list turn stale (g_epoch).
+    bool same = ids.size() == g_devs.size();
+    for (size_t i = 0; same && i < ids.size(); ++i) same = g_devs[i].id == ids[i];
+    if (same && !g_devs.empty()) return DDD_OK;
+    ddd_shutdown();                                                       // receptors / screens of the old list become stale handles
     for (int id : ids) {
         Dev d; d.id = id;
         cudaDeviceProp prop;
-        CUDA_TRY(cudaGetDeviceProperties(&prop, id));
-        if (prop.major < 10) { g_devs.clear(); return fail(DDD_ENODEVICE, "device %d (%s, sm_%d%d) is not Blackwell: this library ships sm_100a code only", id, prop.name, prop.major, prop.minor); }
+        auto bail = [&](int rc) { g_devs.push_back(d); const std::string msg = g_err; ddd_shutdown(); g_err = msg; return rc; };   // destroys what was created so far
+        if (cudaGetDeviceProperties(&prop, id) != cudaSuccess) return bail(fail(DDD_ECUDA, "cudaGetDeviceProperties(%d) failed", id));
+        // the library ships sm_100a SASS only; architecture-specific ("a") code runs on exactly that compute capability
+        if (prop.major != 10 || prop.minor != 0)
+            return bail(fail(DDD_ENODEVICE, "device %d (%s, sm_%d%d) is not sm_100 (B200): this library ships sm_100a code only", id, prop.name, prop.major, prop.minor));
         d.sm_count = prop.multiProcessorCount;
         d.max_smem = prop.sharedMemPerBlockOptin;
-        CUDA_TRY(cudaSetDevice(id));
-        CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
         cudaMemPool_t pool = nullptr;
-        CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, id));
         unsigned long long keep = ~0ull;                                  // never hand pool memory back between calls
-        CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        CUDA_TRY(cudaEventCreate(&d.ev0));
-        CUDA_TRY(cudaEventCreate(&d.ev1));
+        if ((ce = cudaSetDevice(id)) != cudaSuccess || (ce = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (ce = cudaDeviceGetDefaultMemPool(&pool, id)) != cudaSuccess ||
+            (ce = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess ||
+            (ce = cudaEventCreate(&d.ev0)) != cudaSuccess || (ce = cudaEventCreate(&d.ev1)) != cudaSuccess)
+            return bail(fail(DDD_ECUDA, "device %d setup failed: %s", id, cudaGetErrorString(ce)));
         g_devs.push_back(d);
     }
     return DDD_OK;
@@ -545,6 +686,8 @@ int ddd_init(const int *devices, int n_devices) {
 
 int ddd_shutdown(void) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!g_devs.empty()) ++g_epoch;
+    purge_cache(true);
     for (auto &d : g_devs) {
         cudaSetDevice(d.id);
         if (d.ev0) cudaEventDestroy(d.ev0);
@@ -562,7 +705,7 @@ int ddd_num_devices(void) {
 
 const char *ddd_last_error(void) { return g_err.c_str(); }
 
-const char *ddd_version(void) { return "ddd_mc 0.2 (sm_100a; SM-persistent chain engine: 16 warps per SM, speculative proposals, per-group pair sums)"; }
+const char *ddd_version(void) { return "ddd_mc 0.3 (sm_100a; SM-persistent chain engine: 16 warps per SM, speculative proposals, per-group pair sums; resident randomise/shift/pick/RMSD/argmin pipeline)"; }
 
 void ddd_params_default(ddd_params *p) {
     if (!p) return;
@@ -601,6 +744,8 @@ int ddd_receptor_create(const double *xyzq, int64_t n_atoms, ddd_receptor **out)
     if (n_atoms < 0 || (n_atoms > 0 && !xyzq)) return fail(DDD_EINVAL, "bad receptor array");
     if (n_atoms > 0x7fffff00ll) return fail(DDD_ELIMIT, "receptor too large");
     ddd_receptor *r = new ddd_receptor();
+    r->epoch = g_epoch;
+    for (auto &d : g_devs) r->dev_ids.push_back(d.id);
     r->n = n_atoms;
     r->n_pad = (n_atoms + kRecPad - 1) / kRecPad * kRecPad;
     double sx = 0, sy = 0, sz = 0;
@@ -694,7 +839,7 @@ int ddd_receptor_create(const double *xyzq, int64_t n_atoms, ddd_receptor **out)
         if (ce == cudaSuccess) ce = cudaMemcpy(r->f64s[di], h64s.data(), sizeof(Atom64) * h64s.size(), cudaMemcpyHostToDevice);
         if (ce != cudaSuccess) rc = fail(DDD_ECUDA, "receptor upload on device %d: %s", g_devs[di].id, cudaGetErrorString(ce));
     }
-    if (rc) { ddd_receptor_destroy(r); return rc; }
+    if (rc) { destroy_receptor(r); return rc; }
     *out = r;
     return DDD_OK;
 }
@@ -702,13 +847,77 @@ int ddd_receptor_create(const double *xyzq, int64_t n_atoms, ddd_receptor **out)
 int ddd_receptor_destroy(ddd_receptor *r) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!r) return DDD_OK;
-    for (size_t di = 0; di < r->f32.size() && di < g_devs.size(); ++di) {
-        cudaSetDevice(g_devs[di].id);
-        cudaFree(r->f32[di]); cudaFree(r->f64[di]);
-        if (di < r->f32s.size()) { cudaFree(r->f32s[di]); cudaFree(r->ubox[di]); cudaFree(r->f64s[di]); cudaFree(r->gbox[di]);
-                                    cudaFree(r->lj64[di]); cudaFree(r->lj64s[di]); cudaFree(r->lj32s[di]); }
+    if (r->cached) return fail(DDD_EINVAL, "this receptor belongs to the cache: use ddd_receptor_release");
+    destroy_receptor(r);
+    return DDD_OK;
+}
+
+// Receptor cache for the scalar entry points of the host mirrors (CalculateEnergy, FindClosestAtomDistance, Shift...,
+// SimulateEnergyMinimizationParallel called per ligand by RShinyAppMain, main.go:42-48): the same protein arrives on every
+// call, and building a receptor costs a host sort + 9 allocations + synchronous uploads.  Entries are keyed by the content
+// (length + 64-bit FNV-1a of the bytes, compared in full on a hit), reference-counted, and evicted least-recently-used.
+extern "C++" {
+namespace {
+constexpr size_t kReceptorCacheEntries = 8;
+struct CacheEntry { ddd_receptor *r; std::vector<double> copy; uint64_t last_use; };
+std::vector<CacheEntry> g_cache;
+uint64_t g_cache_clock = 0;
+uint64_t fnv1a(const void *p, size_t n) {
+    const unsigned char *b = (const unsigned char *)p;
+    uint64_t h = 1469598103934665603ull;
+    // 8 bytes at a time: this runs on every scalar call
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) { uint64_t w; std::memcpy(&w, b + i, 8); h = (h ^ w) * 1099511628211ull; }
+    for (; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull;
+    return h;
+}
+void purge_cache(bool everything) {
+    for (size_t i = 0; i < g_cache.size();) {
+        ddd_receptor *r = g_cache[i].r;
+        if (everything || r->epoch != g_epoch) {
+            if (r->refs <= 0) destroy_receptor(r);
+            else r->cached = false;                     // still referenced: the last ddd_receptor_release frees it
+            g_cache.erase(g_cache.begin() + (long)i);
+        } else ++i;
     }
-    delete r;
+}
+}  // namespace
+}  // extern "C++"
+
+int ddd_receptor_acquire(const double *xyzq, int64_t n_atoms, ddd_receptor **out) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    REQUIRE_INIT();
+    if (!out) return fail(DDD_EINVAL, "out is NULL");
+    if (n_atoms < 0 || (n_atoms > 0 && !xyzq)) return fail(DDD_EINVAL, "bad receptor array");
+    purge_cache(false);
+    const size_t bytes = (size_t)n_atoms * 32;
+    const uint64_t h = fnv1a(xyzq, bytes);
+    for (auto &e : g_cache) {
+        if (e.r->n == n_atoms && e.r->hash == h && (bytes == 0 || std::memcmp(e.copy.data(), xyzq, bytes) == 0)) {
+            e.last_use = ++g_cache_clock; e.r->refs += 1; *out = e.r;
+            return DDD_OK;
+        }
+    }
+    ddd_receptor *r = nullptr;
+    if (int rc = ddd_receptor_create(xyzq, n_atoms, &r)) return rc;
+    r->hash = h; r->cached = true; r->refs = 1;
+    if (g_cache.size() >= kReceptorCacheEntries) {      // evict the least recently used entry nobody holds
+        size_t victim = g_cache.size();
+        for (size_t i = 0; i < g_cache.size(); ++i)
+            if (g_cache[i].r->refs <= 0 && (victim == g_cache.size() || g_cache[i].last_use < g_cache[victim].last_use)) victim = i;
+        if (victim < g_cache.size()) { destroy_receptor(g_cache[victim].r); g_cache.erase(g_cache.begin() + (long)victim); }
+    }
+    CacheEntry e; e.r = r; e.copy.assign(xyzq, xyzq + n_atoms * 4); e.last_use = ++g_cache_clock;
+    g_cache.push_back(std::move(e));
+    *out = r;
+    return DDD_OK;
+}
+
+int ddd_receptor_release(ddd_receptor *r) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!r) return DDD_OK;
+    r->refs -= 1;
+    if (!r->cached && r->refs <= 0) destroy_receptor(r);   // dropped from the cache (shutdown) while in use
     return DDD_OK;
 }
 
@@ -717,7 +926,7 @@ int64_t ddd_receptor_num_atoms(const ddd_receptor *r) { return r ? r->n : -1; }
 int ddd_receptor_set_lj(ddd_receptor *r, const double *sigma, const double *epsilon) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     REQUIRE_INIT();
-    if (!r) return fail(DDD_EINVAL, "receptor is NULL");
+    if (int rc0 = check_receptor(r)) return rc0;
     if ((sigma == nullptr) != (epsilon == nullptr)) return fail(DDD_EINVAL, "sigma and epsilon must be given together");
     if (!sigma) { r->has_lj = false; return DDD_OK; }
     const int64_t n = r->n;
@@ -748,34 +957,62 @@ int ddd_receptor_set_lj(ddd_receptor *r, const double *sigma, const double *epsi
 }
 
 // ------------------------------------------------------------------ CalculateEnergy batch
+// One-shot batch entry points: the ligand list is cut into one contiguous block per device in use (split_ligands); every
+// block is uploaded, processed and downloaded asynchronously on its device's stream, then all streams are joined.
+extern "C++" {
+namespace {
+struct Scratch {                                 // per-call device buffers, freed (stream-ordered) on the device they live on
+    std::vector<std::pair<int, void *>> bufs;
+    template <typename T> int get(int dev_id, T **p, size_t count) {
+        if (int rc = dev_alloc(p, count)) return rc;
+        bufs.emplace_back(dev_id, (void *)*p);
+        return DDD_OK;
+    }
+    ~Scratch() { for (auto &b : bufs) { cudaSetDevice(b.first); dev_free(b.second); } }
+};
+// the downloads run after EVERY device has its work queued (a D2H copy into pageable memory blocks the host until the
+// device gets there), then all streams are joined
+int join_devices(std::vector<std::function<int()>> &downloads) {
+    for (auto &f : downloads) if (int rc = f()) return rc;
+    for (auto &d : g_devs) { CUDA_TRY(cudaSetDevice(d.id)); CUDA_TRY(cudaStreamSynchronize(d.stream)); }
+    return DDD_OK;
+}
+}  // namespace
+}  // extern "C++"
+
 int ddd_energy_batch(const ddd_receptor *r, const int64_t *offsets, const double *lig_xyzq, int64_t n_lig,
                      const ddd_params *p, double *out_energy, double *out_abs_sum) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     REQUIRE_INIT();
-    if (!r) return fail(DDD_EINVAL, "receptor is NULL");
+    if (int rc0 = check_receptor(r)) return rc0;
     if (int rc = check_params(p)) return rc;
     if (p->lj_scale != 0.0) return fail(DDD_EINVAL, "params.lj_scale: ligand LJ parameters travel with a screen (run it with 0 steps for energies)");
     int64_t max_nl = 0;
     if (int rc = check_csr(offsets, n_lig, lig_xyzq, &max_nl)) return rc;
     if (n_lig == 0) return DDD_OK;
     if (!out_energy) return fail(DDD_EINVAL, "out_energy is NULL");
-    const Dev &dev = g_devs[0];
-    CUDA_TRY(cudaSetDevice(dev.id));
-    long long *d_off = nullptr; double *d_lig = nullptr, *d_e = nullptr, *d_abs = nullptr;
-    int rc = DDD_OK;
-    auto cleanup = [&]() { dev_free(d_off); dev_free(d_lig); dev_free(d_e); dev_free(d_abs); };
-    if ((rc = dev_alloc(&d_off, (size_t)n_lig + 1)) || (rc = dev_alloc(&d_lig, (size_t)offsets[n_lig] * 4)) ||
-        (rc = dev_alloc(&d_e, (size_t)n_lig)) || (out_abs_sum && (rc = dev_alloc(&d_abs, (size_t)n_lig)))) { cleanup(); return rc; }
-    auto run = [&]() -> int {
-        CUDA_TRY(cudaMemcpyAsync(d_off, offsets, sizeof(int64_t) * ((size_t)n_lig + 1), cudaMemcpyHostToDevice, dev.stream));
-        if (offsets[n_lig] > 0)
-            CUDA_TRY(cudaMemcpyAsync(d_lig, lig_xyzq, sizeof(double) * 4 * (size_t)offsets[n_lig], cudaMemcpyHostToDevice, dev.stream));
+    Scratch sc;
+    std::vector<std::function<int()>> later;
+    const std::vector<int64_t> blk = split_ligands(offsets, n_lig);
+    for (size_t di = 0; di < g_devs.size(); ++di) {
+        const int64_t l0 = blk[di], l1 = blk[di + 1], nl_blk = l1 - l0;
+        if (nl_blk <= 0) continue;
+        const Dev &dev = g_devs[di];
+        CUDA_TRY(cudaSetDevice(dev.id));
+        const int64_t a0 = offsets[l0], na = offsets[l1] - a0;
+        long long *d_off = nullptr; double *d_lig = nullptr, *d_e = nullptr, *d_abs = nullptr;
+        if (int rc = sc.get(dev.id, &d_off, (size_t)nl_blk + 1)) return rc;
+        if (int rc = sc.get(dev.id, &d_lig, (size_t)na * 4)) return rc;
+        if (int rc = sc.get(dev.id, &d_e, (size_t)nl_blk)) return rc;
+        if (out_abs_sum) { if (int rc = sc.get(dev.id, &d_abs, (size_t)nl_blk)) return rc; }
+        CUDA_TRY(cudaMemcpyAsync(d_off, offsets + l0, sizeof(int64_t) * ((size_t)nl_blk + 1), cudaMemcpyHostToDevice, dev.stream));
+        if (na > 0) CUDA_TRY(cudaMemcpyAsync(d_lig, lig_xyzq + a0 * 4, sizeof(double) * 4 * (size_t)na, cudaMemcpyHostToDevice, dev.stream));
         EnergyArgs a;
-        a.rec = r->view(0); a.prm = make_dev_params(*p, 0, 1.0);
-        a.offsets = d_off; a.lig_xyzq = d_lig; a.out_energy = d_e; a.out_abs = d_abs; a.nl_cap = even_cap(max_nl);
+        a.rec = r->view(di); a.prm = make_dev_params(*p, 0, 1.0);
+        a.offsets = d_off; a.atom_base = a0; a.lig_xyzq = d_lig; a.out_energy = d_e; a.out_abs = d_abs; a.nl_cap = even_cap(max_nl);
         const size_t smem = chain_smem_bytes(a.nl_cap, kThreads);
         const bool precise = p->precision == DDD_PRECISION_F64, with_abs = out_abs_sum != nullptr;
-        const unsigned grid = (unsigned)n_lig;
+        const unsigned grid = (unsigned)nl_blk;
 #define LAUNCH_E(PR, AB)                                                                   \
         do { if (int rc2 = set_smem(energy_batch_kernel<PR, AB>, smem)) return rc2;        \
              energy_batch_kernel<PR, AB><<<grid, kThreads, smem, dev.stream>>>(a); } while (0)
@@ -785,14 +1022,14 @@ int ddd_energy_batch(const ddd_receptor *r, const int64_t *offsets, const double
         else LAUNCH_E(false, false);
 #undef LAUNCH_E
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(out_energy, d_e, sizeof(double) * (size_t)n_lig, cudaMemcpyDeviceToHost, dev.stream));
-        if (with_abs) CUDA_TRY(cudaMemcpyAsync(out_abs_sum, d_abs, sizeof(double) * (size_t)n_lig, cudaMemcpyDeviceToHost, dev.stream));
-        CUDA_TRY(cudaStreamSynchronize(dev.stream));
-        return DDD_OK;
-    };
-    rc = run();
-    cleanup();
-    return rc;
+        later.push_back([=]() -> int {
+            CUDA_TRY(cudaSetDevice(dev.id));
+            CUDA_TRY(cudaMemcpyAsync(out_energy + l0, d_e, sizeof(double) * (size_t)nl_blk, cudaMemcpyDeviceToHost, dev.stream));
+            if (with_abs) CUDA_TRY(cudaMemcpyAsync(out_abs_sum + l0, d_abs, sizeof(double) * (size_t)nl_blk, cudaMemcpyDeviceToHost, dev.stream));
+            return DDD_OK;
+        });
+    }
+    return join_devices(later);
 }
 
 // ------------------------------------------------------------------ chains
@@ -810,6 +1047,9 @@ int ddd_run_chains(const ddd_receptor *r, const int64_t *offsets, const double *
     int rc = screen_run_impl(s, steps_per_chain, rotate, temperature, p, seed, recorded, recorded_offsets, out_accept_trace != nullptr);
     if (!rc) rc = screen_download_impl(s, out_xyzq, out_stats, out_accept_trace);
     screen_destroy_impl(s);
+    g_status_bits = 0; g_status_chains = 0;
+    if (!rc && out_stats)
+        for (int64_t c = 0; c < n_lig * replicas; ++c) { g_status_bits |= out_stats[c].status; g_status_chains += (out_stats[c].status & DDD_STATUS_RETRY_LIMIT) ? 1 : 0; }
     return rc;
 }
 
@@ -819,6 +1059,7 @@ int ddd_minimize_batch(const ddd_receptor *r, const int64_t *offsets, const doub
                        double *out_xyzq, double *out_energy, ddd_chain_stats *out_chain_stats, int64_t *out_picked) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     REQUIRE_INIT();
+    g_status_bits = 0; g_status_chains = 0;
     if (num_procs <= 0) return fail(DDD_EINVAL, "num_procs must be >= 1 (the reference divides iterations by it, metropolis.go:97)");
     if (iterations < 0) return fail(DDD_EINVAL, "negative iteration count");
     if (int rc = check_csr(offsets, n_lig, lig_xyzq, nullptr)) return rc;
@@ -827,7 +1068,6 @@ int ddd_minimize_batch(const ddd_receptor *r, const int64_t *offsets, const doub
     if (!out_energy) return fail(DDD_EINVAL, "out_energy is NULL");
     const int64_t width = iterations / num_procs;                                  // :97
     const int64_t n_chains = n_lig * num_procs;
-    std::vector<double> chain_pose((size_t)offsets[n_lig] * (size_t)num_procs * 4);
     std::vector<ddd_chain_stats> stats((size_t)n_chains);
     // chain (ligand i, replica r) draws from stream (first_ligand_index + i) * num_procs + r, so a
     // ligand list split over several calls (or ranks) sees the same streams as one call
@@ -839,8 +1079,12 @@ int ddd_minimize_batch(const ddd_receptor *r, const int64_t *offsets, const doub
     if (int rc = screen_create_impl(r, offsets, lig_xyzq, n_lig, num_procs, first_ligand_index * (uint64_t)num_procs, &s)) return rc;
     const double t1 = now();
     int rc = screen_run_impl(s, width, rotate, temperature, p, seed, nullptr, nullptr, false);
+    // the replica pick (:102-109) and the gather of the picked poses run on the device behind the chains: only the
+    // per-ligand results (and the 72-byte chain records) come back
+    if (!rc) rc = screen_pick_impl(s, temperature, seed, first_ligand_index);
     const double t2 = now();
-    if (!rc) rc = screen_download_impl(s, chain_pose.data(), stats.data(), nullptr);
+    if (!rc) rc = screen_download_impl(s, nullptr, stats.data(), nullptr);
+    if (!rc) rc = screen_download_pick(s, out_xyzq, out_energy, out_picked, nullptr);
     const double t3 = now();
     const double kms = ddd_screen_last_kernel_ms(s);
     screen_destroy_impl(s);
@@ -848,28 +1092,17 @@ int ddd_minimize_batch(const ddd_receptor *r, const int64_t *offsets, const doub
     if (dbg) fprintf(stderr, "[ddd_minimize_batch] create %.2f ms, launch %.2f ms, sync+download %.2f ms (kernel %.2f ms), destroy %.2f ms\n",
                      t1 - t0, t2 - t1, t3 - t2, kms, t4 - t3);
     if (rc) return rc;
-    for (int64_t i = 0; i < n_lig; ++i) {
-        const int64_t nl = offsets[i + 1] - offsets[i];
-        double cur_e = stats[(size_t)(i * num_procs)].start_energy;                // :96
-        int64_t picked = -1;
-        uint64_t pos = 0;
-        const uint64_t parent = DDD_STREAM_PARENT_BASE + first_ligand_index + (uint64_t)i;
-        for (int rp = 0; rp < num_procs; ++rp) {                                    // :102-109, replica-index order
-            const double new_e = stats[(size_t)(i * num_procs + rp)].final_energy; // :104
-            if (accept_move_host(cur_e, new_e, temperature, seed, parent, pos)) { cur_e = new_e; picked = rp; }
-        }
-        double *dst = out_xyzq + offsets[i] * 4;
-        if (picked >= 0)
-            std::memcpy(dst, chain_pose.data() + ((size_t)num_procs * (size_t)offsets[i] + (size_t)picked * (size_t)nl) * 4, sizeof(double) * 4 * (size_t)nl);
-        else std::memcpy(dst, lig_xyzq + offsets[i] * 4, sizeof(double) * 4 * (size_t)nl);
-        out_energy[i] = cur_e;                                                      // :61 CalculateEnergy(final)
-        if (out_picked) out_picked[i] = picked;
-    }
+    for (auto &cs : stats) { g_status_bits |= cs.status; g_status_chains += (cs.status & DDD_STATUS_RETRY_LIMIT) ? 1 : 0; }
     if (out_chain_stats) std::memcpy(out_chain_stats, stats.data(), sizeof(ddd_chain_stats) * stats.size());
     return DDD_OK;
 }
 
-// ------------------------------------------------------------------ RMSD / closest / shift / randomize (device 0)
+int64_t ddd_last_chain_status(int64_t *out_retry_limited_chains) {
+    if (out_retry_limited_chains) *out_retry_limited_chains = g_status_chains;
+    return g_status_bits;
+}
+
+// ------------------------------------------------------------------ RMSD / closest / shift / randomize (one block per device)
 int ddd_rmsd_batch(const int64_t *offsets, const double *sim, const double *ref, int32_t atom_stride,
                    int64_t n_pairs, double *out_rmsd) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
@@ -880,66 +1113,76 @@ int ddd_rmsd_batch(const int64_t *offsets, const double *sim, const double *ref,
     if (!offsets || !out_rmsd) return fail(DDD_EINVAL, "offsets/out is NULL");
     if (offsets[0] != 0) return fail(DDD_EINVAL, "offsets[0] must be 0");
     for (int64_t i = 0; i < n_pairs; ++i) if (offsets[i + 1] < offsets[i]) return fail(DDD_EINVAL, "offsets not monotone");
-    const int64_t n_atoms = offsets[n_pairs];
-    if (n_atoms > 0 && (!sim || !ref)) return fail(DDD_EINVAL, "sim/ref is NULL");
-    const Dev &dev = g_devs[0];
-    CUDA_TRY(cudaSetDevice(dev.id));
-    long long *d_off = nullptr; double *d_s = nullptr, *d_r = nullptr, *d_o = nullptr;
-    auto cleanup = [&]() { dev_free(d_off); dev_free(d_s); dev_free(d_r); dev_free(d_o); };
-    int rc;
-    if ((rc = dev_alloc(&d_off, (size_t)n_pairs + 1)) || (rc = dev_alloc(&d_s, (size_t)n_atoms * atom_stride)) ||
-        (rc = dev_alloc(&d_r, (size_t)n_atoms * atom_stride)) || (rc = dev_alloc(&d_o, (size_t)n_pairs))) { cleanup(); return rc; }
-    auto run = [&]() -> int {
-        CUDA_TRY(cudaMemcpyAsync(d_off, offsets, sizeof(int64_t) * ((size_t)n_pairs + 1), cudaMemcpyHostToDevice, dev.stream));
-        if (n_atoms > 0) {
-            CUDA_TRY(cudaMemcpyAsync(d_s, sim, sizeof(double) * (size_t)(n_atoms * atom_stride), cudaMemcpyHostToDevice, dev.stream));
-            CUDA_TRY(cudaMemcpyAsync(d_r, ref, sizeof(double) * (size_t)(n_atoms * atom_stride), cudaMemcpyHostToDevice, dev.stream));
+    if (offsets[n_pairs] > 0 && (!sim || !ref)) return fail(DDD_EINVAL, "sim/ref is NULL");
+    Scratch sc;
+    std::vector<std::function<int()>> later;
+    const std::vector<int64_t> blk = split_ligands(offsets, n_pairs);
+    for (size_t di = 0; di < g_devs.size(); ++di) {
+        const int64_t l0 = blk[di], l1 = blk[di + 1], np_blk = l1 - l0;
+        if (np_blk <= 0) continue;
+        const Dev &dev = g_devs[di];
+        CUDA_TRY(cudaSetDevice(dev.id));
+        const int64_t a0 = offsets[l0], na = offsets[l1] - a0;
+        long long *d_off = nullptr; double *d_s = nullptr, *d_r = nullptr, *d_o = nullptr;
+        if (int rc = sc.get(dev.id, &d_off, (size_t)np_blk + 1)) return rc;
+        if (int rc = sc.get(dev.id, &d_s, (size_t)na * atom_stride)) return rc;
+        if (int rc = sc.get(dev.id, &d_r, (size_t)na * atom_stride)) return rc;
+        if (int rc = sc.get(dev.id, &d_o, (size_t)np_blk)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d_off, offsets + l0, sizeof(int64_t) * ((size_t)np_blk + 1), cudaMemcpyHostToDevice, dev.stream));
+        if (na > 0) {
+            CUDA_TRY(cudaMemcpyAsync(d_s, sim + a0 * atom_stride, sizeof(double) * (size_t)(na * atom_stride), cudaMemcpyHostToDevice, dev.stream));
+            CUDA_TRY(cudaMemcpyAsync(d_r, ref + a0 * atom_stride, sizeof(double) * (size_t)(na * atom_stride), cudaMemcpyHostToDevice, dev.stream));
         }
-        const unsigned grid = (unsigned)((n_pairs + 7) / 8);
-        rmsd_batch_kernel<<<grid, 256, 0, dev.stream>>>(d_off, d_s, d_r, atom_stride, n_pairs, d_o);
+        rmsd_batch_kernel<<<(unsigned)((np_blk + 7) / 8), 256, 0, dev.stream>>>(d_off, a0, d_s, d_r, atom_stride, np_blk, d_o);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(out_rmsd, d_o, sizeof(double) * (size_t)n_pairs, cudaMemcpyDeviceToHost, dev.stream));
-        CUDA_TRY(cudaStreamSynchronize(dev.stream));
-        return DDD_OK;
-    };
-    rc = run();
-    cleanup();
-    return rc;
+        later.push_back([=]() -> int {
+            CUDA_TRY(cudaSetDevice(dev.id));
+            CUDA_TRY(cudaMemcpyAsync(out_rmsd + l0, d_o, sizeof(double) * (size_t)np_blk, cudaMemcpyDeviceToHost, dev.stream));
+            return DDD_OK;
+        });
+    }
+    return join_devices(later);
 }
 
 static int closest_impl(const ddd_receptor *r, const int64_t *offsets, double *lig_xyzq, bool copy_back,
                         int64_t n_lig, double *out_distance, int64_t *out_lig_atom, int64_t *out_prot_atom,
                         double threshold, int do_shift) {
     REQUIRE_INIT();
-    if (!r) return fail(DDD_EINVAL, "receptor is NULL");
+    if (int rc0 = check_receptor(r)) return rc0;
     if (int rc = check_csr(offsets, n_lig, lig_xyzq, nullptr)) return rc;
     if (n_lig == 0) return DDD_OK;
-    const Dev &dev = g_devs[0];
-    CUDA_TRY(cudaSetDevice(dev.id));
-    const int64_t n_atoms = offsets[n_lig];
-    long long *d_off = nullptr, *d_li = nullptr, *d_pj = nullptr; double *d_lig = nullptr, *d_d = nullptr;
-    auto cleanup = [&]() { dev_free(d_off); dev_free(d_li); dev_free(d_pj); dev_free(d_lig); dev_free(d_d); };
-    int rc;
-    if ((rc = dev_alloc(&d_off, (size_t)n_lig + 1)) || (rc = dev_alloc(&d_lig, (size_t)n_atoms * 4)) ||
-        (rc = dev_alloc(&d_d, (size_t)n_lig)) || (rc = dev_alloc(&d_li, (size_t)n_lig)) || (rc = dev_alloc(&d_pj, (size_t)n_lig))) { cleanup(); return rc; }
-    auto run = [&]() -> int {
-        CUDA_TRY(cudaMemcpyAsync(d_off, offsets, sizeof(int64_t) * ((size_t)n_lig + 1), cudaMemcpyHostToDevice, dev.stream));
-        if (n_atoms > 0) CUDA_TRY(cudaMemcpyAsync(d_lig, lig_xyzq, sizeof(double) * 4 * (size_t)n_atoms, cudaMemcpyHostToDevice, dev.stream));
+    Scratch sc;
+    std::vector<std::function<int()>> later;
+    const std::vector<int64_t> blk = split_ligands(offsets, n_lig);
+    for (size_t di = 0; di < g_devs.size(); ++di) {
+        const int64_t l0 = blk[di], l1 = blk[di + 1], nl_blk = l1 - l0;
+        if (nl_blk <= 0) continue;
+        const Dev &dev = g_devs[di];
+        CUDA_TRY(cudaSetDevice(dev.id));
+        const int64_t a0 = offsets[l0], na = offsets[l1] - a0;
+        long long *d_off = nullptr, *d_li = nullptr, *d_pj = nullptr; double *d_lig = nullptr, *d_d = nullptr;
+        if (int rc = sc.get(dev.id, &d_off, (size_t)nl_blk + 1)) return rc;
+        if (int rc = sc.get(dev.id, &d_lig, (size_t)na * 4)) return rc;
+        if (int rc = sc.get(dev.id, &d_d, (size_t)nl_blk)) return rc;
+        if (int rc = sc.get(dev.id, &d_li, (size_t)nl_blk)) return rc;
+        if (int rc = sc.get(dev.id, &d_pj, (size_t)nl_blk)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d_off, offsets + l0, sizeof(int64_t) * ((size_t)nl_blk + 1), cudaMemcpyHostToDevice, dev.stream));
+        if (na > 0) CUDA_TRY(cudaMemcpyAsync(d_lig, lig_xyzq + a0 * 4, sizeof(double) * 4 * (size_t)na, cudaMemcpyHostToDevice, dev.stream));
         ClosestArgs a;
-        a.rec = r->view(0); a.offsets = d_off; a.lig_xyzq = d_lig; a.out_dist = d_d; a.out_lig_atom = d_li; a.out_prot_atom = d_pj;
+        a.rec = r->view(di); a.offsets = d_off; a.atom_base = a0; a.lig_xyzq = d_lig; a.out_dist = d_d; a.out_lig_atom = d_li; a.out_prot_atom = d_pj;
         a.threshold = threshold; a.do_shift = do_shift;
-        closest_atom_kernel<<<(unsigned)n_lig, kThreads, 0, dev.stream>>>(a);
+        closest_atom_kernel<<<(unsigned)nl_blk, kThreads, 0, dev.stream>>>(a);
         CUDA_TRY(cudaGetLastError());
-        if (out_distance) CUDA_TRY(cudaMemcpyAsync(out_distance, d_d, sizeof(double) * (size_t)n_lig, cudaMemcpyDeviceToHost, dev.stream));
-        if (out_lig_atom) CUDA_TRY(cudaMemcpyAsync(out_lig_atom, d_li, sizeof(int64_t) * (size_t)n_lig, cudaMemcpyDeviceToHost, dev.stream));
-        if (out_prot_atom) CUDA_TRY(cudaMemcpyAsync(out_prot_atom, d_pj, sizeof(int64_t) * (size_t)n_lig, cudaMemcpyDeviceToHost, dev.stream));
-        if (copy_back && n_atoms > 0) CUDA_TRY(cudaMemcpyAsync(lig_xyzq, d_lig, sizeof(double) * 4 * (size_t)n_atoms, cudaMemcpyDeviceToHost, dev.stream));
-        CUDA_TRY(cudaStreamSynchronize(dev.stream));
-        return DDD_OK;
-    };
-    rc = run();
-    cleanup();
-    return rc;
+        later.push_back([=]() -> int {
+            CUDA_TRY(cudaSetDevice(dev.id));
+            if (out_distance) CUDA_TRY(cudaMemcpyAsync(out_distance + l0, d_d, sizeof(double) * (size_t)nl_blk, cudaMemcpyDeviceToHost, dev.stream));
+            if (out_lig_atom) CUDA_TRY(cudaMemcpyAsync(out_lig_atom + l0, d_li, sizeof(int64_t) * (size_t)nl_blk, cudaMemcpyDeviceToHost, dev.stream));
+            if (out_prot_atom) CUDA_TRY(cudaMemcpyAsync(out_prot_atom + l0, d_pj, sizeof(int64_t) * (size_t)nl_blk, cudaMemcpyDeviceToHost, dev.stream));
+            if (copy_back && na > 0) CUDA_TRY(cudaMemcpyAsync(lig_xyzq + a0 * 4, d_lig, sizeof(double) * 4 * (size_t)na, cudaMemcpyDeviceToHost, dev.stream));
+            return DDD_OK;
+        });
+    }
+    return join_devices(later);
 }
 
 int ddd_closest_atom_batch(const ddd_receptor *r, const int64_t *offsets, const double *lig_xyzq, int64_t n_lig,
@@ -958,25 +1201,29 @@ int ddd_randomize_pose_batch(const int64_t *offsets, double *lig_xyzq_inout, int
     REQUIRE_INIT();
     if (int rc = check_csr(offsets, n_lig, lig_xyzq_inout, nullptr)) return rc;
     if (n_lig == 0 || offsets[n_lig] == 0) return DDD_OK;
-    const Dev &dev = g_devs[0];
-    CUDA_TRY(cudaSetDevice(dev.id));
-    const int64_t n_atoms = offsets[n_lig];
-    long long *d_off = nullptr; double *d_lig = nullptr;
-    auto cleanup = [&]() { dev_free(d_off); dev_free(d_lig); };
-    int rc;
-    if ((rc = dev_alloc(&d_off, (size_t)n_lig + 1)) || (rc = dev_alloc(&d_lig, (size_t)n_atoms * 4))) { cleanup(); return rc; }
-    auto run = [&]() -> int {
-        CUDA_TRY(cudaMemcpyAsync(d_off, offsets, sizeof(int64_t) * ((size_t)n_lig + 1), cudaMemcpyHostToDevice, dev.stream));
-        CUDA_TRY(cudaMemcpyAsync(d_lig, lig_xyzq_inout, sizeof(double) * 4 * (size_t)n_atoms, cudaMemcpyHostToDevice, dev.stream));
-        randomize_pose_kernel<<<(unsigned)n_lig, kThreads, 0, dev.stream>>>(d_off, d_lig, seed, first_ligand_index);
+    Scratch sc;
+    std::vector<std::function<int()>> later;
+    const std::vector<int64_t> blk = split_ligands(offsets, n_lig);
+    for (size_t di = 0; di < g_devs.size(); ++di) {
+        const int64_t l0 = blk[di], l1 = blk[di + 1], nl_blk = l1 - l0;
+        if (nl_blk <= 0) continue;
+        const Dev &dev = g_devs[di];
+        CUDA_TRY(cudaSetDevice(dev.id));
+        const int64_t a0 = offsets[l0], na = offsets[l1] - a0;
+        long long *d_off = nullptr; double *d_lig = nullptr;
+        if (int rc = sc.get(dev.id, &d_off, (size_t)nl_blk + 1)) return rc;
+        if (int rc = sc.get(dev.id, &d_lig, (size_t)na * 4)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(d_off, offsets + l0, sizeof(int64_t) * ((size_t)nl_blk + 1), cudaMemcpyHostToDevice, dev.stream));
+        if (na > 0) CUDA_TRY(cudaMemcpyAsync(d_lig, lig_xyzq_inout + a0 * 4, sizeof(double) * 4 * (size_t)na, cudaMemcpyHostToDevice, dev.stream));
+        randomize_pose_kernel<<<(unsigned)nl_blk, kThreads, 0, dev.stream>>>(d_off, d_lig, a0, seed, first_ligand_index + (uint64_t)l0);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(lig_xyzq_inout, d_lig, sizeof(double) * 4 * (size_t)n_atoms, cudaMemcpyDeviceToHost, dev.stream));
-        CUDA_TRY(cudaStreamSynchronize(dev.stream));
-        return DDD_OK;
-    };
-    rc = run();
-    cleanup();
-    return rc;
+        later.push_back([=]() -> int {
+            CUDA_TRY(cudaSetDevice(dev.id));
+            if (na > 0) CUDA_TRY(cudaMemcpyAsync(lig_xyzq_inout + a0 * 4, d_lig, sizeof(double) * 4 * (size_t)na, cudaMemcpyDeviceToHost, dev.stream));
+            return DDD_OK;
+        });
+    }
+    return join_devices(later);
 }
 
 // ------------------------------------------------------------------ device-resident screen
@@ -995,7 +1242,7 @@ int ddd_screen_run(ddd_screen *s, int64_t steps_per_chain, int32_t rotate, doubl
 
 int ddd_screen_set_chain_threads(ddd_screen *s, int32_t threads) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
-    if (!s) return fail(DDD_EINVAL, "screen is NULL");
+    if (int rc0 = check_screen(s)) return rc0;
     if (threads != 0 && threads != 32 && threads != 64 && threads != 128 && threads != 256)
         return fail(DDD_EINVAL, "chain CTA width must be 0, 32, 64, 128 or 256 (got %d)", threads);
     s->threads_override = threads;
@@ -1009,7 +1256,7 @@ int32_t ddd_screen_chain_threads(const ddd_screen *s) {
 
 int ddd_screen_set_chain_slots(ddd_screen *s, int32_t slots) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
-    if (!s) return fail(DDD_EINVAL, "screen is NULL");
+    if (int rc0 = check_screen(s)) return rc0;
     if (slots < 0 || slots > kSmMaxSlots) return fail(DDD_EINVAL, "chains per SM must be 0..%d (got %d)", kSmMaxSlots, slots);
     s->slots_override = slots;
     if (slots > 0) s->threads_override = 0;
@@ -1045,7 +1292,7 @@ int ddd_screen_download(ddd_screen *s, double *out_xyzq, ddd_chain_stats *out_st
 int ddd_screen_rmsd(ddd_screen *s, double *out_rmsd, double *out_kernel_ms) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     REQUIRE_INIT();
-    if (!s) return fail(DDD_EINVAL, "screen is NULL");
+    if (int rc0 = check_screen(s)) return rc0;
     if (!s->launched) return fail(DDD_EINVAL, "screen has not been run");
     if (!out_rmsd && s->n_chains > 0) return fail(DDD_EINVAL, "out_rmsd is NULL");
     for (auto &d : s->devs) {
@@ -1072,12 +1319,152 @@ int ddd_screen_rmsd(ddd_screen *s, double *out_rmsd, double *out_kernel_ms) {
     return DDD_OK;
 }
 
+// The RMSD values the chain kernel's own epilogue left behind (SM-persistent engine): same bits as ddd_screen_rmsd, no extra pass.
+int ddd_screen_fused_rmsd(ddd_screen *s, double *out_rmsd) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    REQUIRE_INIT();
+    if (int rc0 = check_screen(s)) return rc0;
+    if (!s->launched) return fail(DDD_EINVAL, "screen has not been run");
+    if (!out_rmsd && s->n_chains > 0) return fail(DDD_EINVAL, "out_rmsd is NULL");
+    for (auto &d : s->devs) {
+        if (!d.fused_rmsd) return fail(DDD_EINVAL, "the last run used the one-CTA-per-chain engine: call ddd_screen_rmsd");
+        CUDA_TRY(cudaSetDevice(g_devs[d.di].id));
+        CUDA_TRY(cudaMemcpyAsync(out_rmsd + d.c0, d.d_rmsd, sizeof(double) * (size_t)(d.c1 - d.c0), cudaMemcpyDeviceToHost, g_devs[d.di].stream));
+    }
+    for (auto &d : s->devs) { CUDA_TRY(cudaSetDevice(g_devs[d.di].id)); CUDA_TRY(cudaStreamSynchronize(g_devs[d.di].stream)); }
+    return DDD_OK;
+}
+
+// ------------------------------------------------------------------ resident pipeline: randomise -> shift -> chains -> pick -> RMSD -> argmin
+// RandomizeLigandPose (validateResults.go:70-79) on the resident start poses, in place.  Ligand i draws from stream
+// (seed, DDD_STREAM_RANDOMIZE_BASE + first_ligand_index + i), like ddd_randomize_pose_batch.
+int ddd_screen_randomize(ddd_screen *s, uint64_t seed, uint64_t first_ligand_index) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    REQUIRE_INIT();
+    if (int rc0 = check_screen(s)) return rc0;
+    if (int rc = ensure_reference(s)) return rc;
+    for (auto &d : s->devs) {
+        const int64_t n_ll = d.lig1 - d.lig0;
+        if (n_ll <= 0 || d.n_atoms_in == 0) continue;
+        const Dev &dev = g_devs[d.di];
+        CUDA_TRY(cudaSetDevice(dev.id));
+        randomize_pose_kernel<<<(unsigned)n_ll, kThreads, 0, dev.stream>>>(d.d_offsets + d.lig0, d.d_lig, d.atom_base, seed, first_ligand_index + (uint64_t)d.lig0);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return DDD_OK;
+}
+
+// ShiftLigandCloserByThreshold (metropolis.go:267-285; what SimulateMultipleLigands does first, :14-16) on the resident start poses
+int ddd_screen_shift_closer(ddd_screen *s, double threshold) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    REQUIRE_INIT();
+    if (int rc0 = check_screen(s)) return rc0;
+    if (int rc = ensure_reference(s)) return rc;
+    for (auto &d : s->devs) {
+        const int64_t n_ll = d.lig1 - d.lig0;
+        if (n_ll <= 0) continue;
+        const Dev &dev = g_devs[d.di];
+        CUDA_TRY(cudaSetDevice(dev.id));
+        ClosestArgs a;
+        a.rec = s->rec->view(d.di); a.offsets = d.d_offsets + d.lig0; a.atom_base = d.atom_base; a.lig_xyzq = d.d_lig;
+        a.out_dist = nullptr; a.out_lig_atom = nullptr; a.out_prot_atom = nullptr; a.threshold = threshold; a.do_shift = 1;
+        closest_atom_kernel<<<(unsigned)n_ll, kThreads, 0, dev.stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return DDD_OK;
+}
+
+// the start poses as they are resident now (after randomise / shift): for checking the pipeline stage by stage
+int ddd_screen_download_start(ddd_screen *s, double *out_xyzq) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    REQUIRE_INIT();
+    if (int rc0 = check_screen(s)) return rc0;
+    for (auto &d : s->devs) {
+        if (d.n_atoms_in == 0) continue;
+        if (!out_xyzq) return fail(DDD_EINVAL, "out_xyzq is NULL");
+        CUDA_TRY(cudaSetDevice(g_devs[d.di].id));
+        CUDA_TRY(cudaMemcpyAsync(out_xyzq + d.atom_base * 4, d.d_lig, sizeof(double) * 4 * (size_t)d.n_atoms_in, cudaMemcpyDeviceToHost, g_devs[d.di].stream));
+    }
+    for (auto &d : s->devs) { CUDA_TRY(cudaSetDevice(g_devs[d.di].id)); CUDA_TRY(cudaStreamSynchronize(g_devs[d.di].stream)); }
+    return DDD_OK;
+}
+
+// Replica pick (:102-109) of the last run, per ligand, on the device; the picked pose, its energy (= CalculateEnergy(minLigand),
+// :61), the replica index and CalculateRMSD(picked pose, reference pose) (= CompareRMSD's return, validateResults.go:40-45)
+// stay resident for ddd_screen_argmin and are copied out where a pointer is given.
+int ddd_screen_pick(ddd_screen *s, double temperature, uint64_t seed, uint64_t first_ligand_index,
+                    double *out_xyzq, double *out_energy, int64_t *out_picked, double *out_rmsd) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    REQUIRE_INIT();
+    if (int rc0 = check_screen(s)) return rc0;
+    if (int rc = screen_pick_impl(s, temperature, seed, first_ligand_index)) return rc;
+    return screen_download_pick(s, out_xyzq, out_energy, out_picked, out_rmsd);
+}
+
+// SaveMinimumEnergyLigand's choice (plotting.go:109-121) over the picked per-ligand energies, as a device reduction:
+// rule DDD_ARGMIN_SAVE_MIN_LIGAND = (minIndex 0, minEnergy 0.0, strict <): only a negative energy can win;
+// rule DDD_ARGMIN_RSHINY = RShinyAppMain's (main.go:35, 51-54): minEnergy starts at 1e20.
+int ddd_screen_argmin(ddd_screen *s, int32_t rule, int64_t *out_index, double *out_energy) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    REQUIRE_INIT();
+    if (int rc0 = check_screen(s)) return rc0;
+    if (!s->picked) return fail(DDD_EINVAL, "ddd_screen_argmin needs ddd_screen_pick on the last run's results");
+    if (rule != DDD_ARGMIN_SAVE_MIN_LIGAND && rule != DDD_ARGMIN_RSHINY) return fail(DDD_EINVAL, "unknown argmin rule %d", rule);
+    std::vector<double> hv(s->devs.size(), 0.0);
+    std::vector<long long> hi(s->devs.size(), -1);
+    for (size_t k = 0; k < s->devs.size(); ++k) {
+        auto &d = s->devs[k];
+        const Dev &dev = g_devs[d.di];
+        CUDA_TRY(cudaSetDevice(dev.id));
+        if (!d.d_arg_val) { if (int rc = dev_alloc(&d.d_arg_val, 1)) return rc; }
+        if (!d.d_arg_idx) { if (int rc = dev_alloc(&d.d_arg_idx, 1)) return rc; }
+        argmin_first_kernel<<<1, 1024, 0, dev.stream>>>(d.d_min_e, d.lig1 - d.lig0, d.lig0, d.d_arg_val, d.d_arg_idx);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(&hv[k], d.d_arg_val, sizeof(double), cudaMemcpyDeviceToHost, dev.stream));
+        CUDA_TRY(cudaMemcpyAsync(&hi[k], d.d_arg_idx, sizeof(long long), cudaMemcpyDeviceToHost, dev.stream));
+    }
+    for (auto &d : s->devs) { CUDA_TRY(cudaSetDevice(g_devs[d.di].id)); CUDA_TRY(cudaStreamSynchronize(g_devs[d.di].stream)); }
+    double best = rule == DDD_ARGMIN_RSHINY ? 1e20 : 0.0;                  // main.go:35 / plotting.go:111
+    int64_t bi = 0;                                                        // minIndex := 0 (plotting.go:110; main.go:36 likewise)
+    for (size_t k = 0; k < s->devs.size(); ++k)                            // devices hold ascending ligand blocks: strict < keeps the first
+        if (hi[k] >= 0 && hv[k] < best) { best = hv[k]; bi = hi[k]; }
+    if (out_index) *out_index = bi;
+    if (out_energy) *out_energy = best;
+    return DDD_OK;
+}
+
+// EXTENSION (north_star: "per-ligand minimum energies and poses"; the reference returns the FINAL pose, metropolis.go:110,135):
+// track the lowest-energy pose every chain visits.  Identical to the final pose while the sampler is greedy.
+int ddd_screen_set_track_best(ddd_screen *s, int32_t on) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (!s) return fail(DDD_EINVAL, "screen is NULL");
+    s->track_best = on != 0;
+    return DDD_OK;
+}
+
+// out_xyzq: chain-major like ddd_screen_download; out_energy[n_chains] = the chain's own (fp32-summed in F32 mode) energy of that pose
+int ddd_screen_download_best(ddd_screen *s, double *out_xyzq, double *out_energy) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    REQUIRE_INIT();
+    if (int rc0 = check_screen(s)) return rc0;
+    if (!s->launched) return fail(DDD_EINVAL, "screen has not been run");
+    for (auto &d : s->devs) {
+        if (!d.d_best || !d.d_best_e) return fail(DDD_EINVAL, "the last run did not track best-ever poses (ddd_screen_set_track_best)");
+        CUDA_TRY(cudaSetDevice(g_devs[d.di].id));
+        if (out_xyzq && d.out_atoms > 0)
+            CUDA_TRY(cudaMemcpyAsync(out_xyzq + d.out_base * 4, d.d_best, sizeof(double) * 4 * (size_t)d.out_atoms, cudaMemcpyDeviceToHost, g_devs[d.di].stream));
+        if (out_energy) CUDA_TRY(cudaMemcpyAsync(out_energy + d.c0, d.d_best_e, sizeof(double) * (size_t)(d.c1 - d.c0), cudaMemcpyDeviceToHost, g_devs[d.di].stream));
+    }
+    for (auto &d : s->devs) { CUDA_TRY(cudaSetDevice(g_devs[d.di].id)); CUDA_TRY(cudaStreamSynchronize(g_devs[d.di].stream)); }
+    return DDD_OK;
+}
+
 // Cutoff extension: receptor atoms actually paired with each ligand atom by chain c's fp32 sums, summed over its
 // evaluations (32 x the units its poses' cell-list queries returned).  Zero-filled when the last run had no cutoff.
 int ddd_screen_pair_units(ddd_screen *s, int64_t *out_receptor_atoms) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     REQUIRE_INIT();
-    if (!s) return fail(DDD_EINVAL, "screen is NULL");
+    if (int rc0 = check_screen(s)) return rc0;
     if (!s->launched) return fail(DDD_EINVAL, "screen has not been run");
     if (!out_receptor_atoms && s->n_chains > 0) return fail(DDD_EINVAL, "out is NULL");
     if (int rc = screen_sync_impl(s)) return rc;
@@ -1095,7 +1482,7 @@ int ddd_screen_pair_units(ddd_screen *s, int64_t *out_receptor_atoms) {
 int ddd_screen_set_lj(ddd_screen *s, const double *sigma, const double *epsilon) {
     std::lock_guard<std::recursive_mutex> lk(g_mu);
     REQUIRE_INIT();
-    if (!s) return fail(DDD_EINVAL, "screen is NULL");
+    if (int rc0 = check_screen(s)) return rc0;
     if (!sigma || !epsilon) return fail(DDD_EINVAL, "sigma/epsilon is NULL");
     for (auto &d : s->devs) {
         std::vector<double2> h((size_t)std::max<int64_t>(d.n_atoms_in, 1));

@@ -37,7 +37,9 @@ constexpr int kSmWarps    = kSmThreads / 32;
 constexpr int kSmMaxSlots = 16;
 constexpr int kSmMaxItems = 128;            // work items per energy evaluation (item sums kept per slot)
 constexpr int kSlotIdle   = 0x3fffffff;     // next_item of a slot that has nothing to hand out
-constexpr int kUbufDraws  = 256;            // jitter uniforms staged per proposal attempt (ligands up to 84 atoms)
+constexpr int kUbufMaxAtoms = 512;         // ligands up to this size stage an attempt's jitter uniforms in shared memory (Rshiny/MCdata reaches 140)
+// uniforms staged per proposal attempt for ligands of up to `cap` atoms: 3 per atom + 2 (block alignment), even
+__host__ __device__ constexpr int ubuf_draws(int cap) { return ((3 * (cap < kUbufMaxAtoms ? cap : kUbufMaxAtoms) + 2) + 1) & ~1; }
 constexpr int kNearCap    = 128;            // near-pair list entries per slot
 constexpr int kUnitCap    = 512;            // cutoff extension: receptor units (32 atoms) within reach of one pose
 #ifndef DDD_NEAR_MARGIN
@@ -71,15 +73,16 @@ struct __align__(16) SmSlotCtl {
     long long spec_rej;
     int n_e, upi_e;                                   // pair-sum items of the evaluation handed out, receptor units per item
     int n_surv[3];                                    // cutoff extension: units within reach of pose buffer b (-1: list overflow)
-    int pad0, pad1, pad2;
+    int best_is_cur, pad1, pad2;                      // best-ever tracker: the current pose is the best one seen so far
     long long units_done;                             // cutoff extension: receptor units evaluated by the chain's fp32 sums
-    long long pad3;
+    double best_e;                                    // lowest chain energy seen (start pose included)
     float lbox[3][8];                                 // fp32 bounding box of pose buffer b: (min xyz, -, max xyz, -)
     unsigned apart[3][2];                             // bit g: receptor group g's box is apart from pose buffer b's box (clamp-free)
     unsigned pad4, pad5;
 };
 static_assert(sizeof(SmSlotCtl) == 352, "SmSlotCtl is laid out as twenty-two 16-byte words");
-constexpr int kSlotFixedBytes = (int)sizeof(SmSlotCtl) + kSmMaxItems * 8 + kUbufDraws * 8 + 2 * kNearCap * 4;
+constexpr int kSlotFixedBytes = (int)sizeof(SmSlotCtl) + kSmMaxItems * 8 + 2 * kNearCap * 4;      // + ubuf_draws(cap) * 8, see slot_fixed_bytes
+__host__ __device__ constexpr int slot_fixed_bytes(int cap) { return kSlotFixedBytes + ubuf_draws(cap) * 8; }
 constexpr int kAtomRecBytes = 88;                     // fp64 record per atom: 3 poses x (x,y,z), q, pad
 constexpr int kAtomBytes = kAtomRecBytes + 3 * 16;    // + three pair-packed fp32 poses
 
@@ -106,17 +109,17 @@ struct SmArgs {
 
 constexpr int kMaxLaneSumGroups = 64;       // receptors up to 8 192 atoms keep per-group, per-lane fp32 sums
 __host__ __device__ inline size_t sm_smem_bytes(int nl_cap, int slots, int extra_bytes = 0) {
-    return kCtaHeaderBytes + (size_t)slots * (kSlotFixedBytes + (size_t)nl_cap * kAtomBytes + extra_bytes);
+    return kCtaHeaderBytes + (size_t)slots * (slot_fixed_bytes(nl_cap) + (size_t)nl_cap * kAtomBytes + extra_bytes);
 }
 
-// Views into the CTA's shared memory: [live 16][keys 64] then per slot [ctl][item sums][uniform staging][base list][dyn list]
+// Views into the CTA's shared memory: [live 16][keys 64] then per slot [ctl][item sums][base list][dyn list][uniform staging]
 // [fp64 atom records (cap x 88 B)][fp32 pair-packed poses (3 x cap x 16 B)]
 struct SlotView {
     unsigned char *blk;      // this slot's block
     unsigned char *pose;     // its pose part
     int cap;
-    __device__ __forceinline__ double *ubuf() const { return reinterpret_cast<double *>(blk + sizeof(SmSlotCtl) + kSmMaxItems * 8); }
-    __device__ __forceinline__ ushort2 *base_list() const { return reinterpret_cast<ushort2 *>(blk + sizeof(SmSlotCtl) + kSmMaxItems * 8 + kUbufDraws * 8); }
+    __device__ __forceinline__ ushort2 *base_list() const { return reinterpret_cast<ushort2 *>(blk + sizeof(SmSlotCtl) + kSmMaxItems * 8); }
+    __device__ __forceinline__ double *ubuf() const { return reinterpret_cast<double *>(blk + kSlotFixedBytes); }
     __device__ __forceinline__ ushort2 *dyn_list() const { return base_list() + kNearCap; }
     // One 88-byte record per atom {x0 y0 z0 x1 y1 z1 x2 y2 z2 q pad}: every field sits at a compile-time offset from
     // pose + 88 * i whatever the capacity, and half-warp 8-byte accesses of stride 88 B are bank-conflict free.
@@ -139,14 +142,14 @@ struct SmView {
     __device__ __forceinline__ int *live() const { return reinterpret_cast<int *>(raw); }
     // scheduling key of a slot: the chain's step count while it has work to hand out, kKeyNone otherwise
     __device__ __forceinline__ int *keys() const { return reinterpret_cast<int *>(raw + 16); }
-    __device__ __forceinline__ unsigned char *block(int s) const { return raw + kCtaHeaderBytes + (size_t)s * (kSlotFixedBytes + cap * kAtomBytes + ulb); }   // ulb: all per-slot extras
+    __device__ __forceinline__ unsigned char *block(int s) const { return raw + kCtaHeaderBytes + (size_t)s * (slot_fixed_bytes(cap) + cap * kAtomBytes + ulb); }   // ulb: all per-slot extras
     __device__ __forceinline__ SmSlotCtl *ctl(int s) const { return reinterpret_cast<SmSlotCtl *>(block(s)); }
     __device__ __forceinline__ double *items(int s) const { return reinterpret_cast<double *>(block(s) + sizeof(SmSlotCtl)); }
     __device__ __forceinline__ SlotView slot(int s) const {
         SlotView v;
         v.cap = cap;
         v.blk = block(s);
-        v.pose = v.blk + kSlotFixedBytes;
+        v.pose = v.blk + slot_fixed_bytes(cap);
         return v;
     }
 };
@@ -159,9 +162,11 @@ __device__ __forceinline__ void cta_fence() { asm volatile("fence.acq_rel.cta;" 
 __device__ __forceinline__ int ld_volatile(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 __device__ __forceinline__ void st_volatile(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
 
-__device__ __forceinline__ bool boxes_apart(const float4 gmin, const float4 gmax, const float *lbox) {
-    return gmin.x - lbox[4] > 1e-3f || lbox[0] - gmax.x > 1e-3f || gmin.y - lbox[5] > 1e-3f ||
-           lbox[1] - gmax.y > 1e-3f || gmin.z - lbox[6] > 1e-3f || lbox[2] - gmax.z > 1e-3f;
+// `gap` = DevParams::apart_gap: max(1e-3 A, 2.5 x clamp_distance) -- boxes farther apart than this cannot hold a pair inside
+// the clamp distance, whatever the caller set it to (fp32 box / pose rounding is orders of magnitude below the margin)
+__device__ __forceinline__ bool boxes_apart(const float4 gmin, const float4 gmax, const float *lbox, float gap) {
+    return gmin.x - lbox[4] > gap || lbox[0] - gmax.x > gap || gmin.y - lbox[5] > gap ||
+           lbox[1] - gmax.y > gap || gmin.z - lbox[6] > gap || lbox[2] - gmax.z > gap;
 }
 
 // ------------------------------------------------------------------ energy work items
@@ -233,7 +238,7 @@ __device__ __noinline__ double sm_item_f32(const SmArgs &A, const float4 *lf, co
         for (; u + 4 <= u1; u += 4) {
             const float4 gmin = __ldg(A.c.rec.gbox + (u >> 1)), gmax = __ldg(A.c.rec.gbox + (u >> 1) + 1);
             int ub[4] = {u * 32, u * 32 + 32, u * 32 + 64, u * 32 + 96};
-            if (boxes_apart(gmin, gmax, lbox)) acc += (double)warp_units_sum_f32<4, false, false>(rec, ub, lf2, n_pairs, rmax, 0.f);
+            if (boxes_apart(gmin, gmax, lbox, A.c.prm.apart_gap)) acc += (double)warp_units_sum_f32<4, false, false>(rec, ub, lf2, n_pairs, rmax, 0.f);
             else acc += (double)warp_units_sum_f32<4, false, true>(rec, ub, lf2, n_pairs, rmax, 0.f);
         }
     } else {
@@ -445,7 +450,7 @@ __device__ __noinline__ void warp_write_lf(const SmArgs &A, const SlotView &s, S
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
             const int g = 32 * w + lane;
-            const bool ap = g < A.n_groups4 && boxes_apart(__ldg(A.c.rec.gbox + 2 * g), __ldg(A.c.rec.gbox + 2 * g + 1), lb);
+            const bool ap = g < A.n_groups4 && boxes_apart(__ldg(A.c.rec.gbox + 2 * g), __ldg(A.c.rec.gbox + 2 * g + 1), lb, A.c.prm.apart_gap);
             const unsigned m = __ballot_sync(0xffffffffu, ap);
             if (lane == 0) c->apart[buf][w] = m;
         }
@@ -619,7 +624,7 @@ __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotVie
     const double pair_step = fabs(P.jitter_width) * 1.7320508075688774;   // max change of a pair distance per attempt
     const int k_max = pair_step > 0.0 ? (int)fmin((kNearMargin - 1e-6) / (pair_step * (1.0 + 1e-9)), 1.0e6) : 1000000;
     const float r_near = (float)(P.min_distance + kNearMargin), r2_near = r_near * r_near;
-    const bool use_ubuf = !st.rec && 3 * nl + 2 <= kUbufDraws;
+    const bool use_ubuf = !st.rec && nl <= kUbufMaxAtoms;
     int base_n = c->base_n;
     if (base_n < 0) {                                                     // first proposal after a load or an accepted move
         base_n = warp_build_near_list(s.lf(src), c, s.base_list(), nl, r2_near);
@@ -806,6 +811,7 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 c->i_cur = 0; c->i_trial = 0; c->i_spec = 1; c->has_spec = 0;
                 c->local = local; c->step = 0; c->pos = 0; c->accepted = 0; c->downhill = 0; c->retries = 0;
                 c->cur_e = 0.0; c->start_e = 0.0; c->off = off; c->base_n = -1; c->list_cnt = 0; c->units_done = 0;
+                c->best_e = 0.0; c->best_is_cur = 1;
                 c->stream_id = a.chain_id_base + (uint64_t)chain;
                 c->rec_ptr = nullptr; c->rec_len = 0;
                 if (a.recorded) {
@@ -824,7 +830,7 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
         }
         const int nl = c->nl;
         if (stage == ST_START64) {
-            if (lane == 0) { c->start_e = e; c->cur_e = e; }
+            if (lane == 0) { c->start_e = e; c->cur_e = e; c->best_e = e; }
             __syncwarp();
             if (PRECISE) stage = ST_NEXT;
             else {
@@ -834,7 +840,7 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
             }
         }
         if (stage == ST_START32) {
-            if (lane == 0) c->cur_e = P.k_coulomb * e;
+            if (lane == 0) { c->cur_e = P.k_coulomb * e; c->best_e = c->cur_e; }
             __syncwarp();
             stage = ST_NEXT;
         }
@@ -858,6 +864,25 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 pos += 1;
             }
             __syncwarp();
+            // EXTENSION (no reference row): best-ever pose.  While every accepted move lowers the energy the current pose IS
+            // the best one; only when a move that does not improve on the best is accepted (an uphill accept, or a downhill
+            // one below an earlier peak) does the pose being left have to be saved -- never at the reference constants (F7).
+            bool save_best = false;
+            if (acc && a.out_best_e) {
+                if (new_e < c->best_e) { if (lane == 0) { c->best_e = new_e; c->best_is_cur = 1; } }
+                else if (c->best_is_cur) { save_best = true; if (lane == 0) c->best_is_cur = 0; }
+            }
+            __syncwarp();
+            if (save_best) {
+                const long long out_atom = (long long)a.replicas * c->off + (long long)c->rep * c->nl - a.out_base;
+                double *bdst = a.out_best_xyzq + out_atom * 4;
+                const int cu = c->i_cur;
+                for (int i = lane; i < c->nl; i += 32) {
+                    const double *p = s.xyz(cu, i);
+                    bdst[4 * i] = p[0]; bdst[4 * i + 1] = p[1]; bdst[4 * i + 2] = p[2]; bdst[4 * i + 3] = s.q(i);
+                }
+                __syncwarp();
+            }
             if (lane == 0) {
                 const int t = c->i_trial, sp = c->i_spec, cu = c->i_cur;
                 if (acc) { c->cur_e = new_e; c->base_n = -1; c->i_cur = t; c->i_trial = cu; c->i_spec = sp; }   // :129-130
@@ -913,11 +938,27 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
             const long long out_atom = (long long)a.replicas * c->off + (long long)c->rep * nl - a.out_base;
             double *dst = a.out_xyzq + out_atom * 4;
             const int cu = c->i_cur;
+            // fused CalculateRMSD (validateResults.go:50-65) of the final pose against the reference pose: same lane-strided
+            // partial sums and butterfly as rmsd_chains_kernel, so both give the same bits
+            const double4 *ref4 = a.out_rmsd ? reinterpret_cast<const double4 *>(a.ref_xyzq) + (c->off - a.atom_base) : nullptr;
+            double *bdst = (a.out_best_e && c->best_is_cur) ? a.out_best_xyzq + out_atom * 4 : nullptr;
+            double rsum = 0.0;
             for (int i = lane; i < nl; i += 32) {
                 const double *p = s.xyz(cu, i);
                 dst[4 * i] = p[0]; dst[4 * i + 1] = p[1]; dst[4 * i + 2] = p[2]; dst[4 * i + 3] = s.q(i);
+                if (bdst) { bdst[4 * i] = p[0]; bdst[4 * i + 1] = p[1]; bdst[4 * i + 2] = p[2]; bdst[4 * i + 3] = s.q(i); }
+                if (ref4) {
+                    const double4 r = ref4[i];
+                    const double dx = p[0] - r.x, dy = p[1] - r.y, dz = p[2] - r.z;
+                    rsum += dx * dx + dy * dy + dz * dz;                       // :58-62
+                }
+            }
+            if (ref4) {
+                rsum = warp_sum(rsum);
+                if (lane == 0) a.out_rmsd[c->local] = sqrt(rsum / (double)nl);  // :64 (nl == 0 -> NaN)
             }
             if (lane == 0) {
+                if (a.out_best_e) a.out_best_e[c->local] = c->best_e;
                 ChainStats cs;
                 cs.accepted = c->accepted; cs.downhill = c->downhill; cs.retries = c->retries; cs.steps = c->step;
                 cs.draws = (long long)c->pos; cs.status = c->status;
@@ -975,8 +1016,10 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
         it = __shfl_sync(0xffffffffu, it, 0);
         cta_fence();
         const int n_total = ld_volatile(&c->n_total);
-        // whoever takes the last piece clears the key (it still holds that piece, so the slot cannot be re-published before)
-        if (it == n_total - 1 && lane == 0) st_volatile(V.keys() + sid, kKeyNone);
+        // whoever takes the last piece clears the key AND parks the counter (it still holds that piece, so the slot cannot be
+        // re-published before): a warp that read the key long ago and bumps the counter only now gets a value >= kSlotIdle,
+        // never an index that the next hand-out (with a larger n_total) would take for one of its own pieces
+        if (it == n_total - 1 && lane == 0) { st_volatile(V.keys() + sid, kKeyNone); st_volatile(&c->next_item, kSlotIdle); }
         if (it >= n_total) continue;
         const int has_spec = c->has_spec;                   // the speculative proposal is handed out first: it is the long pole
         if (has_spec && it == 0) sm_spec_task(A, V, sid);

@@ -22,6 +22,8 @@
  *    except inside the opaque handles.
  *  - Thread-safe: calls are serialised on an internal mutex and select their device on entry
  *    (goroutines migrate between OS threads).
+ *  - ddd_init with the device list already in use is a no-op; ddd_shutdown (and ddd_init with a different list) makes every
+ *    receptor / screen created before it STALE: entry points refuse stale handles, the destroy functions still free them.
  */
 #ifndef DDD_MC_H
 #define DDD_MC_H
@@ -51,6 +53,10 @@ extern "C" {
 /* chain status bits */
 #define DDD_STATUS_RETRY_LIMIT      1  /* collision retry bound hit (reference would spin, :155,:173) */
 #define DDD_STATUS_STREAM_EXHAUSTED 2  /* recorded uniform stream ran dry */
+
+/* ddd_screen_argmin rules */
+#define DDD_ARGMIN_SAVE_MIN_LIGAND 0  /* plotting.go:109-121: minIndex 0, minEnergy 0.0, strict < (only a negative energy wins) */
+#define DDD_ARGMIN_RSHINY          1  /* main.go:35-36, 51-54: minEnergy 1e20, strict < */
 
 /* Philox stream-id spaces */
 #define DDD_STREAM_PARENT_BASE    0x4000000000000000ull  /* + ligand index: replica-pick draws (:105) */
@@ -109,6 +115,13 @@ void        ddd_params_default(ddd_params *p);
 int     ddd_receptor_create(const double *xyzq, int64_t n_atoms, ddd_receptor **out);
 int     ddd_receptor_destroy(ddd_receptor *r);
 int64_t ddd_receptor_num_atoms(const ddd_receptor *r);
+/* Content-keyed receptor cache for the scalar Go functions that receive the protein on every call (CalculateEnergy
+ * metropolis.go:247, FindClosestAtomDistance :290, ShiftLigandCloserByThreshold :267, SimulateEnergyMinimizationParallel :94
+ * as RShinyAppMain calls it per ligand, main.go:42-48): acquire returns the resident receptor of an identical xyzq array
+ * (length + hash, compared in full) or builds one; release drops the caller's reference.  Up to 8 receptors stay cached
+ * (least recently used evicted); handles from acquire must not be passed to ddd_receptor_destroy. */
+int     ddd_receptor_acquire(const double *xyzq, int64_t n_atoms, ddd_receptor **out);
+int     ddd_receptor_release(ddd_receptor *r);
 /* LJ extension: per-atom sigma (A) and epsilon of the receptor (n_atoms entries each); NULL, NULL clears them */
 int     ddd_receptor_set_lj(ddd_receptor *r, const double *sigma, const double *epsilon);
 
@@ -146,6 +159,11 @@ int ddd_minimize_batch(const ddd_receptor *r, const int64_t *offsets, const doub
                        uint64_t first_ligand_index,
                        double *out_xyzq, double *out_energy,
                        ddd_chain_stats *out_chain_stats, int64_t *out_picked);
+
+/* Chain status of this THREAD's last ddd_minimize_batch / ddd_run_chains call: returns the OR of the DDD_STATUS_* bits over
+ * its chains; *out_retry_limited_chains (nullable) = how many stopped at the collision-retry bound, where the reference
+ * would still be retrying (metropolis.go:155, :173).  The Go / C++ / Python mirrors warn when this is non-zero. */
+int64_t ddd_last_chain_status(int64_t *out_retry_limited_chains);
 
 /* ---- CalculateRMSD (validateResults.go:50-65), batched over (simulated, reference) pairs ----
  * atom_stride: doubles per atom in sim/ref (4 = Go []Atom layout, 3 = packed xyz).
@@ -191,6 +209,34 @@ int    ddd_screen_download(ddd_screen *s, double *out_xyzq, ddd_chain_stats *out
  * out_rmsd[c] = CalculateRMSD(final pose of chain c, start pose of its ligand) (validateResults.go:50-65).
  * out_kernel_ms (nullable): CUDA-event time of the RMSD kernel, max over devices. */
 int    ddd_screen_rmsd(ddd_screen *s, double *out_rmsd, double *out_kernel_ms);
+/* The same values as left behind by the chain kernel's own epilogue (SM-persistent engine): no extra pass, same bits. */
+int    ddd_screen_fused_rmsd(ddd_screen *s, double *out_rmsd);
+
+/* ---- resident pipeline: TestMethodRMSD / CompareRMSD (validateResults.go:14-45), SimulateMultipleLigands' shift
+ *      (metropolis.go:14-16) and SaveMinimumEnergyLigand's choice (plotting.go:109-121) without leaving HBM ----
+ * ddd_screen_randomize: RandomizeLigandPose (validateResults.go:70-79) on the resident start poses, in place; ligand i draws
+ *   from stream (seed, DDD_STREAM_RANDOMIZE_BASE + first_ligand_index + i).  The poses as uploaded stay resident as the RMSD
+ *   reference (CompareRMSD takes its CopyLigand before randomising, :41).
+ * ddd_screen_shift_closer: ShiftLigandCloserByThreshold (metropolis.go:267-285) on the resident start poses.
+ * ddd_screen_download_start: the start poses as resident now (out_xyzq: offsets[n_lig] atoms x 4).
+ * ddd_screen_pick: the replica pick of SimulateEnergyMinimizationParallel (:102-109) over the last run's chains, replica-index
+ *   order, draws from (seed, DDD_STREAM_PARENT_BASE + first_ligand_index + i); per ligand: picked pose (CSR like the input),
+ *   energy = CalculateEnergy(picked pose) in fp64 (:61), replica kept (-1 = start pose), CalculateRMSD(picked pose, reference
+ *   pose) = CompareRMSD's return value.  Every out pointer is nullable: the results stay resident either way.
+ * ddd_screen_argmin: index and energy SaveMinimumEnergyLigand (rule 0) / RShinyAppMain (rule 1) would select among the
+ *   picked per-ligand energies. */
+int    ddd_screen_randomize(ddd_screen *s, uint64_t seed, uint64_t first_ligand_index);
+int    ddd_screen_shift_closer(ddd_screen *s, double threshold);
+int    ddd_screen_download_start(ddd_screen *s, double *out_xyzq);
+int    ddd_screen_pick(ddd_screen *s, double temperature, uint64_t seed, uint64_t first_ligand_index,
+                       double *out_xyzq, double *out_energy, int64_t *out_picked, double *out_rmsd);
+int    ddd_screen_argmin(ddd_screen *s, int32_t rule, int64_t *out_index, double *out_energy);
+/* EXTENSION (no reference row; north_star asks for per-ligand MINIMUM energies and poses, the reference returns the FINAL pose,
+ * metropolis.go:110,135): when on, every chain also keeps the lowest-energy pose it visited.  Equal to the final pose while
+ * the sampler is greedy.  download_best: out_xyzq chain-major like ddd_screen_download, out_energy[n_chains] =
+ * the chain's own energy of that pose (fp32-summed in F32 mode).  Needs the SM-persistent engine. */
+int    ddd_screen_set_track_best(ddd_screen *s, int32_t on);
+int    ddd_screen_download_best(ddd_screen *s, double *out_xyzq, double *out_energy);
 /* LJ extension: per-atom sigma / epsilon of the screen's ligands, in the CSR order of ddd_screen_create
  * (offsets[n_lig] entries each); used by runs whose params.lj_scale != 0 */
 int    ddd_screen_set_lj(ddd_screen *s, const double *sigma, const double *epsilon);

@@ -487,6 +487,54 @@ void orc_chain_one_proc(const orc_atom *prot, int64_t np, orc_atom *lig, int64_t
     if (stats) *stats = st;
 }
 
+/* EXTENSION (no reference row): the same chain, additionally tracking the lowest-energy pose it visits (start pose
+ * included; a later pose replaces it only on a strictly lower energy).  best_pose has nl atoms. */
+void orc_chain_one_proc_best(const orc_atom *prot, int64_t np, orc_atom *lig, int64_t nl,
+                             int64_t iterations, int rotate, double temperature,
+                             const orc_params *p, orc_stream *s, orc_chain_stats *stats,
+                             orc_atom *best_pose, double *best_energy) {
+    orc_chain_stats st; memset(&st, 0, sizeof st);
+    orc_atom *prev = (orc_atom *)malloc(sizeof(orc_atom) * (size_t)(nl > 0 ? nl : 1));
+    double current_energy = orc_calculate_energy(prot, np, lig, nl, p);
+    double best = current_energy;
+    memcpy(best_pose, lig, sizeof(orc_atom) * (size_t)nl);
+    st.start_energy = current_energy;
+    for (int64_t i = 0; i < iterations; ++i) {
+        memcpy(prev, lig, sizeof(orc_atom) * (size_t)nl);
+        int64_t rej;
+        if (p->move_mode == 1) { orc_rigid_move(lig, nl, p, s); rej = 0; }
+        else if (rotate) rej = orc_jitter_and_rotate_ligand(lig, nl, p, s);
+        else rej = orc_jitter_ligand(lig, nl, p, s);
+        if (rej < 0) { st.retries += -rej - 1; st.status |= 1; memcpy(lig, prev, sizeof(orc_atom) * (size_t)nl); break; }
+        st.retries += rej;
+        double new_energy = orc_calculate_energy(prot, np, lig, nl, p);
+        int downhill = new_energy < current_energy;
+        int acc = orc_accept_move(current_energy, new_energy, temperature, s);
+        if (acc) {
+            current_energy = new_energy; st.accepted++; st.downhill += downhill;
+            if (new_energy < best) { best = new_energy; memcpy(best_pose, lig, sizeof(orc_atom) * (size_t)nl); }
+        } else memcpy(lig, prev, sizeof(orc_atom) * (size_t)nl);
+        st.steps++;
+    }
+    if (s->exhausted) st.status |= 2;
+    st.draws = (int64_t)s->pos;
+    st.final_energy = current_energy;
+    free(prev);
+    if (stats) *stats = st;
+    if (best_energy) *best_energy = best;
+}
+
+/* plotting.go:109-121 SaveMinimumEnergyLigand's choice (rule 0: minIndex 0, minEnergy 0.0) and RShinyAppMain's
+ * (main.go:35-36, 51-54; rule 1: minEnergy 1e20): a sequential scan with a strict `<`. */
+int64_t orc_min_energy_index(const double *energy, int64_t n, int rule, double *min_energy_out) {
+    int64_t min_index = 0;
+    double min_energy = rule == 1 ? 1e20 : 0.0;
+    for (int64_t i = 0; i < n; ++i)
+        if (energy[i] < min_energy) { min_index = i; min_energy = energy[i]; }
+    if (min_energy_out) *min_energy_out = min_energy;
+    return min_index;
+}
+
 /* metropolis.go:94-111 */
 int orc_minimize_parallel(const orc_atom *prot, int64_t np, orc_atom *lig, int64_t nl,
                           int64_t iterations, int rotate, double temperature, int num_procs,

@@ -137,6 +137,13 @@ void orc_chain_one_proc(const orc_atom *prot, int64_t np, orc_atom *lig, int64_t
  * parent pick draws from stream (seed, ORC_STREAM_PARENT_BASE + lig_index).
  * chain_poses (nullable): num_procs*nl atoms, each chain's final pose.
  * Returns 0, or -1 if num_procs <= 0 (Go: integer divide by zero panic). */
+/* EXTENSION: orc_chain_one_proc + best-ever (lowest-energy) pose tracking; no reference row */
+void orc_chain_one_proc_best(const orc_atom *prot, int64_t np, orc_atom *lig, int64_t nl,
+                             int64_t iterations, int rotate, double temperature,
+                             const orc_params *p, orc_stream *s, orc_chain_stats *stats,
+                             orc_atom *best_pose, double *best_energy);
+/* plotting.go:109-121 (rule 0) / main.go:35-36,51-54 (rule 1): index the reference would select */
+int64_t orc_min_energy_index(const double *energy, int64_t n, int rule, double *min_energy_out);
 int orc_minimize_parallel(const orc_atom *prot, int64_t np, orc_atom *lig, int64_t nl,
                           int64_t iterations, int rotate, double temperature, int num_procs,
                           const orc_params *p, uint64_t seed, uint64_t lig_index,

@@ -77,6 +77,8 @@ class Oracle:
             "orc_is_collision_free": (C.c_int, [vp, i64, d]),
             "orc_calculate_energy": (d, [vp, i64, vp, i64, PP]),
             "orc_calculate_energy_abs": (d, [vp, i64, vp, i64, PP, vp]),
+            "orc_chain_one_proc_best": (None, [vp, i64, vp, i64, i64, C.c_int, d, PP, SP, vp, vp, vp]),
+            "orc_min_energy_index": (i64, [vp, i64, C.c_int, vp]),
             "orc_accept_move": (C.c_int, [d, d, d, SP]),
             "orc_rotate_ligand": (None, [vp, i64, d, SP]),
             "orc_jitter_ligand": (i64, [vp, i64, PP, SP]),
@@ -226,6 +228,23 @@ class Oracle:
         if want_trace:
             return lig, st[0], tr[:iterations], et[:iterations]
         return lig, st[0]
+
+    def chain_best(self, prot, lig, iterations, rotate, temperature, stream, params=None):
+        """EXTENSION: chain + best-ever pose -> (final pose, stats, best pose, best energy)"""
+        prot = _atoms(prot); lig = np.array(_atoms(lig), copy=True)
+        st = np.zeros(1, dtype=STATS_DTYPE)
+        best = np.zeros_like(lig); be = np.zeros(1)
+        self.L.orc_chain_one_proc_best(_vp(prot), len(prot), _vp(lig), len(lig), iterations, int(bool(rotate)),
+                                       float(temperature), C.byref(params or self.params()), C.byref(stream),
+                                       _vp(st), _vp(best), _vp(be))
+        return lig, st[0], best, float(be[0])
+
+    def min_energy_index(self, energies, rule=0):
+        """SaveMinimumEnergyLigand (plotting.go:109-121, rule 0) / RShinyAppMain (main.go:51-54, rule 1) -> (index, energy)"""
+        e = np.ascontiguousarray(energies, dtype=np.float64)
+        out = np.zeros(1)
+        i = self.L.orc_min_energy_index(_vp(e), len(e), rule, _vp(out))
+        return int(i), float(out[0])
 
     def minimize_parallel(self, prot, lig, iterations, rotate, temperature, num_procs, seed, lig_index=0, params=None):
         prot = _atoms(prot); lig = np.array(_atoms(lig), copy=True)

@@ -129,6 +129,65 @@ def test_recorded_stream_replay(gpu, orc, synth_small):
         assert np.all(stats["status"] & gpu.STATUS_STREAM_EXHAUSTED)
 
 
+@pytest.mark.parametrize("temperature,k_coulomb", [(3.0e8, 9e9), (0.02, 1.0)])
+@pytest.mark.parametrize("engine", ["sm", "cta64", "sm_slots3"])
+def test_accept_branch_with_intermediate_probability(gpu, orc, synth_small, temperature, k_coulomb, engine):
+    # AcceptMove's uphill branch (metropolis.go:145-148) with 0 < exp(-dE/T) < 1: at the reference constants (K = 9e9,
+    # T = 310.15) the probability is always exactly 0 or 1, so here T is raised / K lowered until about half of
+    # the uphill moves are accepted.  fp64 replay: every draw-vs-exp decision, the conditional draw count and the discarded
+    # speculative proposals (an accept invalidates the speculation) must reproduce the oracle step for step.
+    prot, off, lig = synth_small
+    n = len(off) - 1
+    prm = _p64(gpu, k_coulomb=k_coulomb)
+    with gpu.Receptor(prot) as rec:
+        scr = gpu.Screen(rec, off, lig, 2)
+        if engine == "cta64":
+            scr.set_chain_threads(64)
+        elif engine == "sm_slots3":
+            scr.set_chain_slots(3)
+        scr.run(200, True, temperature, prm, seed=9)
+        poses, stats = scr.download()
+        scr.close()
+        _, _, trace = gpu.run_chains(rec, off, lig, 2, 200, True, temperature, prm, seed=9, want_trace=True)
+    po = orc.params(k_coulomb=k_coulomb)
+    uphill_acc = rejected = 0
+    for c in range(2 * n):
+        li, r = divmod(c, 2)
+        pose_o, st_o, tr_o, _ = orc.chain(prot, lig[off[li]:off[li + 1]], 200, True, temperature, orc.philox_stream(9, c), po, want_trace=True)
+        for k in ("steps", "accepted", "downhill", "retries", "draws", "status"):
+            assert stats[c][k] == st_o[k], (c, k)
+        assert np.array_equal(trace[c], tr_o), c
+        assert np.allclose(gpu.chain_pose(off, 2, poses, li, r), pose_o, rtol=0, atol=1e-9)
+        assert stats[c]["final_energy"] == pytest.approx(st_o["final_energy"], rel=1e-10)
+        uphill_acc += st_o["accepted"] - st_o["downhill"]
+        rejected += st_o["steps"] - st_o["accepted"]
+    assert uphill_acc > 200 and rejected > 200          # both outcomes of the draw < exp(x) comparison really occur
+
+
+def test_accept_branch_intermediate_probability_recorded_stream_and_f32(gpu, orc, synth_small):
+    prot, off, lig = synth_small
+    sel = [2, 4, 7]
+    ligs = [lig[off[i]:off[i + 1]] for i in sel]
+    o2, l2 = gpu.pack_ligands(ligs)
+    rng = np.random.default_rng(7)
+    streams = [rng.random(80 * (4 + 3 * len(l) + 1) * 2) for l in ligs]
+    roff = np.concatenate([[0], np.cumsum([len(s) for s in streams])]).astype(np.int64)
+    Tt = 3.0e8
+    with gpu.Receptor(prot) as rec:
+        poses, stats, trace = gpu.run_chains(rec, o2, l2, 1, 80, True, Tt, _p64(gpu), seed=0, recorded=np.concatenate(streams),
+                                             recorded_offsets=roff, want_trace=True)
+        p32, s32, t32 = gpu.run_chains(rec, o2, l2, 1, 80, True, Tt, gpu.default_params(), seed=5, want_trace=True)
+    for c, l in enumerate(ligs):
+        pose_o, st_o, tr_o, _ = orc.chain(prot, l, 80, True, Tt, orc.recorded_stream(streams[c]), want_trace=True)
+        assert np.array_equal(trace[c], tr_o) and stats[c]["draws"] == st_o["draws"] and stats[c]["status"] == 0
+        assert st_o["accepted"] > st_o["downhill"]
+        assert np.allclose(gpu.chain_pose(o2, 1, poses, c, 0), pose_o, rtol=0, atol=1e-9)
+        # production precision in the same regime: same decisions unless an fp32 near-tie intervenes; statistics alike
+        pose_p, st_p, tr_p, _ = orc.chain(prot, l, 80, True, Tt, orc.philox_stream(5, c), want_trace=True)
+        assert abs(int(s32[c]["accepted"]) - int(st_p["accepted"])) <= 8
+        assert s32[c]["accepted"] > s32[c]["downhill"]
+
+
 def test_collision_retry_is_cumulative_and_bounded(gpu, orc):
     prot = np.array([[5.0, 5, 5, 1.0], [-3.0, 2, 1, -0.5]])
     lig = np.array([[0.0, 0, 0, 0.1], [0.52, 0, 0, -0.1], [0.0, 0.53, 0, 0.2]])      # pairs hover around MINDISTANCE

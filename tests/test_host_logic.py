@@ -29,8 +29,10 @@ def test_shard_plan_balances_atoms_not_counts(capi, ddd):
 
 def test_shard_plan_edge_cases(capi):
     assert capi.shard_plan(np.array([0]), 4, 3).tolist() == [0, 0, 0, 0]            # no ligands
-    b = capi.shard_plan(np.array([0, 10]), 8, 3)                                    # one ligand, 8 replicas
-    assert b[0] == 0 and b[-1] == 8 and np.all(np.diff(b) >= 2)
+    b = capi.shard_plan(np.array([0, 10]), 8, 3)                                    # one ligand, 8 replicas: they stay together
+    assert b[0] == 0 and b[-1] == 8 and sorted(np.diff(b).tolist()) == [0, 0, 8]
+    b = capi.shard_plan(np.array([0, 10, 20, 30, 40, 50]), 8, 2)                    # cuts fall between ligands (replica pick per device)
+    assert b.tolist() in ([0, 16, 40], [0, 24, 40])
     b = capi.shard_plan(np.array([0, 5, 5, 9]), 2, 8)                               # more shards than chains
     assert b[0] == 0 and b[-1] == 6 and np.all(np.diff(b) >= 0)
     with pytest.raises(capi.DddError):

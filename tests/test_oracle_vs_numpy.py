@@ -77,6 +77,21 @@ def test_chain_matches_numpy_restatement(orc, synth_small, rotate):
     assert st["accepted"] == sum(tr_n)
 
 
+@pytest.mark.parametrize("rotate", [False, True])
+def test_chain_uphill_accept_branch_matches_numpy_restatement(orc, synth_small, rotate):
+    # AcceptMove :145-148 with 0 < exp(-dE/T) < 1 (T raised to 3e8: at the reference constants p is always 0 or 1)
+    prot, off, lig = synth_small
+    prot = prot[:120]
+    l = lig[off[2]:off[3]]
+    T = 3.0e8 if rotate else 1.0e7                                        # jitter-only moves change the energy far less
+    pose, st, tr, _ = orc.chain(prot, l, 80, rotate, T, orc.philox_stream(9, 4), want_trace=True)
+    pose_n, cur_n, tr_n = npr.chain(prot, l, 80, rotate, T, npr.Stream(9, 4))
+    assert tr.tolist() == tr_n
+    assert np.allclose(pose[:, :3], pose_n[:, :3], rtol=0, atol=1e-11)
+    assert st["final_energy"] == pytest.approx(cur_n, rel=1e-12)
+    assert st["accepted"] > st["downhill"] and st["accepted"] < 80        # uphill moves both accepted and rejected
+
+
 def test_chain_recorded_stream_equals_philox_stream(orc, synth_small):
     prot, off, lig = synth_small
     l = lig[off[2]:off[3]]
