@@ -7,6 +7,8 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
+#include <cstdlib>
 #include <filesystem>
 #include <fstream>
 #include <iostream>
@@ -44,14 +46,27 @@ ddd_params params() {
 const double *ptr(const Molecule &m) { return m.atoms.empty() ? nullptr : &m.atoms[0].Position.X; }
 double *ptr(Molecule &m) { return m.atoms.empty() ? nullptr : &m.atoms[0].Position.X; }
 
+// The Go functions receive the protein on every call (metropolis.go:247, :267, :290, :94 as RShinyAppMain calls it per ligand,
+// main.go:42-48): the library's content-keyed cache keeps it resident instead of rebuilding it per call.
 struct Receptor {
     ddd_receptor *h = nullptr;
     explicit Receptor(const Molecule &protein) {
         init();
-        check(ddd_receptor_create(ptr(protein), (int64_t)protein.atoms.size(), &h));
+        check(ddd_receptor_acquire(ptr(protein), (int64_t)protein.atoms.size(), &h));
     }
-    ~Receptor() { ddd_receptor_destroy(h); }
+    ~Receptor() { ddd_receptor_release(h); }
+    Receptor(const Receptor &) = delete;
+    Receptor &operator=(const Receptor &) = delete;
 };
+
+// a chain that needed more than max_retries collision retries in one step stopped there; the reference would still be
+// retrying (metropolis.go:155, :173) -- say so instead of returning a truncated chain silently
+void warn_if_truncated(const char *where) {
+    int64_t n = 0;
+    if (ddd_last_chain_status(&n) & DDD_STATUS_RETRY_LIMIT)
+        std::cerr << "ddd_mc warning: " << n << " chain(s) of " << where << " stopped at the collision-retry bound; the reference would "
+                     "still be retrying there (metropolis.go:173)" << std::endl;
+}
 
 void pack(const std::vector<Molecule> &ligands, std::vector<int64_t> &offsets, std::vector<Atom> &flat) {
     offsets.assign(ligands.size() + 1, 0);
@@ -73,6 +88,7 @@ Molecule one_chain(const Molecule &protein, const Molecule &ligand, int iteratio
     ddd_params p = params();
     check(ddd_run_chains(rec.h, offsets, ptr(ligand), 1, 1, iterations, rotate ? 1 : 0, temperature, &p, next_seed(), 0,
                          nullptr, nullptr, ptr(out), &st, nullptr));
+    warn_if_truncated("SimulateEnergyMinimizationOneProc");
     return out;
 }
 
@@ -89,8 +105,28 @@ Position3d Position3d::Scale(double s) const { return {X * s, Y * s, Z * s}; }
 
 // ---- metropolis.go, device-backed
 std::pair<std::vector<Molecule>, std::vector<double>> SimulateMultipleLigands(const Molecule &protein, std::vector<Molecule> &ligands, int iterations, bool rotate, double temperature, int numProcs) {
-    for (auto &l : ligands) ShiftLigandCloserByThreshold(l, protein, THRESHOLD);          // :14-16, in place
-    return SimulateMultipleLigandsParallel(protein, ligands, iterations, rotate, temperature, numProcs);
+    // :14-16 shift every ligand (in place, as the reference's slice aliasing does), then :17-20 minimise: one upload, the
+    // shift, the chains, the replica pick and the gather all run on the resident screen
+    if (numProcs == 0) throw GoPanic("runtime error: integer divide by zero");                // :97
+    Receptor rec(protein);
+    std::vector<int64_t> offsets;
+    std::vector<Atom> flat;
+    pack(ligands, offsets, flat);
+    std::vector<Atom> out(flat.size());
+    std::vector<double> energy(ligands.size());
+    ddd_params p = params();
+    const uint64_t seed = next_seed();
+    ddd_screen *scr = nullptr;
+    check(ddd_screen_create(rec.h, offsets.data(), ptr(flat), (int64_t)ligands.size(), numProcs, 0, &scr));
+    struct Guard { ddd_screen *s; ~Guard() { ddd_screen_destroy(s); } } guard{scr};
+    check(ddd_screen_shift_closer(scr, THRESHOLD));
+    check(ddd_screen_download_start(scr, ptr(flat)));
+    for (size_t i = 0; i < ligands.size(); ++i) std::copy(flat.begin() + offsets[i], flat.begin() + offsets[i + 1], ligands[i].atoms.begin());
+    check(ddd_screen_run(scr, iterations / numProcs, rotate ? 1 : 0, temperature, &p, seed));
+    check(ddd_screen_pick(scr, temperature, seed, 0, ptr(out), energy.data(), nullptr, nullptr));
+    std::vector<Molecule> minLigands(ligands.size());
+    for (size_t i = 0; i < ligands.size(); ++i) minLigands[i].atoms.assign(out.begin() + offsets[i], out.begin() + offsets[i + 1]);
+    return {minLigands, energy};
 }
 
 std::pair<std::vector<Molecule>, std::vector<double>> SimulateMultipleLigandsParallel(const Molecule &protein, const std::vector<Molecule> &ligands, int iterations, bool rotate, double temperature, int numProcs) {
@@ -104,6 +140,7 @@ std::pair<std::vector<Molecule>, std::vector<double>> SimulateMultipleLigandsPar
     ddd_params p = params();
     check(ddd_minimize_batch(rec.h, offsets.data(), ptr(flat), (int64_t)ligands.size(), iterations, rotate ? 1 : 0, temperature,
                              numProcs, &p, next_seed(), 0, ptr(out), energy.data(), nullptr, nullptr));
+    warn_if_truncated("SimulateMultipleLigandsParallel");
     std::vector<Molecule> minLigands(ligands.size());
     for (size_t i = 0; i < ligands.size(); ++i) minLigands[i].atoms.assign(out.begin() + offsets[i], out.begin() + offsets[i + 1]);
     return {minLigands, energy};
@@ -230,10 +267,21 @@ Molecule &RandomizeLigandPose(Molecule &ligand) {
 }
 
 double CompareRMSD(const Molecule &protein, Molecule ligand, int iterations, bool rotate, double temperature, int numProcs) {
-    const Molecule reference = CopyLigand(ligand);
-    RandomizeLigandPose(ligand);
-    const Molecule simulated = SimulateEnergyMinimizationParallel(protein, ligand, iterations, rotate, temperature, numProcs);
-    return CalculateRMSD(simulated, reference);
+    // :41 reference = CopyLigand(ligand); :42 RandomizeLigandPose; :43 SimulateEnergyMinimizationParallel; :44 CalculateRMSD --
+    // on the resident screen: the uploaded pose stays behind as the reference, nothing but the RMSD comes back
+    if (numProcs == 0) throw GoPanic("runtime error: integer divide by zero");
+    Receptor rec(protein);
+    const int64_t offsets[2] = {0, (int64_t)ligand.atoms.size()};
+    ddd_params p = params();
+    const uint64_t seed = next_seed();
+    ddd_screen *scr = nullptr;
+    check(ddd_screen_create(rec.h, offsets, ptr(ligand), 1, numProcs, 0, &scr));
+    struct Guard { ddd_screen *s; ~Guard() { ddd_screen_destroy(s); } } guard{scr};
+    check(ddd_screen_randomize(scr, seed, 0));
+    check(ddd_screen_run(scr, iterations / numProcs, rotate ? 1 : 0, temperature, &p, seed));
+    double rmsd = 0;
+    check(ddd_screen_pick(scr, temperature, seed, 0, nullptr, nullptr, nullptr, &rmsd));
+    return rmsd;
 }
 
 double average(const std::vector<double> &arr) {
@@ -261,25 +309,153 @@ double MultipleProteinRMSD(const std::string &dir, int iterations, bool rotate, 
 }
 
 // ---- parsing.go
-Molecule ParseMol2(const std::string &filename) {
-    std::ifstream f(filename);
-    if (!f) throw GoPanic("open " + filename + ": no such file or directory");
-    Molecule m;
-    std::string line;
+namespace {
+// strconv.ParseFloat(s, 64) with the error discarded (parsing.go:85-88): a field that is not entirely a number yields 0
+double parse_field(const char *b, const char *e) {
+    if (b == e) return 0.0;
+    char buf[64];
+    const size_t n = (size_t)(e - b);
+    if (n >= sizeof buf) return 0.0;
+    std::memcpy(buf, b, n); buf[n] = '\0';
+    char *end = nullptr;
+    const double v = std::strtod(buf, &end);
+    return (end == buf + n) ? v : 0.0;
+}
+bool is_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; }
+
+// parsing.go:50-106 over a file already in memory: lines between "@<TRIPOS>ATOM" and the next "@<TRIPOS>", strings.Fields
+// split, >= 9 fields, x/y/z = fields 2..4, charge = the LAST field
+void parse_mol2_buffer(const std::string &text, std::vector<Atom> &atoms) {
     bool inAtoms = false;
-    auto num = [](const std::string &s) { try { size_t n = 0; double v = std::stod(s, &n); return n == s.size() ? v : 0.0; } catch (...) { return 0.0; } };
-    while (std::getline(f, line)) {
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        if (line.rfind("@<TRIPOS>ATOM", 0) == 0) { inAtoms = true; continue; }
-        if (inAtoms && line.rfind("@<TRIPOS>", 0) == 0) break;
-        if (!inAtoms) continue;
-        std::istringstream ss(line);
-        std::vector<std::string> fields;
-        for (std::string t; ss >> t;) fields.push_back(t);
-        if (fields.size() < 9) continue;
-        m.atoms.push_back({{num(fields[2]), num(fields[3]), num(fields[4])}, num(fields.back())});
+    const char *p = text.data(), *end = p + text.size();
+    while (p < end) {
+        const char *eol = (const char *)std::memchr(p, '\n', (size_t)(end - p));
+        const char *le = eol ? eol : end;
+        const size_t len = (size_t)(le - p);
+        if (len >= 13 && std::memcmp(p, "@<TRIPOS>ATOM", 13) == 0) inAtoms = true;
+        else if (inAtoms && len >= 9 && std::memcmp(p, "@<TRIPOS>", 9) == 0) break;
+        else if (inAtoms) {
+            const char *fb[4] = {nullptr, nullptr, nullptr, nullptr}, *fe[4] = {nullptr, nullptr, nullptr, nullptr};   // fields 2, 3, 4, last
+            int nf = 0;
+            const char *q = p;
+            while (q < le) {
+                while (q < le && is_space(*q)) ++q;
+                if (q >= le) break;
+                const char *b = q;
+                while (q < le && !is_space(*q)) ++q;
+                if (nf >= 2 && nf <= 4) { fb[nf - 2] = b; fe[nf - 2] = q; }
+                fb[3] = b; fe[3] = q;
+                ++nf;
+            }
+            if (nf >= 9) atoms.push_back({{parse_field(fb[0], fe[0]), parse_field(fb[1], fe[1]), parse_field(fb[2], fe[2])}, parse_field(fb[3], fe[3])});
+        }
+        p = eol ? eol + 1 : end;
     }
+}
+
+bool read_file(const std::string &filename, std::string &text) {
+    std::ifstream f(filename, std::ios::binary);
+    if (!f) return false;
+    f.seekg(0, std::ios::end);
+    const std::streamoff n = f.tellg();
+    f.seekg(0);
+    text.resize((size_t)std::max<std::streamoff>(n, 0));
+    if (n > 0) f.read(&text[0], n);
+    return true;
+}
+}  // namespace
+
+Molecule ParseMol2(const std::string &filename) {
+    std::string text;
+    if (!read_file(filename, text)) throw GoPanic("open " + filename + ": no such file or directory");
+    Molecule m;
+    parse_mol2_buffer(text, m.atoms);
     return m;
+}
+
+// Screen-scale ingest: every file parsed on its own host thread straight into the CSR staging buffers the C ABI takes
+// (offsets[n+1] + flat xyzq), same order as `files`.  A 100 000-ligand sweep otherwise spends longer in ParseMol2 than on the GPU.
+void ParseMol2Batch(const std::vector<std::string> &files, std::vector<int64_t> &offsets, std::vector<Atom> &flat, int threads) {
+    const size_t n = files.size();
+    std::vector<std::vector<Atom>> parsed(n);
+    std::vector<std::string> errors(n);
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>(n, threads > 0 ? (size_t)threads : std::max(1u, std::thread::hardware_concurrency())));
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+        std::string text;
+        for (size_t i; (i = next.fetch_add(1)) < n;) {
+            if (!read_file(files[i], text)) { errors[i] = "open " + files[i] + ": no such file or directory"; continue; }
+            parse_mol2_buffer(text, parsed[i]);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    for (auto &e : errors) if (!e.empty()) throw GoPanic(e);
+    offsets.assign(n + 1, 0);
+    for (size_t i = 0; i < n; ++i) offsets[i + 1] = offsets[i] + (int64_t)parsed[i].size();
+    flat.resize((size_t)offsets[n]);
+    for (size_t i = 0; i < n; ++i) std::copy(parsed[i].begin(), parsed[i].end(), flat.begin() + offsets[i]);
+}
+
+// ---- plotting.go:126-189: rewrite the ATOM section of `originalFile` with the molecule's coordinates ("%.4f"), fields joined
+// by single spaces as strings.Join does; everything else copied line by line
+void UpdateMol2Coordinates(const std::string &originalFile, const std::string &updatedFile, const Molecule &newMolecule) {
+    std::string text;
+    if (!read_file(originalFile, text)) throw GoPanic("failed to open file: open " + originalFile + ": no such file or directory");
+    std::ofstream out(updatedFile, std::ios::binary);
+    if (!out) throw GoPanic("failed to create output file: open " + updatedFile);
+    size_t atomIndex = 0;
+    bool inAtomSection = false;
+    std::string acc;
+    acc.reserve(text.size() + 64);
+    const char *p = text.data(), *end = p + text.size();
+    while (p < end) {                                                         // bufio.Scanner: lines without their terminator
+        const char *eol = (const char *)std::memchr(p, '\n', (size_t)(end - p));
+        const char *le = eol ? eol : end;
+        std::string line(p, le);
+        if (!line.empty() && line.back() == '\r') line.pop_back();            // ScanLines drops a trailing \r
+        p = eol ? eol + 1 : end;
+        if (line.rfind("@<TRIPOS>ATOM", 0) == 0) { inAtomSection = true; acc += line; acc += '\n'; continue; }
+        else if (line.rfind("@<TRIPOS>", 0) == 0 && inAtomSection) inAtomSection = false;
+        if (inAtomSection && atomIndex < newMolecule.atoms.size()) {
+            std::vector<std::string> parts;
+            for (size_t i = 0; i < line.size();) {
+                while (i < line.size() && is_space(line[i])) ++i;
+                if (i >= line.size()) break;
+                size_t j = i;
+                while (j < line.size() && !is_space(line[j])) ++j;
+                parts.emplace_back(line, i, j - i);
+                i = j;
+            }
+            if (parts.size() >= 9) {
+                const Atom &a = newMolecule.atoms[atomIndex];
+                char buf[64];
+                std::snprintf(buf, sizeof buf, "%.4f", a.Position.X); parts[2] = buf;
+                std::snprintf(buf, sizeof buf, "%.4f", a.Position.Y); parts[3] = buf;
+                std::snprintf(buf, sizeof buf, "%.4f", a.Position.Z); parts[4] = buf;
+                for (size_t k = 0; k < parts.size(); ++k) { if (k) acc += ' '; acc += parts[k]; }
+                acc += '\n';
+                ++atomIndex;
+            } else { acc += line; acc += '\n'; }
+        } else { acc += line; acc += '\n'; }
+    }
+    if (atomIndex != newMolecule.atoms.size()) throw GoPanic("mismatch between number of atoms in molecule and file");   // before Flush: nothing written
+    out << acc;
+}
+
+// plotting.go:109-121 -- note minEnergy starts at 0.0: only a negative energy can displace index 0
+size_t SaveMinimumEnergyLigand(const std::vector<double> &energyList, const std::vector<std::string> &ligandFiles, const std::string &fileName,
+                               const std::vector<Molecule> &minLigands) {
+    size_t minIndex = 0;
+    double minEnergy = 0.0;
+    for (size_t i = 0; i < energyList.size(); ++i)
+        if (energyList[i] < minEnergy) { minIndex = i; minEnergy = energyList[i]; }
+    if (minIndex >= ligandFiles.size() || minIndex >= minLigands.size()) throw GoPanic("runtime error: index out of range");
+    UpdateMol2Coordinates(ligandFiles[minIndex], fileName, minLigands[minIndex]);
+    std::cout << "Wrote min ligand file to " << fileName;
+    return minIndex;
 }
 
 std::vector<std::string> findFilesWithSubstring(const std::string &rootDir, const std::string &searchString) {
@@ -306,7 +482,12 @@ int RunMultipleLigands(const std::string &dir) {
     if (ligandFiles.size() < 5) throw GoPanic("runtime error: slice bounds out of range [:5]");
     ligandFiles.resize(5);
     std::vector<Molecule> ligands;
-    for (auto &f : ligandFiles) ligands.push_back(ParseMol2(f));
+    {
+        std::vector<int64_t> off;
+        std::vector<Atom> flat;
+        ParseMol2Batch(ligandFiles, off, flat, 0);
+        for (size_t i = 0; i < ligandFiles.size(); ++i) ligands.push_back(Molecule{{flat.begin() + off[i], flat.begin() + off[i + 1]}});
+    }
     const std::string proteinFile = "223l_protein.mol2";
     const Molecule protein = ParseMol2(dir + "/" + proteinFile);
     std::cout << "Starting simulation" << std::endl;
@@ -316,6 +497,54 @@ int RunMultipleLigands(const std::string &dir) {
     std::cout << "Time taken for simulation:  " << sec << "s" << std::endl;
     // plotting.go (gonum PNG) is out of scope; the label -> energy table it plots is printed instead
     for (size_t i = 0; i < ligandFiles.size(); ++i) std::printf("%s %.6f\n", ExtractFileLabel(ligandFiles[i]).c_str(), res.second[i]);
+    const std::string proteinPDB = ExtractFileLabel(proteinFile);
+    const std::string outputDir = "Output/" + proteinPDB + "/";                // main.go:152-154
+    std::error_code ec;
+    std::filesystem::create_directories(outputDir, ec);
+    if (ec) throw GoPanic("mkdir " + outputDir + ": " + ec.message());
+    SaveMinimumEnergyLigand(res.second, ligandFiles, outputDir + "minLigand_" + proteinFile, res.first);      // main.go:157
+    std::cout << std::endl;
+    return 0;
+}
+
+// Screen-scale entry: every *ligand* mol2 file under `ligandDir` against one protein -- parallel ingest into the
+// CSR staging buffers, one resident screen (chains, replica pick, SaveMinimumEnergyLigand's argmin on the device), the
+// winner's mol2 rewritten by UpdateMol2Coordinates, the energies as the Shiny CSV (header BindingEnergy, %.6f).
+int RunScreen(const std::string &proteinFile, const std::string &ligandDir, const std::string &outputDir, int iterations, int numProcs) {
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ligandFiles = findFilesWithSubstring(ligandDir, "ligand");
+    if (ligandFiles.empty()) throw GoPanic("no ligand files under " + ligandDir);
+    if (numProcs <= 0) throw GoPanic("runtime error: integer divide by zero");
+    const Molecule protein = ParseMol2(proteinFile);
+    std::vector<int64_t> offsets;
+    std::vector<Atom> flat;
+    ParseMol2Batch(ligandFiles, offsets, flat, 0);
+    const double t_parse = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    Receptor rec(protein);
+    ddd_params p = params();
+    const uint64_t seed = next_seed();
+    ddd_screen *scr = nullptr;
+    check(ddd_screen_create(rec.h, offsets.data(), ptr(flat), (int64_t)ligandFiles.size(), numProcs, 0, &scr));
+    struct Guard { ddd_screen *s; ~Guard() { ddd_screen_destroy(s); } } guard{scr};
+    check(ddd_screen_run(scr, iterations / numProcs, 1, TEMPERATURE, &p, seed));
+    std::vector<Atom> out(flat.size());
+    std::vector<double> energy(ligandFiles.size());
+    check(ddd_screen_pick(scr, TEMPERATURE, seed, 0, ptr(out), energy.data(), nullptr, nullptr));
+    int64_t minIndex = 0;
+    double minEnergy = 0;
+    check(ddd_screen_argmin(scr, DDD_ARGMIN_SAVE_MIN_LIGAND, &minIndex, &minEnergy));       // plotting.go:109-121 on the device
+    const double t_gpu = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() - t_parse;
+    std::error_code ec;
+    std::filesystem::create_directories(outputDir, ec);
+    Molecule best{{out.begin() + offsets[(size_t)minIndex], out.begin() + offsets[(size_t)minIndex + 1]}};
+    const std::string minFile = outputDir + "/minLigand_" + std::filesystem::path(proteinFile).filename().string();
+    UpdateMol2Coordinates(ligandFiles[(size_t)minIndex], minFile, best);
+    std::ofstream csv(outputDir + "/simulations.csv");
+    csv << "BindingEnergy\n";
+    char buf[64];
+    for (double e : energy) { std::snprintf(buf, sizeof buf, "%.6f", e); csv << buf << "\n"; }
+    std::printf("screen: %zu ligands (%lld atoms) parsed in %.3f s, minimised in %.3f s; min ligand %s (%.6f) -> %s\n", ligandFiles.size(),
+                (long long)offsets.back(), t_parse, t_gpu, ExtractFileLabel(ligandFiles[(size_t)minIndex]).c_str(), minEnergy, minFile.c_str());
     return 0;
 }
 

@@ -81,12 +81,18 @@ double average(const std::vector<double> &arr);                                 
 
 // ---- parsing.go / plotting.go helpers on the path
 Molecule ParseMol2(const std::string &filename);                                                            // parsing.go:50
+// screen-scale ingest: all files parsed on host threads straight into the C ABI's CSR staging buffers (threads <= 0: all cores)
+void ParseMol2Batch(const std::vector<std::string> &files, std::vector<int64_t> &offsets, std::vector<Atom> &flat, int threads);
 std::vector<std::string> findFilesWithSubstring(const std::string &rootDir, const std::string &searchString);   // parsing.go:142
 std::string ExtractFileLabel(const std::string &filePath);                                                  // plotting.go:95
+void UpdateMol2Coordinates(const std::string &originalFile, const std::string &updatedFile, const Molecule &newMolecule);       // plotting.go:126
+size_t SaveMinimumEnergyLigand(const std::vector<double> &energyList, const std::vector<std::string> &ligandFiles, const std::string &fileName,
+                               const std::vector<Molecule> &minLigands);                                  // plotting.go:109 (returns minIndex)
 
 // ---- main.go entry points
 int RunMultipleLigands(const std::string &dir);                                                             // main.go:125
 int TestMethodRMSD(const std::string &dir);                                                                 // main.go:116
 int RShinyAppMain(const std::vector<std::string> &args);                                                    // main.go:21 (argv -> ../output/simulations.csv)
+int RunScreen(const std::string &proteinFile, const std::string &ligandDir, const std::string &outputDir, int iterations, int numProcs);   // screen-scale driver (no reference row)
 
 }  // namespace ddd_host

@@ -16,6 +16,7 @@ from __future__ import annotations
 import math
 import os
 import random as _random
+import sys
 from dataclasses import dataclass
 from pathlib import Path
 
@@ -127,12 +128,35 @@ def _ensure_init():
         capi.init()
 
 
+def _warn_if_truncated(where):
+    """A chain that needed more than max_retries collision retries in one step stopped there; the reference would still be
+    retrying (metropolis.go:155, :173): say so instead of returning a truncated chain silently."""
+    bits, n = capi.last_chain_status()
+    if bits & capi.STATUS_RETRY_LIMIT:
+        print(f"ddd_mc warning: {n} chain(s) of {where} stopped at the collision-retry bound; the reference would still be "
+              "retrying there (metropolis.go:173)", file=sys.stderr)
+
+
 # ---------------------------------------------------------------- metropolis.go, device-backed
 def SimulateMultipleLigands(protein, ligands, iterations, rotate, temperature, numProcs):
     """metropolis.go:11-22 (serial variant: ShiftLigandCloserByThreshold pre-pass, then per ligand)."""
-    for i, ligand in enumerate(ligands):
-        ligands[i] = ShiftLigandCloserByThreshold(ligand, protein, THRESHOLD)       # :14-16, in place
-    return SimulateMultipleLigandsParallel(protein, ligands, iterations, rotate, temperature, numProcs)
+    if numProcs <= 0:
+        raise ZeroDivisionError("integer divide by zero")        # :97
+    _ensure_init()
+    offsets, xyzq = capi.pack_ligands([l.xyzq for l in ligands])
+    seed = _next_seed()
+    with capi.Receptor(protein.xyzq, cached=True) as rec:
+        scr = capi.Screen(rec, offsets, xyzq, numProcs)
+        try:                                                     # one upload: shift, chains, replica pick and gather stay resident
+            scr.shift_closer(THRESHOLD)                          # :14-16
+            shifted = scr.download_start()
+            for i, ligand in enumerate(ligands):                 # the reference shifts the caller's atoms in place (alias)
+                ligand.xyzq[:] = shifted[offsets[i]:offsets[i + 1]]
+            scr.run(iterations // numProcs, rotate, temperature, _params(), seed=seed)      # :17-18
+            out, energy, _, _ = scr.pick(temperature, seed=seed)                            # :102-109, :19
+        finally:
+            scr.close()
+    return [Molecule(xyzq=x) for x in capi.unpack_ligands(offsets, out)], [float(e) for e in energy]
 
 
 def SimulateMultipleLigandsParallel(protein, ligands, iterations, rotate, temperature, numProcs):
@@ -142,9 +166,10 @@ def SimulateMultipleLigandsParallel(protein, ligands, iterations, rotate, temper
         raise ZeroDivisionError("integer divide by zero")        # Go: len(ligands)/numProcs panics (:34)
     _ensure_init()
     offsets, xyzq = capi.pack_ligands([l.xyzq for l in ligands])
-    with capi.Receptor(protein.xyzq) as rec:
+    with capi.Receptor(protein.xyzq, cached=True) as rec:
         out, energy, _ = capi.minimize_batch(rec, offsets, xyzq, iterations, rotate, temperature, numProcs,
                                              _params(), seed=_next_seed())
+    _warn_if_truncated("SimulateMultipleLigandsParallel")
     return [Molecule(xyzq=x) for x in capi.unpack_ligands(offsets, out)], [float(e) for e in energy]
 
 
@@ -166,9 +191,10 @@ def SimulateEnergyMinimizationParallel(protein, ligand, iterations, rotate, temp
 def _one_chain(protein, ligand, iterations, rotate, temperature):
     _ensure_init()
     offsets, xyzq = capi.pack_ligands([ligand.xyzq])
-    with capi.Receptor(protein.xyzq) as rec:
+    with capi.Receptor(protein.xyzq, cached=True) as rec:
         poses, stats, _ = capi.run_chains(rec, offsets, xyzq, 1, iterations, rotate, temperature, _params(),
                                           seed=_next_seed())
+    _warn_if_truncated("SimulateEnergyMinimizationOneProc")
     return Molecule(xyzq=poses)
 
 
@@ -188,7 +214,7 @@ def CalculateEnergy(protein, ligand) -> float:
     """metropolis.go:247-262, evaluated on device in fp64 with the reference's per-term arithmetic."""
     _ensure_init()
     offsets, xyzq = capi.pack_ligands([ligand.xyzq])
-    with capi.Receptor(protein.xyzq) as rec:
+    with capi.Receptor(protein.xyzq, cached=True) as rec:
         e = capi.energy_batch(rec, offsets, xyzq, capi.default_params(precision=capi.PRECISION_F64))
     return float(e[0])
 
@@ -197,7 +223,7 @@ def FindClosestAtomDistance(ligand, protein):
     """metropolis.go:290-304 -> (distance, ligand atom Position3d, protein atom Position3d)."""
     _ensure_init()
     offsets, xyzq = capi.pack_ligands([ligand.xyzq])
-    with capi.Receptor(protein.xyzq) as rec:
+    with capi.Receptor(protein.xyzq, cached=True) as rec:
         d, li, pj = capi.closest_atom_batch(rec, offsets, xyzq)
     lpos = Position3d(*ligand.xyzq[li[0], :3]) if li[0] >= 0 else Position3d()
     ppos = Position3d(*protein.xyzq[pj[0], :3]) if pj[0] >= 0 else Position3d()
@@ -208,7 +234,7 @@ def ShiftLigandCloserByThreshold(ligand, protein, threshold):
     """metropolis.go:267-285; mutates the ligand's atoms in place and returns the same Molecule."""
     _ensure_init()
     offsets, xyzq = capi.pack_ligands([ligand.xyzq])
-    with capi.Receptor(protein.xyzq) as rec:
+    with capi.Receptor(protein.xyzq, cached=True) as rec:
         ligand.xyzq[:] = capi.shift_closer_batch(rec, offsets, xyzq, threshold)
     return ligand
 
@@ -319,10 +345,20 @@ def RandomizeLigandPose(ligand, rand=None):
 
 def CompareRMSD(protein, ligand, iterations, rotate, temperature, numProcs) -> float:
     """validateResults.go:40-45."""
-    reference = CopyLigand(ligand)
-    ligand = RandomizeLigandPose(ligand)
-    simulated = SimulateEnergyMinimizationParallel(protein, ligand, iterations, rotate, temperature, numProcs)
-    return CalculateRMSD(simulated, reference)
+    if numProcs <= 0:
+        raise ZeroDivisionError("integer divide by zero")
+    _ensure_init()
+    offsets, xyzq = capi.pack_ligands([ligand.xyzq])
+    seed = _next_seed()
+    with capi.Receptor(protein.xyzq, cached=True) as rec:
+        scr = capi.Screen(rec, offsets, xyzq, numProcs)          # the uploaded pose stays resident as the reference (:41)
+        try:
+            scr.randomize(seed=seed)                             # :42
+            scr.run(iterations // numProcs, rotate, temperature, _params(), seed=seed)       # :43
+            _, _, _, rmsd = scr.pick(temperature, seed=seed)     # :44 CalculateRMSD(simulated, reference)
+        finally:
+            scr.close()
+    return float(rmsd[0])
 
 
 def average(arr) -> float:
@@ -358,6 +394,64 @@ def ParseMol2(filename) -> Molecule:
                 continue
             rows.append([num(fields[2]), num(fields[3]), num(fields[4]), num(fields[-1])])
     return Molecule(xyzq=np.array(rows, dtype=np.float64).reshape(-1, 4))
+
+
+def ParseMol2Batch(filenames, threads=0):
+    """Screen-scale ingest: the files parsed on a thread pool straight into the C ABI's CSR staging buffers ->
+    (offsets int64[n+1], xyzq float64[sum, 4]), same order as `filenames`."""
+    from concurrent.futures import ThreadPoolExecutor
+    if not filenames:
+        return np.zeros(1, dtype=np.int64), np.zeros((0, 4))
+    with ThreadPoolExecutor(max_workers=threads or (os.cpu_count() or 1)) as pool:
+        mols = list(pool.map(lambda f: ParseMol2(f).xyzq, filenames))
+    return capi.pack_ligands(mols)
+
+
+def UpdateMol2Coordinates(originalFile, updatedFile, newMolecule) -> None:
+    """plotting.go:126-189: rewrite the ATOM section's x/y/z ("%.4f") with the molecule's coordinates, fields re-joined by single
+    spaces (strings.Join), every other line copied; raises when the atom counts differ (nothing is written then: the
+    reference returns before Flush)."""
+    with open(originalFile, "r", newline="") as fh:
+        lines = fh.read().split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()
+    out, atomIndex, inAtomSection = [], 0, False
+    n = len(newMolecule)
+    for line in lines:
+        line = line[:-1] if line.endswith("\r") else line          # bufio.ScanLines drops a trailing \r
+        if line.startswith("@<TRIPOS>ATOM"):
+            inAtomSection = True
+            out.append(line)
+            continue
+        elif line.startswith("@<TRIPOS>") and inAtomSection:
+            inAtomSection = False
+        if inAtomSection and atomIndex < n:
+            parts = line.split()
+            if len(parts) >= 9:
+                x, y, z = newMolecule.xyzq[atomIndex, :3]
+                parts[2], parts[3], parts[4] = "%.4f" % x, "%.4f" % y, "%.4f" % z
+                out.append(" ".join(parts))
+                atomIndex += 1
+            else:
+                out.append(line)
+        else:
+            out.append(line)
+    if atomIndex != n:
+        open(updatedFile, "w").close()                           # os.Create ran before the scan: an empty file is left behind
+        raise ValueError("mismatch between number of atoms in molecule and file")
+    with open(updatedFile, "w", newline="") as fh:
+        fh.write("".join(l + "\n" for l in out))
+
+
+def SaveMinimumEnergyLigand(energyList, ligandFiles, fileName, minLigands) -> int:
+    """plotting.go:109-121 (minEnergy starts at 0.0: only a negative energy can displace index 0); returns minIndex."""
+    minIndex, minEnergy = 0, 0.0
+    for i, energy in enumerate(energyList):
+        if energy < minEnergy:
+            minIndex, minEnergy = i, energy
+    UpdateMol2Coordinates(ligandFiles[minIndex], fileName, minLigands[minIndex])
+    print(f"Wrote min ligand file to {fileName}", end="")
+    return minIndex
 
 
 def ParseMol2Types(filename) -> list:

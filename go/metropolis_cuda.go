@@ -3,10 +3,14 @@
 // through the C ABI of libddd_mc.so (include/ddd_mc.h).
 //
 // HOW TO USE (INTEGRATION.md has the full recipe):
-//   1. copy this file and ddd_mc.h next to the reference's main.go / datatypes.go / parsing.go / plotting.go /
-//      validateResults.go, and DELETE metropolis.go (every function it defined is re-defined here with the same
-//      signature) and the body of CalculateRMSD in validateResults.go (see validate_cuda.go);
-//   2. CGO_LDFLAGS="-L<repo>/drug-design-dynamics_b200/csrc -lddd_mc" go build
+//   1. python go/strip_heavy.py <reference>/metropolisMethod/metropolis.go > metropolis_helpers.go
+//      -- this keeps the reference's OWN scalar helpers (AcceptMove, JitterLigand, JitterAndRotateLigand, RotateLigand,
+//      RotateAtom, IsCollisionFree, Distance, CopyLigand) byte for byte and removes only the functions re-defined below, so
+//      this overlay carries no line of the reference;
+//   2. put metropolis_helpers.go, this file, validate_cuda.go and ddd_mc.h next to the reference's main.go / datatypes.go /
+//      parsing.go / plotting.go / validateResults.go, delete metropolis.go, and delete the bodies of CalculateRMSD and
+//      CompareRMSD in validateResults.go (validate_cuda.go re-defines them);
+//   3. CGO_LDFLAGS="-L<repo>/drug-design-dynamics_b200/csrc -lddd_mc" go build
 //   main.go, the tests in metropolis_test.go and the R Shiny driver (argv -> ../output/simulations.csv) run unchanged.
 //
 // STATUS: written against go1.23 / cgo rules but NOT COMPILED in the build container (no Go toolchain there,
@@ -20,7 +24,11 @@
 //     numProcs x numProcs goroutines (metropolis.go:27-51, :94-111); results come back in input order.
 //   - every replica chain starts from a private copy of the ligand, which removes the reference's data race on the
 //     shared backing array (SURVEY.md F5); the replica pick (:102-109) runs in replica-index order.
-//   - the scalar helpers (AcceptMove, RotateAtom, Distance, JitterLigand, ...) stay pure Go, as in the reference.
+//   - the scalar helpers (AcceptMove, RotateAtom, Distance, JitterLigand, ...) stay the reference's own Go code
+//     (metropolis_helpers.go, produced by go/strip_heavy.py); a kernel launch for them would be absurd (SURVEY.md 8b).
+//   - the protein arrives on every call: the library's content-keyed receptor cache (ddd_receptor_acquire) keeps it resident,
+//     so CalculateEnergy / FindClosestAtomDistance / ShiftLigandCloserByThreshold and RShinyAppMain's per-ligand loop
+//     (main.go:42-48) do not rebuild it.
 package main
 
 /*
@@ -32,8 +40,9 @@ package main
 import "C"
 
 import (
-	"math"
+	"fmt"
 	"math/rand"
+	"os"
 	"sync"
 	"sync/atomic"
 	"unsafe"
@@ -80,14 +89,26 @@ func atomsPtr(m Molecule) *C.double {
 
 type dddReceptor struct{ h *C.ddd_receptor }
 
+// newReceptor borrows the resident copy of `protein` from the library's content-keyed cache (built on first use).
 func newReceptor(protein Molecule) dddReceptor {
 	dddInit()
 	var r dddReceptor
-	dddCheck(C.ddd_receptor_create(atomsPtr(protein), C.int64_t(len(protein.atoms)), &r.h))
+	dddCheck(C.ddd_receptor_acquire(atomsPtr(protein), C.int64_t(len(protein.atoms)), &r.h))
 	return r
 }
 
-func (r dddReceptor) close() { C.ddd_receptor_destroy(r.h) }
+func (r dddReceptor) close() { C.ddd_receptor_release(r.h) }
+
+// dddWarnIfTruncated: a chain that needed more than max_retries collision retries in ONE step stopped there; the reference
+// would still be retrying (metropolis.go:155, :173).  Say so instead of returning a truncated chain silently.
+// (cgo calls stay on one OS thread from entry to return, and the status is thread-local in the library: call this right
+// after the batch call, in the same goroutine, with the thread locked.)
+func dddWarnIfTruncated(where string) {
+	var n C.int64_t
+	if bits := C.ddd_last_chain_status(&n); bits&C.DDD_STATUS_RETRY_LIMIT != 0 {
+		fmt.Fprintf(os.Stderr, "ddd_mc warning: %d chain(s) of %s stopped at the collision-retry bound; the reference would still be retrying there (metropolis.go:173)\n", int64(n), where)
+	}
+}
 
 // packLigands flattens []Molecule into the CSR batch of the C ABI (one contiguous []Atom + offsets).
 func packLigands(ligands []Molecule) ([]C.int64_t, []Atom) {
@@ -111,12 +132,42 @@ func flatPtr(a []Atom) *C.double {
 	return (*C.double)(unsafe.Pointer(&a[0]))
 }
 
-// SimulateMultipleLigands: metropolis.go:11-22 (serial variant: shift every ligand first, in place).
+// SimulateMultipleLigands: metropolis.go:11-22 (serial variant: shift every ligand first, in place, then minimise).
+// One upload: the shift (:14-16), the chains, the replica pick (:102-109) and the gather run on the resident screen.
 func SimulateMultipleLigands(protein Molecule, ligands []Molecule, iterations int, rotate bool, temperature float64, numProcs int) ([]Molecule, []float64) {
-	for i, ligand := range ligands {
-		ligands[i] = ShiftLigandCloserByThreshold(ligand, protein, THRESHOLD)
+	width := iterations / numProcs // panics with "integer divide by zero" when numProcs == 0, like :97
+	rec := newReceptor(protein)
+	defer rec.close()
+	offsets, flat := packLigands(ligands)
+	out := make([]Atom, len(flat))
+	energy := make([]float64, len(ligands))
+	if len(ligands) == 0 {
+		return []Molecule{}, energy
 	}
-	return SimulateMultipleLigandsParallel(protein, ligands, iterations, rotate, temperature, numProcs)
+	p := dddParams()
+	seed := C.uint64_t(dddNextSeed())
+	var scr *C.ddd_screen
+	dddCheck(C.ddd_screen_create(rec.h, &offsets[0], flatPtr(flat), C.int64_t(len(ligands)), C.int32_t(numProcs), 0, &scr))
+	defer C.ddd_screen_destroy(scr)
+	dddCheck(C.ddd_screen_shift_closer(scr, C.double(THRESHOLD)))
+	dddCheck(C.ddd_screen_download_start(scr, flatPtr(flat)))
+	for i := range ligands { // the reference shifts the caller's atoms in place (slice alias, SURVEY F4)
+		copy(ligands[i].atoms, flat[offsets[i]:offsets[i+1]])
+	}
+	dddCheck(C.ddd_screen_run(scr, C.int64_t(width), boolToC(rotate), C.double(temperature), &p, seed))
+	dddCheck(C.ddd_screen_pick(scr, C.double(temperature), seed, 0, flatPtr(out), (*C.double)(unsafe.Pointer(&energy[0])), nil, nil))
+	minLigands := make([]Molecule, len(ligands))
+	for i := range ligands {
+		minLigands[i] = Molecule{atoms: out[offsets[i]:offsets[i+1]:offsets[i+1]]}
+	}
+	return minLigands, energy
+}
+
+func boolToC(b bool) C.int32_t {
+	if b {
+		return 1
+	}
+	return 0
 }
 
 // SimulateMultipleLigandsParallel: metropolis.go:27-51 + :56-67 + :94-111 in one ddd_minimize_batch call.
@@ -136,6 +187,7 @@ func SimulateMultipleLigandsParallel(protein Molecule, ligands []Molecule, itera
 		var ePtr *C.double = (*C.double)(unsafe.Pointer(&energy[0]))
 		dddCheck(C.ddd_minimize_batch(rec.h, &offsets[0], flatPtr(flat), C.int64_t(len(ligands)), C.int64_t(iterations), rot,
 			C.double(temperature), C.int32_t(numProcs), &p, C.uint64_t(dddNextSeed()), 0, flatPtr(out), ePtr, nil, nil))
+		dddWarnIfTruncated("SimulateMultipleLigandsParallel")
 	}
 	minLigands := make([]Molecule, len(ligands))
 	for i := range ligands {
@@ -169,6 +221,7 @@ func runOneChain(protein, ligand Molecule, iterations int, rotate bool, temperat
 	}
 	dddCheck(C.ddd_run_chains(rec.h, &offsets[0], atomsPtr(ligand), 1, 1, C.int64_t(iterations), rot, C.double(temperature),
 		&p, C.uint64_t(dddNextSeed()), 0, nil, nil, flatPtr(out), &st, nil))
+	dddWarnIfTruncated("SimulateEnergyMinimizationOneProc")
 	return Molecule{atoms: out}
 }
 
@@ -216,96 +269,4 @@ func ShiftLigandCloserByThreshold(ligand, protein Molecule, threshold float64) M
 	offsets := []C.int64_t{0, C.int64_t(len(ligand.atoms))}
 	dddCheck(C.ddd_shift_closer_batch(rec.h, &offsets[0], atomsPtr(ligand), 1, C.double(threshold)))
 	return ligand
-}
-
-// ---- scalar helpers: unchanged host code (a kernel launch for these would be absurd, SURVEY.md 8b) ----
-
-// AcceptMove: metropolis.go:141-149.
-func AcceptMove(currentEnergy, newEnergy, temperature float64) bool {
-	if newEnergy < currentEnergy {
-		return true
-	}
-	deltaE := newEnergy - currentEnergy
-	probability := math.Exp(-deltaE / temperature)
-	return rand.Float64() < probability
-}
-
-// JitterLigand: metropolis.go:154-167.
-func JitterLigand(ligand Molecule, minDistance float64) Molecule {
-	for {
-		newLigand := ligand
-		for i := range newLigand.atoms {
-			newLigand.atoms[i].Position.X += (rand.Float64() - 0.5) * 0.1
-			newLigand.atoms[i].Position.Y += (rand.Float64() - 0.5) * 0.1
-			newLigand.atoms[i].Position.Z += (rand.Float64() - 0.5) * 0.1
-		}
-		if IsCollisionFree(newLigand, minDistance) {
-			return newLigand
-		}
-	}
-}
-
-// JitterAndRotateLigand: metropolis.go:172-184.
-func JitterAndRotateLigand(ligand Molecule, minDistance float64, maxAngle float64) Molecule {
-	for {
-		newLigand := RotateLigand(ligand, maxAngle)
-		for i := range newLigand.atoms {
-			newLigand.atoms[i].Position.X += (rand.Float64() - 0.5) * 0.1
-			newLigand.atoms[i].Position.Y += (rand.Float64() - 0.5) * 0.1
-			newLigand.atoms[i].Position.Z += (rand.Float64() - 0.5) * 0.1
-		}
-		if IsCollisionFree(newLigand, minDistance) {
-			return newLigand
-		}
-	}
-}
-
-// RotateLigand: metropolis.go:189-208.
-func RotateLigand(ligand Molecule, maxAngle float64) Molecule {
-	newLigand := ligand
-	axis := Position3d{X: rand.Float64()*2 - 1, Y: rand.Float64()*2 - 1, Z: rand.Float64()*2 - 1}
-	axis.Normalize()
-	theta := (rand.Float64()*2 - 1) * maxAngle
-	for i := range newLigand.atoms {
-		newLigand.atoms[i].Position = RotateAtom(newLigand.atoms[i].Position, axis, theta)
-	}
-	return newLigand
-}
-
-// RotateAtom: metropolis.go:213-224.
-func RotateAtom(pos, axis Position3d, theta float64) Position3d {
-	cosTheta := math.Cos(theta)
-	sinTheta := math.Sin(theta)
-	dot := pos.Dot(axis)
-	x := pos.X*cosTheta + sinTheta*(axis.Y*pos.Z-axis.Z*pos.Y) + axis.X*dot*(1-cosTheta)
-	y := pos.Y*cosTheta + sinTheta*(axis.Z*pos.X-axis.X*pos.Z) + axis.Y*dot*(1-cosTheta)
-	z := pos.Z*cosTheta + sinTheta*(axis.X*pos.Y-axis.Y*pos.X) + axis.Z*dot*(1-cosTheta)
-	return Position3d{X: x, Y: y, Z: z}
-}
-
-// IsCollisionFree: metropolis.go:229-242.
-func IsCollisionFree(ligand Molecule, minDistance float64) bool {
-	for i := 0; i < len(ligand.atoms); i++ {
-		for j := i + 1; j < len(ligand.atoms); j++ {
-			if Distance(ligand.atoms[i].Position, ligand.atoms[j].Position) < minDistance {
-				return false
-			}
-		}
-	}
-	return true
-}
-
-// Distance: metropolis.go:309-314.
-func Distance(a, b Position3d) float64 {
-	dx := a.X - b.X
-	dy := a.Y - b.Y
-	dz := a.Z - b.Z
-	return math.Sqrt(dx*dx + dy*dy + dz*dz)
-}
-
-// CopyLigand: metropolis.go:319-334.
-func CopyLigand(ligand Molecule) Molecule {
-	newAtoms := make([]Atom, len(ligand.atoms))
-	copy(newAtoms, ligand.atoms)
-	return Molecule{atoms: newAtoms}
 }
