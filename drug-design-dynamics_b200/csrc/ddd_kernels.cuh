@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <stdio.h>
 
 namespace ddd {
 
@@ -197,21 +198,22 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
 // 3 FADD2, FMUL2 + 2 FFMA2 (d^2), 2 MUFU.RSQ, 2 FMNMX (clamp d >= 1e-6 <=> 1/d <= 1e6), FFMA2
 // (s += q_l / d): 11 issue slots per 2 pair terms.  MUFU (16/clk/SM) is the binding pipe.
 // q_p is applied once per tile and K once per call.  An odd ligand is padded with a q = 0 atom.
-// CUT (the cutoff extension): every term becomes max(min(1/d, 1/clamp) - 1/cutoff, 0) -- the shifted Coulomb term, which
-// is exactly 0 from the cutoff outwards, so no distance compare is needed: + 1 FADD2 and 2 FMNMX per ligand pair.
+// CUT (the cutoff extension): every term is the shifted Coulomb term q_l (max(min(1/d, 1/clamp), 1/cutoff) - 1/cutoff), which is
+// exactly 0 from the cutoff outwards, so no distance compare is needed.  The loop sums q_l * max(.., 1/cutoff) (2 FMNMX per
+// ligand pair on top of the plain loop) and the constant part, (1/cutoff) * sum_l q_l = `rc_q`, is subtracted once per
+// receptor atom at the end.
 // `ubase[a]` is the first atom of the a-th unit of 32 receptor atoms this call covers (units need not be adjacent).
 // CLAMP = false drops the two FMNMX of the d >= 1e-6 clamp (:255-257): the caller has established that no atom of these
 // units can be within the clamp distance of the ligand (their boxes are apart), so min(1/d, 1/clamp) == 1/d bit for bit.
 template <int A, bool CUT, bool CLAMP = true>
 __device__ __forceinline__ float warp_atoms_sum_f32(const float4 (&P)[A], const ulonglong2 *__restrict__ lf2, int n_pairs,
-                                                    float rinv_max, float rc_inv, float *t_lo = nullptr) {
+                                                    float rinv_max, float rc_inv, float *t_lo = nullptr, float rc_q = 0.f) {
     f32x2 px[A], py[A], pz[A], s[A];
 #pragma unroll
     for (int a = 0; a < A; ++a) {
         px[a] = pack2(P[a].x, P[a].x); py[a] = pack2(P[a].y, P[a].y); pz[a] = pack2(P[a].z, P[a].z);
         s[a] = pack2(0.f, 0.f);
     }
-    const f32x2 m_rc = pack2(-rc_inv, -rc_inv);
     constexpr int kPairUnroll = A >= 8 ? 1 : 2;          // measured: 8 atoms per lane already fill the pipes
 #pragma unroll kPairUnroll
     for (int k = 0; k < n_pairs; ++k) {
@@ -224,10 +226,7 @@ __device__ __forceinline__ float warp_atoms_sum_f32(const float4 (&P)[A], const 
             unpack2(d2, d2a, d2b);
             float ra = rsqrt_approx(d2a), rb = rsqrt_approx(d2b);
             if (CLAMP) { ra = fminf(ra, rinv_max); rb = fminf(rb, rinv_max); }
-            if (CUT) {
-                unpack2(add2(pack2(ra, rb), m_rc), ra, rb);
-                ra = fmaxf(ra, 0.f); rb = fmaxf(rb, 0.f);
-            }
+            if (CUT) { ra = fmaxf(ra, rc_inv); rb = fmaxf(rb, rc_inv); }
             s[a] = fma2(Lzq.y, pack2(ra, rb), s[a]);
         }
     }
@@ -235,7 +234,8 @@ __device__ __forceinline__ float warp_atoms_sum_f32(const float4 (&P)[A], const 
 #pragma unroll
     for (int a = 0; a < A; ++a) {
         if (A == 8 && a == 4 && t_lo) { *t_lo = t; t = 0.f; }           // 8 atoms per lane = two groups of 4, summed separately
-        float sa, sb; unpack2(s[a], sa, sb); t = fmaf(P[a].w, sa + sb, t);
+        float sa, sb; unpack2(s[a], sa, sb);
+        t = fmaf(P[a].w, CUT ? (sa + sb) - rc_q : sa + sb, t);
     }
     return t;
 }
@@ -299,21 +299,21 @@ __device__ __forceinline__ float warp_units_sum_lj_f32(const float4 *__restrict_
 template <int A, bool CUT, bool CLAMP = true>
 __device__ __forceinline__ float warp_units_sum_f32(const float4 *__restrict__ rec, const int (&ubase)[A],
                                                     const ulonglong2 *__restrict__ lf2, int n_pairs, float rinv_max, float rc_inv,
-                                                    float *t_lo = nullptr) {
+                                                    float *t_lo = nullptr, float rc_q = 0.f) {
     float4 P[A];
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int a = 0; a < A; ++a) P[a] = __ldg(rec + ubase[a] + lane);
-    return warp_atoms_sum_f32<A, CUT, CLAMP>(P, lf2, n_pairs, rinv_max, rc_inv, t_lo);
+    return warp_atoms_sum_f32<A, CUT, CLAMP>(P, lf2, n_pairs, rinv_max, rc_inv, t_lo, rc_q);
 }
 
 template <int A, bool CUT = false>
 __device__ __forceinline__ float warp_tile_sum_f32(const float4 *__restrict__ rec, int base,
-                                                   const ulonglong2 *__restrict__ lf2, int n_pairs, float rinv_max, float rc_inv = 0.f) {
+                                                   const ulonglong2 *__restrict__ lf2, int n_pairs, float rinv_max, float rc_inv = 0.f, float rc_q = 0.f) {
     int ub[A];
 #pragma unroll
     for (int a = 0; a < A; ++a) ub[a] = base + a * 32;
-    return warp_units_sum_f32<A, CUT>(rec, ub, lf2, n_pairs, rinv_max, rc_inv);
+    return warp_units_sum_f32<A, CUT>(rec, ub, lf2, n_pairs, rinv_max, rc_inv, nullptr, rc_q);
 }
 
 // sum_p sum_l q_p q_l / max(d, clamp) for the whole CTA, returned to every thread (K applied by the caller).
@@ -330,14 +330,14 @@ __host__ __device__ constexpr int max_items(int threads) { return threads > 32 ?
 #endif
 template <int THREADS, bool CUT = false>
 __device__ __forceinline__ double cta_pair_sum_f32(const RecView &rv, const float4 *lf, int nl, float rinv_max,
-                                                   int *ctl, double *item_out, double *red, int &parity, float rc_inv = 0.f) {
+                                                   int *ctl, double *item_out, double *red, int &parity, float rc_inv = 0.f, float rc_q = 0.f) {
     const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
     const int n_pairs = (nl + 1) >> 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_wt = (rv.n + kWarpTile - 1) / kWarpTile;                 // n_pad is a multiple of kRecPad >= kWarpTile
     if (THREADS == 32) {                                                  // one warp: tiles in order, no staging
         double e1 = 0.0;
-        for (int t = 0; t < n_wt; ++t) e1 += (double)warp_tile_sum_f32<kTileA, CUT>(rv.f32, t * kWarpTile, lf2, n_pairs, rinv_max, rc_inv);
+        for (int t = 0; t < n_wt; ++t) e1 += (double)warp_tile_sum_f32<kTileA, CUT>(rv.f32, t * kWarpTile, lf2, n_pairs, rinv_max, rc_inv, rc_q);
         return warp_sum(e1);
     }
     constexpr int kMaxItems = max_items(THREADS) > 0 ? max_items(THREADS) : 1;
@@ -354,7 +354,7 @@ __device__ __forceinline__ double cta_pair_sum_f32(const RecView &rv, const floa
         const int t_end = min((it + 1) * chunk, n_wt);
         double acc = 0.0;
         for (int t = it * chunk; t < t_end; ++t)
-            acc += (double)warp_tile_sum_f32<kTileA, CUT>(rv.f32, t * kWarpTile, lf2, n_pairs, rinv_max, rc_inv);
+            acc += (double)warp_tile_sum_f32<kTileA, CUT>(rv.f32, t * kWarpTile, lf2, n_pairs, rinv_max, rc_inv, rc_q);
         item_out[it * 32 + lane] = acc;                                   // per item AND per lane: no reduction here
     }
     __syncthreads();
@@ -363,6 +363,15 @@ __device__ __forceinline__ double cta_pair_sum_f32(const RecView &rv, const floa
     double e = 0.0;
     for (int it = warp; it < n_items; it += THREADS / 32) e += item_out[it * 32 + lane];
     return block_sum<THREADS>(e, red, parity);
+}
+
+// sum of the ligand's fp32 charges as stored in the pair-packed pose, in atom order (every thread computes the same value):
+// the constant part of the shifted-Coulomb cutoff terms
+__device__ __forceinline__ float ligand_charge_sum_f32(const float4 *lf, int nl) {
+    const float *f = reinterpret_cast<const float *>(lf);
+    float q = 0.f;
+    for (int i = 0; i < nl; ++i) q += f[8 * (i >> 1) + 6 + (i & 1)];
+    return q;
 }
 
 // write atom i of the fp32 pose in the pair-packed layout
@@ -543,6 +552,11 @@ __device__ __forceinline__ void rotate_atom(double &x, double &y, double &z, dou
     x = nx; y = ny; z = nz;
 }
 
+// IEEE fp64 divide / square root as ONE out-of-line copy each: the inline expansions are ~30 instructions per use, and the
+// serial side of the chain kernels is bound by instruction fetch.  Same operations, same bits.
+__device__ __noinline__ double cold_div(double a, double b) { return a / b; }
+__device__ __noinline__ double cold_sqrt(double a) { return sqrt(a); }
+
 // axis draws X,Y,Z (U*2-1), Normalize (no-op at zero magnitude, datatypes.go:33-40), theta draw (:192-200)
 __device__ __forceinline__ void draw_axis_angle(const Stream &st, uint64_t pos, double max_angle, int &status,
                                                 double &ax, double &ay, double &az, double &theta) {
@@ -551,8 +565,8 @@ __device__ __forceinline__ void draw_axis_angle(const Stream &st, uint64_t pos, 
     ax = u[0] * 2 - 1;
     ay = u[1] * 2 - 1;
     az = u[2] * 2 - 1;
-    const double mag = sqrt(ax * ax + ay * ay + az * az);
-    if (mag > 0) { ax /= mag; ay /= mag; az /= mag; }
+    const double mag = cold_sqrt(ax * ax + ay * ay + az * az);
+    if (mag > 0) { ax = cold_div(ax, mag); ay = cold_div(ay, mag); az = cold_div(az, mag); }
     theta = (u[3] * 2 - 1) * max_angle;
 }
 
@@ -772,8 +786,10 @@ __global__ void __launch_bounds__(kThreads) energy_batch_kernel(const EnergyArgs
         part = pair_sum_f64<kThreads, WITH_ABS>(a.rec, s.cx(), s.cy(), s.cz(), s.q(), nl, a.prm.k_coulomb, a.prm.clamp_distance, &ab, a.prm.cutoff);
     }
     if (PRECISE) e = block_sum<kThreads>(part, s.red(), parity);
-    else if (a.prm.cutoff > 0)                          // every unit, no cell list: this entry point is not the hot path
-        e = a.prm.k_coulomb * cta_pair_sum_f32<kThreads, true>(a.rec, s.lf(), nl, a.prm.rinv_max, s.ctl(), s.item_out(), s.red(), parity, a.prm.rc_inv);
+    else if (a.prm.cutoff > 0) {                        // every unit, no cell list: this entry point is not the hot path
+        const float rc_q = a.prm.rc_inv * ligand_charge_sum_f32(s.lf(), nl);
+        e = a.prm.k_coulomb * cta_pair_sum_f32<kThreads, true>(a.rec, s.lf(), nl, a.prm.rinv_max, s.ctl(), s.item_out(), s.red(), parity, a.prm.rc_inv, rc_q);
+    }
     else e = a.prm.k_coulomb * cta_pair_sum_f32<kThreads>(a.rec, s.lf(), nl, a.prm.rinv_max, s.ctl(), s.item_out(), s.red(), parity);
     if (WITH_ABS) ab = block_sum<kThreads>(ab, s.red(), parity);
     if (tid == 0) {
@@ -859,6 +875,33 @@ __global__ void __launch_bounds__(kThreads) closest_atom_kernel(const ClosestArg
 }
 
 // ------------------------------------------------------------------ CalculateRMSD batch (validateResults.go:50-65)
+// sum_i |sim_i - ref_i|^2 over one warp's lane-strided atoms (32-byte Go atoms).  The loads of the first 96 atoms are issued
+// before the first is used (a warp has only 1-3 trips for 20..80-atom ligands, so memory parallelism has to come from here);
+// the additions stay in atom order, so the result does not depend on the batching.
+__device__ __forceinline__ double warp_rmsd_partial(const double4 *__restrict__ s4, const double4 *__restrict__ r4, int n) {
+    const int lane = threadIdx.x & 31;
+    double4 sa[3], ra[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const int i = lane + 32 * t;
+        if (i < n) { sa[t] = s4[i]; ra[t] = r4[i]; }
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        if (lane + 32 * t < n) {
+            const double dx = sa[t].x - ra[t].x, dy = sa[t].y - ra[t].y, dz = sa[t].z - ra[t].z;
+            acc += dx * dx + dy * dy + dz * dz;                               // :58-62
+        }
+    }
+    for (int i = lane + 96; i < n; i += 32) {
+        const double4 a = s4[i], b = r4[i];
+        const double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+        acc += dx * dx + dy * dy + dz * dz;
+    }
+    return acc;
+}
+
 // One warp per (simulated, reference) pair; lane-strided atoms, coalesced; memory-bound.
 __global__ void __launch_bounds__(256) rmsd_batch_kernel(const long long *__restrict__ offsets, long long atom_base,
                                                          const double *__restrict__ sim,
@@ -871,13 +914,7 @@ __global__ void __launch_bounds__(256) rmsd_batch_kernel(const long long *__rest
     const int n = (int)(offsets[pair + 1] - offsets[pair]);
     double acc = 0.0;
     if (stride == 4) {
-        const double4 *s4 = reinterpret_cast<const double4 *>(sim) + off;
-        const double4 *r4 = reinterpret_cast<const double4 *>(ref) + off;
-        for (int i = lane; i < n; i += 32) {
-            const double4 sa = s4[i], ra = r4[i];
-            const double dx = sa.x - ra.x, dy = sa.y - ra.y, dz = sa.z - ra.z;
-            acc += dx * dx + dy * dy + dz * dz;                               // :58-62
-        }
+        acc = warp_rmsd_partial(reinterpret_cast<const double4 *>(sim) + off, reinterpret_cast<const double4 *>(ref) + off, n);
     } else {
         const double *sp = sim + off * 3, *rp = ref + off * 3;
         for (int i = lane; i < n; i += 32) {
@@ -904,12 +941,7 @@ __global__ void __launch_bounds__(256) rmsd_chains_kernel(const long long *__res
     const int n = (int)(offsets[lig + 1] - off);
     const double4 *r4 = reinterpret_cast<const double4 *>(start_xyzq) + (off - atom_base);
     const double4 *s4 = reinterpret_cast<const double4 *>(final_xyzq) + ((long long)replicas * off + (long long)rep * n - out_base);
-    double acc = 0.0;
-    for (int i = lane; i < n; i += 32) {
-        const double4 sa = s4[i], ra = r4[i];
-        const double dx = sa.x - ra.x, dy = sa.y - ra.y, dz = sa.z - ra.z;
-        acc += dx * dx + dy * dy + dz * dz;                               // :58-62
-    }
+    double acc = warp_rmsd_partial(s4, r4, n);
     acc = warp_sum(acc);
     if (lane == 0) out[local] = sqrt(acc / (double)n);                    // :64 (n == 0 -> NaN)
 }

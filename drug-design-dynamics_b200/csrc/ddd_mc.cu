@@ -435,7 +435,7 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
         if (lj && !fits_sm_engine) return fail(DDD_ELIMIT, "params.lj_scale: the ligand does not fit one SM's shared memory");
         if (cut && (s->threads_override > 0 || !fits_sm_engine))
             return fail(DDD_EINVAL, "params.cutoff needs the SM-persistent engine (chain_threads 0 and a ligand that fits one SM's shared memory)");
-        if (cut && s->rec->n_units_s > 65535) return fail(DDD_ELIMIT, "params.cutoff supports receptors up to 2097120 atoms");
+        if (cut && s->rec->n_units_s > 32767) return fail(DDD_ELIMIT, "params.cutoff supports receptors up to 1048544 atoms");
         if (s->track_best && n_local > 0 && (s->threads_override > 0 || !fits_sm_engine))
             return fail(DDD_EINVAL, "best-ever tracking needs the SM-persistent engine (chain_threads 0 and a ligand that fits one SM's shared memory)");
         if (s->threads_override <= 0 && n_local > 0 && fits_sm_engine) {
@@ -476,13 +476,14 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
             d.threads = kSmThreads; d.slots = A.slots;
             CUDA_TRY(cudaMemsetAsync(d.d_queue, 0, sizeof(int), dev.stream));
             CUDA_TRY(cudaEventRecord(dev.ev0, dev.stream));
-            if (precise) {
-                if (int rc = set_smem(mc_sm_kernel<true>, smem)) return rc;
-                mc_sm_kernel<true><<<(unsigned)grid, kSmThreads, smem, dev.stream>>>(A);
-            } else {
-                if (int rc = set_smem(mc_sm_kernel<false>, smem)) return rc;
-                mc_sm_kernel<false><<<(unsigned)grid, kSmThreads, smem, dev.stream>>>(A);
-            }
+            // one instantiation per (precision, extension): the default kernel carries no cutoff / Lennard-Jones code
+#define LAUNCH_SM(PR, MD)                                                                     \
+            do { if (int rc = set_smem(mc_sm_kernel<PR, MD>, smem)) return rc;                 \
+                 mc_sm_kernel<PR, MD><<<(unsigned)grid, kSmThreads, smem, dev.stream>>>(A); } while (0)
+            const int mode = lj ? MODE_LJ : cut ? MODE_CUT : MODE_PLAIN;
+            if (precise) { if (mode == MODE_LJ) LAUNCH_SM(true, MODE_LJ); else if (mode == MODE_CUT) LAUNCH_SM(true, MODE_CUT); else LAUNCH_SM(true, MODE_PLAIN); }
+            else { if (mode == MODE_LJ) LAUNCH_SM(false, MODE_LJ); else if (mode == MODE_CUT) LAUNCH_SM(false, MODE_CUT); else LAUNCH_SM(false, MODE_PLAIN); }
+#undef LAUNCH_SM
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaEventRecord(dev.ev1, dev.stream));
             continue;
@@ -1532,13 +1533,13 @@ int ddd_chain_kernel_info(int32_t precision, int32_t *threads, int32_t *regs, in
     int blocks = 0;
     const size_t smem = sm_smem_bytes(40, 7);            // the SM-persistent engine at config 2's shape: 7 chains of 40 atoms per SM
     if (precision == DDD_PRECISION_F64) {
-        if (int rc = set_smem(mc_sm_kernel<true>, smem)) return rc;
-        CUDA_TRY(cudaFuncGetAttributes(&fa, mc_sm_kernel<true>));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, mc_sm_kernel<true>, kSmThreads, smem));
+        if (int rc = set_smem(mc_sm_kernel<true, MODE_PLAIN>, smem)) return rc;
+        CUDA_TRY(cudaFuncGetAttributes(&fa, mc_sm_kernel<true, MODE_PLAIN>));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, mc_sm_kernel<true, MODE_PLAIN>, kSmThreads, smem));
     } else {
-        if (int rc = set_smem(mc_sm_kernel<false>, smem)) return rc;
-        CUDA_TRY(cudaFuncGetAttributes(&fa, mc_sm_kernel<false>));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, mc_sm_kernel<false>, kSmThreads, smem));
+        if (int rc = set_smem(mc_sm_kernel<false, MODE_PLAIN>, smem)) return rc;
+        CUDA_TRY(cudaFuncGetAttributes(&fa, mc_sm_kernel<false, MODE_PLAIN>));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, mc_sm_kernel<false, MODE_PLAIN>, kSmThreads, smem));
     }
     if (threads) *threads = kSmThreads;
     if (regs) *regs = fa.numRegs;

@@ -73,7 +73,7 @@ struct __align__(16) SmSlotCtl {
     long long spec_rej;
     int n_e, upi_e;                                   // pair-sum items of the evaluation handed out, receptor units per item
     int n_surv[3];                                    // cutoff extension: units within reach of pose buffer b (-1: list overflow)
-    int best_is_cur, pad1, pad2;                      // best-ever tracker: the current pose is the best one seen so far
+    int best_is_cur; float qsum; int pad2;            // best-ever tracker: the current pose is the best one; qsum = sum of the fp32 charges (cutoff extension)
     long long units_done;                             // cutoff extension: receptor units evaluated by the chain's fp32 sums
     double best_e;                                    // lowest chain energy seen (start pose included)
     float lbox[3][8];                                 // fp32 bounding box of pose buffer b: (min xyz, -, max xyz, -)
@@ -169,6 +169,28 @@ __device__ __forceinline__ bool boxes_apart(const float4 gmin, const float4 gmax
            lbox[1] - gmax.y > gap || gmin.z - lbox[6] > gap || lbox[2] - gmax.z > gap;
 }
 
+// Development instrumentation (-DDDD_SM_PROF; never in the shipped library): warp-cycles per phase, summed per CTA in shared
+// memory and printed by CTA 0..3 at exit.  Phases: 0 pair items (fp32), 1 fp64 items, 2 speculative proposals, 3 serial phase
+// (incl. inline proposals), 4 idle polling, 5 inline proposals inside the serial phase, 6 cell-list query; counts: 8 items,
+// 9 spec tasks, 10 serial phases, 11 proposal attempts, 12 idle polls.
+#ifdef DDD_SM_PROF
+__shared__ unsigned long long ddd_prof[16];
+#define PROF_T0() const long long prof_t0_ = clock64()
+#define PROF_ADD(k) do { if ((threadIdx.x & 31) == 0) atomicAdd(&ddd_prof[k], (unsigned long long)(clock64() - prof_t0_)); } while (0)
+#define PROF_CNT(k, n) do { if ((threadIdx.x & 31) == 0) atomicAdd(&ddd_prof[k], (unsigned long long)(n)); } while (0)
+#else
+#define PROF_T0() do {} while (0)
+#define PROF_ADD(k) do {} while (0)
+#define PROF_CNT(k, n) do {} while (0)
+#endif
+
+// MODE of a kernel instantiation: the extensions live in their own instantiations so that the default (reference) kernel
+// does not carry their code -- the chain kernels are bound by instruction fetch wherever a warp is not inside the pair loop
+// (ncu: no_instruction), and 16 warps in different phases share one instruction cache.
+enum : int { MODE_PLAIN = 0, MODE_CUT = 1, MODE_LJ = 2 };      // MODE_LJ: Lennard-Jones, with or without the cutoff
+template <int MODE> __device__ __forceinline__ bool mode_cut(const SmArgs &A) { return MODE == MODE_CUT ? true : MODE == MODE_LJ ? A.cut != 0 : false; }
+template <int MODE> __device__ __forceinline__ int mode_lj_bytes(const SmArgs &A) { return MODE == MODE_LJ ? A.lj_bytes : 0; }
+
 // ------------------------------------------------------------------ energy work items
 // Receptors up to 8 192 atoms: the fp32 sum is kept PER GROUP (4 units = 128 atoms, 4 per lane) AND PER LANE in shared
 // memory -- gsum[g][lane] = the lane's fp32 sum over its 4 atoms x nL ligand atoms -- and added in (group, lane) order by
@@ -177,6 +199,7 @@ __device__ __forceinline__ bool boxes_apart(const float4 gmin, const float4 gmax
 // groups when one chain has it to itself.  Two adjacent groups go through the loop together (8 atoms per lane share every
 // ligand load) but keep separate sums.  The clamp d >= 1e-6 (:255-257) can only matter where a group's box touches the
 // pose's box; everywhere else min(1/d, 1e6) == 1/d exactly and the loop without the two FMNMX gives the same bits.
+template <int MODE>
 __device__ __forceinline__ void sm_item_f32_groups(const SmArgs &A, const float4 *lf, const float4 *ljf, const unsigned *apart_mask, float *gsum, int nl, int g, int g1) {
     const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
     const ulonglong2 *ljp = reinterpret_cast<const ulonglong2 *>(ljf);
@@ -184,7 +207,7 @@ __device__ __forceinline__ void sm_item_f32_groups(const SmArgs &A, const float4
     const float rmax = A.c.prm.rinv_max;
     const float4 *rec = A.c.rec.f32s;                 // Morton order: a group is spatially compact
     const int lane = threadIdx.x & 31;
-    if (A.lj_bytes) {                                   // LJ extension: one group at a time, Coulomb + 12-6
+    if (mode_lj_bytes<MODE>(A)) {                       // LJ extension: one group at a time, Coulomb + 12-6
         for (; g < g1; ++g) {
             int ub[4] = {4 * g * 32, 4 * g * 32 + 32, 4 * g * 32 + 64, 4 * g * 32 + 96};
             gsum[g * 32 + lane] = warp_units_sum_lj_f32<4, false>(rec, A.c.rec.lj32s, ub, lf2, ljp, n_pairs, rmax, 0.f, A.c.prm.lj_c32, A.c.prm.lj_cap32);
@@ -214,6 +237,7 @@ __device__ __forceinline__ void sm_item_f32_groups(const SmArgs &A, const float4
 }
 
 // larger receptors: static items (runs of A.upi units), one fp64 sum per item
+template <int MODE>
 __device__ __noinline__ double sm_item_f32(const SmArgs &A, const float4 *lf, const float4 *ljf, const float *lbox, int nl, int it) {
     const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
     const int n_pairs = (nl + 1) >> 1;
@@ -222,7 +246,7 @@ __device__ __noinline__ double sm_item_f32(const SmArgs &A, const float4 *lf, co
     const float rmax = A.c.prm.rinv_max;
     const float4 *rec = A.c.rec.f32s;
     double acc = 0.0;
-    if (A.lj_bytes) {                                   // LJ extension
+    if (mode_lj_bytes<MODE>(A)) {                       // LJ extension
         const ulonglong2 *ljp = reinterpret_cast<const ulonglong2 *>(ljf);
         for (; u + 4 <= u1; u += 4) {
             int ub[4] = {u * 32, u * 32 + 32, u * 32 + 64, u * 32 + 96};
@@ -250,7 +274,11 @@ __device__ __noinline__ double sm_item_f32(const SmArgs &A, const float4 *lf, co
 }
 
 // cutoff extension: item `it` covers entries [it*upi, (it+1)*upi) of the pose's unit list (or of all units after a list
-// overflow); the units are whatever the Morton order put within reach, so each A-wide call gathers its own bases
+// overflow); the units are whatever the Morton order put within reach, so each call gathers its own bases.  A list entry
+// is (unit id | kUnitApart): the flag says the unit's box is farther than the clamp distance from the pose's box, so the
+// clamp-free loop applies (same bits).  Eight units (8 receptor atoms per lane) go through the loop together.
+constexpr unsigned kUnitApart = 0x8000u;
+template <int MODE>
 __device__ __forceinline__ double sm_item_f32_cut(const SmArgs &A, const SlotView &s, const SmSlotCtl *c, int buf, int nl, int it) {
     const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(s.lf(buf));
     const int n_pairs = (nl + 1) >> 1;
@@ -263,37 +291,53 @@ __device__ __forceinline__ double sm_item_f32_cut(const SmArgs &A, const SlotVie
     const float rmax = A.c.prm.rinv_max, rci = A.c.prm.rc_inv;
     const float4 *rec = A.c.rec.f32s;
     double acc = 0.0;
-    if (A.lj_bytes) {                                   // LJ extension
+    if (mode_lj_bytes<MODE>(A)) {                       // LJ extension
         const ulonglong2 *ljp = reinterpret_cast<const ulonglong2 *>(s.ljf(A.unit_list_bytes + A.gsum_bytes));
         for (; j + 4 <= j1; j += 4) {
             int ub[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) ub[a] = 32 * (ns >= 0 ? (int)ul[j + a] : j + a);
+            for (int a = 0; a < 4; ++a) ub[a] = 32 * (ns >= 0 ? (int)(ul[j + a] & ~kUnitApart) : j + a);
             acc += (double)warp_units_sum_lj_f32<4, true>(rec, A.c.rec.lj32s, ub, lf2, ljp, n_pairs, rmax, rci, A.c.prm.lj_c32, A.c.prm.lj_cap32);
         }
         for (; j < j1; ++j) {
-            int ub[1] = {32 * (ns >= 0 ? (int)ul[j] : j)};
+            int ub[1] = {32 * (ns >= 0 ? (int)(ul[j] & ~kUnitApart) : j)};
             acc += (double)warp_units_sum_lj_f32<1, true>(rec, A.c.rec.lj32s, ub, lf2, ljp, n_pairs, rmax, rci, A.c.prm.lj_c32, A.c.prm.lj_cap32);
         }
         return warp_sum(acc);
     }
-    // the sorted receptor of a large complex lives in L2, not L1: the next group's atoms are prefetched into L1 while
-    // this group's pairs are summed
+    // the sorted receptor of a large complex lives in L2, not L1: the next call's atoms are prefetched into L1 while
+    // this call's pairs are summed
     const int lane = threadIdx.x & 31;
-    for (; j + 4 <= j1; j += 4) {
+    const float rc_q = rci * c->qsum;                   // (1/cutoff) * sum_l q_l: the constant part of the shifted terms
+    for (; j + 8 <= j1; j += 8) {
+        int ub[8];
+        unsigned ap = kUnitApart;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const unsigned e = ns >= 0 ? (unsigned)ul[j + a] : (unsigned)(j + a);
+            ub[a] = 32 * (int)(e & ~kUnitApart);
+            ap &= e;
+        }
+        if (j + 16 <= j1) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(rec + 32 * (ns >= 0 ? (int)(ul[j + 8 + a] & ~kUnitApart) : j + 8 + a) + lane));
+        }
+        float lo, hi;
+        if (ap) hi = warp_units_sum_f32<8, true, false>(rec, ub, lf2, n_pairs, rmax, rci, &lo, rc_q);
+        else hi = warp_units_sum_f32<8, true, true>(rec, ub, lf2, n_pairs, rmax, rci, &lo, rc_q);
+        acc += (double)lo + (double)hi;
+    }
+    if (j + 4 <= j1) {
         int ub[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) ub[a] = 32 * (ns >= 0 ? (int)ul[j + a] : j + a);
-        if (j + 8 <= j1) {
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(rec + 32 * (ns >= 0 ? (int)ul[j + 4 + a] : j + 4 + a) + lane));
-        }
-        acc += (double)warp_units_sum_f32<4, true>(rec, ub, lf2, n_pairs, rmax, rci);
+        for (int a = 0; a < 4; ++a) ub[a] = 32 * (ns >= 0 ? (int)(ul[j + a] & ~kUnitApart) : j + a);
+        acc += (double)warp_units_sum_f32<4, true, true>(rec, ub, lf2, n_pairs, rmax, rci, nullptr, rc_q);
+        j += 4;
     }
     for (; j < j1; ++j) {
-        int ub[1] = {32 * (ns >= 0 ? (int)ul[j] : j)};
-        acc += (double)warp_units_sum_f32<1, true>(rec, ub, lf2, n_pairs, rmax, rci);
+        int ub[1] = {32 * (ns >= 0 ? (int)(ul[j] & ~kUnitApart) : j)};
+        acc += (double)warp_units_sum_f32<1, true, true>(rec, ub, lf2, n_pairs, rmax, rci, nullptr, rc_q);
     }
     return warp_sum(acc);
 }
@@ -308,18 +352,19 @@ __device__ __forceinline__ double lj_term(const DevParams &P, const double2 pj, 
 }
 
 // the reference's per-term fp64 arithmetic (:253-258) for the receptor atoms of one item
+template <int MODE>
 __device__ __noinline__ double sm_item_f64(const SmArgs &A, const SlotView &s, const SmSlotCtl *c, int buf, int nl, int it) {
     const double K = A.c.prm.k_coulomb, clampd = A.c.prm.clamp_distance, cutoff = A.c.prm.cutoff;
-    const bool lj = A.lj_bytes != 0;
+    const bool lj = mode_lj_bytes<MODE>(A) != 0;
     const double2 *ljl = s.lj64(A.unit_list_bytes + A.gsum_bytes);
     double e = 0.0;
-    if (A.cut) {                                                          // the pose's cell-list units, exact per-pair test
+    if (mode_cut<MODE>(A)) {                                                          // the pose's cell-list units, exact per-pair test
         const int ns = c->n_surv[buf];
         const int nu = ns >= 0 ? ns : A.c.rec.n_units_s;
         const unsigned short *ul = s.units(buf);
         const int j1 = min((it + 1) * c->upi_e, nu);
         for (int j = it * c->upi_e; j < j1; ++j) {
-            const int p = 32 * (ns >= 0 ? (int)ul[j] : j) + (int)(threadIdx.x & 31);
+            const int p = 32 * (ns >= 0 ? (int)(ul[j] & ~kUnitApart) : j) + (int)(threadIdx.x & 31);
             if (p >= A.c.rec.n) continue;
             const Atom64 P = A.c.rec.f64s[p];
             const double2 PJ = lj ? A.c.rec.lj64s[p] : make_double2(0.0, 0.0);
@@ -346,10 +391,10 @@ __device__ __noinline__ double sm_item_f64(const SmArgs &A, const SlotView &s, c
             const double ddx = P.x - L[0], ddy = P.y - L[1], ddz = P.z - L[2];
             const double d2 = ddx * ddx + ddy * ddy + ddz * ddz;
             double d = sqrt(d2);                                          // :253 (Pow(x,2) == x*x)
-            if (cutoff > 0 && !(d < cutoff)) continue;                    // EXTENSION: shifted-Coulomb cutoff
+            if (MODE != MODE_PLAIN && cutoff > 0 && !(d < cutoff)) continue;      // EXTENSION: shifted-Coulomb cutoff
             if (d < clampd) d = clampd;                                   // :255-257
             double term = K * (P.q * s.q(l)) / d;                         // :258
-            if (cutoff > 0) term -= K * (P.q * s.q(l)) / cutoff;
+            if (MODE != MODE_PLAIN && cutoff > 0) term -= K * (P.q * s.q(l)) / cutoff;
             if (lj) term += lj_term(A.c.prm, PJ, ljl[l], d2);
             e += term;
         }
@@ -358,6 +403,9 @@ __device__ __noinline__ double sm_item_f64(const SmArgs &A, const SlotView &s, c
 }
 
 // ------------------------------------------------------------------ one-warp proposal helpers
+// Every loop on the serial side is kept ROLLED (#pragma unroll 1): this code runs once per step per chain on one warp, it is
+// bound by instruction fetch, not by issue slots -- ncu shows the SM's instruction cache missing (sm__icc_request_hit_rate 69 % with
+// the cutoff extension, 93 % without) and the GPC-level cache behind it at 60-80 % of its bandwidth, so bytes of code are what counts.
 // fp32 screen in front of IsCollisionFree, one warp: atoms in rows of 32 lanes; a short last row gives every atom
 // 32/rem lanes that split the ligand pairs.  Same classification as collision_screen_f32 (ddd_kernels.cuh).
 __device__ __noinline__ int warp_collision_screen(const float4 *lf, int nl, float m2) {
@@ -366,6 +414,7 @@ __device__ __noinline__ int warp_collision_screen(const float4 *lf, int nl, floa
     const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(lf);
     const float *lff = reinterpret_cast<const float *>(lf);
     float dmin = 3.0e38f, slack = 0.f;
+    #pragma unroll 1
     for (int b = 0; b < nl; b += 32) {
         const int rem = nl - b;
         int i, k0, ks;
@@ -376,7 +425,7 @@ __device__ __noinline__ int warp_collision_screen(const float4 *lf, int nl, floa
         const float xi = -mine[0], yi = -mine[2], zi = -mine[4];
         slack = fmaxf(slack, 1e-6f * (fabsf(xi) + fabsf(yi) + fabsf(zi) + 1.0f));
         const f32x2 ax = pack2(xi, xi), ay = pack2(yi, yi), az = pack2(zi, zi);
-#pragma unroll 4
+        #pragma unroll 1
         for (int k = k0; k < n_pairs; k += ks) {
             const ulonglong2 Lxy = lf2[2 * k], Lzq = lf2[2 * k + 1];
             const f32x2 dx = add2(ax, Lxy.x), dy = add2(ay, Lxy.y), dz = add2(az, Lzq.x);
@@ -399,6 +448,7 @@ __device__ __noinline__ bool warp_collision_exact(const SlotView &s, int buf, in
     const int total = n_full + ((nl & 1) ? 0 : nl / 2);
     const double m2 = min_distance * min_distance, m2_lo = m2 * (1.0 - 1e-9), m2_hi = m2 * (1.0 + 1e-9);
     bool hit = false;
+    #pragma unroll 1
     for (int w = threadIdx.x & 31; w < total; w += 32) {
         int i, m;
         if (w < n_full) { m = w / nl + 1; i = w - (m - 1) * nl; } else { i = w - n_full; m = nl / 2; }
@@ -416,6 +466,7 @@ __device__ __noinline__ bool warp_collision_exact(const SlotView &s, int buf, in
 // the same without the bounding box: enough for the near-pair scan of a pose that has just failed its collision test
 __device__ __noinline__ void warp_write_lf_only(const SmArgs &A, const SlotView &s, int buf, int nl) {
     float4 *lf = s.lf(buf);
+    #pragma unroll 1
     for (int i = threadIdx.x & 31; i < nl; i += 32) {
         const double *a = s.xyz(buf, i);
         store_lig_f32(lf, i, (float)(a[0] - A.c.rec.cx), (float)(a[1] - A.c.rec.cy), (float)(a[2] - A.c.rec.cz), (float)s.q(i));
@@ -427,26 +478,29 @@ __device__ __noinline__ void warp_write_lf_only(const SmArgs &A, const SlotView 
 __device__ __noinline__ void warp_write_lf(const SmArgs &A, const SlotView &s, SmSlotCtl *c, int buf, int nl) {
     float4 *lf = s.lf(buf);
     const int lane = threadIdx.x & 31;
-    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    float lox = 3.0e38f, loy = 3.0e38f, loz = 3.0e38f, hix = -3.0e38f, hiy = -3.0e38f, hiz = -3.0e38f;
+#pragma unroll 1
     for (int i = lane; i < nl; i += 32) {
         const double *a = s.xyz(buf, i);
         const float x = (float)(a[0] - A.c.rec.cx), y = (float)(a[1] - A.c.rec.cy), z = (float)(a[2] - A.c.rec.cz);
         store_lig_f32(lf, i, x, y, z, (float)s.q(i));
-        lo[0] = fminf(lo[0], x); hi[0] = fmaxf(hi[0], x); lo[1] = fminf(lo[1], y); hi[1] = fmaxf(hi[1], y);
-        lo[2] = fminf(lo[2], z); hi[2] = fmaxf(hi[2], z);
+        lox = fminf(lox, x); hix = fmaxf(hix, x); loy = fminf(loy, y); hiy = fmaxf(hiy, y);
+        loz = fminf(loz, z); hiz = fmaxf(hiz, z);
     }
     if ((nl & 1) && lane == 0) store_lig_f32(lf, nl, -kPadCoord, -kPadCoord, -kPadCoord, 0.f);   // q = 0 pad atom
     // the pose's fp32 bounding box: lets the pair loop skip the clamp (and the cutoff extension skip whole units)
-#pragma unroll
-    for (int d = 0; d < 3; ++d)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
-            hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
-        }
-    if (lane < 3) { c->lbox[buf][lane] = lo[lane]; c->lbox[buf][4 + lane] = hi[lane]; }
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+        lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+        loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+        loz = fminf(loz, __shfl_xor_sync(0xffffffffu, loz, o)); hiz = fmaxf(hiz, __shfl_xor_sync(0xffffffffu, hiz, o));
+    }
+    if (lane == 0) {
+        float *lb = c->lbox[buf];
+        lb[0] = lox; lb[1] = loy; lb[2] = loz; lb[4] = hix; lb[5] = hiy; lb[6] = hiz;
+    }
     if (A.gsum_bytes) {                                 // which 128-atom groups can skip the clamp for this pose (<= 64 groups)
-        const float lb[8] = {lo[0], lo[1], lo[2], 0.f, hi[0], hi[1], hi[2], 0.f};
+        const float lb[8] = {lox, loy, loz, 0.f, hix, hiy, hiz, 0.f};
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
             const int g = 32 * w + lane;
@@ -470,20 +524,29 @@ __device__ __noinline__ void warp_build_unit_list(const SmArgs &A, const SlotVie
     const float rc2 = rc * rc * 1.0001f + 1e-3f;                      // conservative: fp32 boxes, fp32 pose
     unsigned short *ul = s.units(buf);
     const int n_units = A.c.rec.n_units_s;
+    const float gap_apart = A.c.prm.apart_gap;
+    bool apart_out = false;                                               // side result of the last test: the boxes are farther apart than the clamp margin
     auto within = [&](const float4 bmin, const float4 bmax) {
         const float gx = fmaxf(0.f, fmaxf(bmin.x - hi[0], lo[0] - bmax.x));
         const float gy = fmaxf(0.f, fmaxf(bmin.y - hi[1], lo[1] - bmax.y));
         const float gz = fmaxf(0.f, fmaxf(bmin.z - hi[2], lo[2] - bmax.z));
+        apart_out = fmaxf(gx, fmaxf(gy, gz)) > gap_apart;                 // == boxes_apart(bmin, bmax, lbox, gap)
         return gx * gx + gy * gy + gz * gz < rc2;
     };
-    // level 1: the boxes of the groups of 4 units; the survivors' ids are staged in the (idle) dynamic near-pair list
+    // level 1: the boxes of the groups of 4 units; the survivors' ids are staged in the (idle) dynamic near-pair list.
+    // Rolled loops on purpose: the body is fetched once and then runs out of the instruction cache (see the note above).
     unsigned short *grp = reinterpret_cast<unsigned short *>(s.dyn_list());
     constexpr int kGroupCap = kNearCap * 2;                               // ushort entries in that list
     const int n_groups = (n_units + 3) >> 2;
     int n_g = 0;
+    // the query is one warp chasing global loads: pull every group box towards L1 first (one round trip instead of one per step)
+#pragma unroll 1
+    for (int b = lane; b < n_groups; b += 32) asm volatile("prefetch.global.L1 [%0];" :: "l"(A.c.rec.gbox + 2 * b));
+#pragma unroll 1
     for (int b = 0; b < n_groups; b += 32) {
         const int g = b + lane;
-        const bool keep = g < n_groups && nl > 0 && within(__ldg(A.c.rec.gbox + 2 * g), __ldg(A.c.rec.gbox + 2 * g + 1));
+        const int gc = min(g, n_groups - 1);
+        const bool keep = g < n_groups && nl > 0 && within(__ldg(A.c.rec.gbox + 2 * gc), __ldg(A.c.rec.gbox + 2 * gc + 1));
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         if (keep) {
             const int idx = n_g + __popc(m & ((1u << lane) - 1));
@@ -496,18 +559,23 @@ __device__ __noinline__ void warp_build_unit_list(const SmArgs &A, const SlotVie
     int count = 0;
     if (n_g > kGroupCap) count = kUnitCap + 1;                            // more than 1024 units in reach: overflow
     else {
+#pragma unroll 1
+        for (int e = lane; e < 4 * n_g; e += 32) {
+            const int u = min(4 * (int)grp[e >> 2] + (e & 3), n_units - 1);
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(A.c.rec.ubox + 2 * u));
+        }
+#pragma unroll 1
         for (int b = 0; b < 4 * n_g; b += 32) {
             const int e = b + lane;
-            bool keep = false;
-            int u = 0;
-            if (e < 4 * n_g) {
-                u = 4 * (int)grp[e >> 2] + (e & 3);
-                keep = u < n_units && within(__ldg(A.c.rec.ubox + 2 * u), __ldg(A.c.rec.ubox + 2 * u + 1));
-            }
+            const int u = e < 4 * n_g ? 4 * (int)grp[e >> 2] + (e & 3) : n_units;
+            const int uc = min(u, n_units - 1);
+            const float4 bmin = __ldg(A.c.rec.ubox + 2 * uc), bmax = __ldg(A.c.rec.ubox + 2 * uc + 1);
+            const bool keep = within(bmin, bmax) && u < n_units;
+            const bool apart = apart_out;
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             if (keep) {
                 const int idx = count + __popc(m & ((1u << lane) - 1));
-                if (idx < kUnitCap) ul[idx] = (unsigned short)u;
+                if (idx < kUnitCap) ul[idx] = (unsigned short)((unsigned)u | (apart ? kUnitApart : 0u));
             }
             count += __popc(m);
         }
@@ -529,6 +597,7 @@ __device__ __noinline__ int warp_build_near_list(const float4 *lf, SmSlotCtl *c,
     const float *lff = reinterpret_cast<const float *>(lf);
     if (lane == 0) c->list_cnt = 0;
     __syncwarp();
+    #pragma unroll 1
     for (int b = 0; b < nl; b += 32) {
         const int rem = nl - b;
         int i, k0, ks;
@@ -539,7 +608,7 @@ __device__ __noinline__ int warp_build_near_list(const float4 *lf, SmSlotCtl *c,
         const float xi = -mine[0], yi = -mine[2], zi = -mine[4];
         const float lim = r2 * 1.001f + 4e-6f * (fabsf(xi) + fabsf(yi) + fabsf(zi) + 1.0f);
         const f32x2 ax = pack2(xi, xi), ay = pack2(yi, yi), az = pack2(zi, zi);
-#pragma unroll 2
+        #pragma unroll 1
         for (int k = k0; k < n_pairs; k += ks) {
             const ulonglong2 Lxy = lf2[2 * k], Lzq = lf2[2 * k + 1];
             const f32x2 dx = add2(ax, Lxy.x), dy = add2(ay, Lxy.y), dz = add2(az, Lzq.x);
@@ -559,6 +628,7 @@ __device__ __noinline__ int warp_build_near_list(const float4 *lf, SmSlotCtl *c,
 __device__ __noinline__ bool warp_check_near_list(const SlotView &s, int buf, const ushort2 *list, int n, double min_distance) {
     const double m2 = min_distance * min_distance, m2_lo = m2 * (1.0 - 1e-9), m2_hi = m2 * (1.0 + 1e-9);
     bool hit = false;
+    #pragma unroll 1
     for (int e = threadIdx.x & 31; e < n; e += 32) {
         const ushort2 pr = list[e];
         const double *a = s.xyz(buf, pr.x), *b = s.xyz(buf, pr.y);
@@ -572,6 +642,48 @@ __device__ __noinline__ bool warp_check_near_list(const SlotView &s, int buf, co
 
 struct ProposalResult { uint64_t pos; long long rej; int status; };
 
+// EXTENSION (no reference row), out of line: rigid-body move
+template <int MODE>
+__device__ __noinline__ ProposalResult sm_propose_rigid(const SmArgs &A, const SlotView &s, SmSlotCtl *c, int src, int dst, uint64_t pos0) {
+    const int lane = threadIdx.x & 31;
+    const DevParams &P = A.c.prm;
+    const int nl = c->nl;
+    Stream st; st.seed = A.c.seed; st.id = c->stream_id; st.rec = c->rec_ptr; st.rec_len = c->rec_len;
+    ProposalResult R; R.pos = pos0; R.rej = 0; R.status = 0;
+    int status = 0;
+    // EXTENSION: rigid-body move, draws tx,ty,tz,ax,ay,az,theta (no reference row); no collision test
+    const double tx = (st.draw(pos0, status) - 0.5) * P.rigid_translation;
+    const double ty = (st.draw(pos0 + 1, status) - 0.5) * P.rigid_translation;
+    const double tz = (st.draw(pos0 + 2, status) - 0.5) * P.rigid_translation;
+    double ax, ay, az, theta;
+    draw_axis_angle(st, pos0 + 3, P.rigid_angle, status, ax, ay, az, theta);
+    double gx = 0, gy = 0, gz = 0;
+    #pragma unroll 1
+    for (int i = 0; i < nl; ++i) { const double *p = s.xyz(src, i); gx += p[0]; gy += p[1]; gz += p[2]; }
+    if (nl > 0) { gx /= (double)nl; gy /= (double)nl; gz /= (double)nl; }
+    const double h = 0.5 * theta;
+    double sh, w; sincos(h, &sh, &w);
+    const double qx = sh * ax, qy = sh * ay, qz = sh * az;
+    #pragma unroll 1
+    for (int i = lane; i < nl; i += 32) {
+        const double *p = s.xyz(src, i);
+        const double vx = p[0] - gx, vy = p[1] - gy, vz = p[2] - gz;
+        const double c1x = qy * vz - qz * vy, c1y = qz * vx - qx * vz, c1z = qx * vy - qy * vx;
+        const double c2x = qy * c1z - qz * c1y, c2y = qz * c1x - qx * c1z, c2z = qx * c1y - qy * c1x;
+        double *o = s.xyz(dst, i);
+        o[0] = gx + (vx + 2.0 * (w * c1x + c2x)) + tx;
+        o[1] = gy + (vy + 2.0 * (w * c1y + c2y)) + ty;
+        o[2] = gz + (vz + 2.0 * (w * c1z + c2z)) + tz;
+    }
+    __syncwarp();
+    warp_write_lf(A, s, c, dst, nl);
+    if (mode_cut<MODE>(A)) warp_build_unit_list(A, s, c, dst, nl);
+    R.pos = pos0 + 7;
+    R.status = __any_sync(0xffffffffu, status & 2) ? 2 : 0;
+    return R;
+}
+
+
 // One proposal of the chain in slot `c`: pose buffer `src` (the current pose) -> buffer `dst`, uniforms from stream
 // position `pos0`.  REFERENCE move: JitterAndRotateLigand (:172-184) / JitterLigand (:154-167), retried cumulatively on
 // `dst` until IsCollisionFree (:180 / :162).  Latency is what matters here (late in a chain the jitter piles atoms up
@@ -582,6 +694,7 @@ struct ProposalResult { uint64_t pos; long long rej; int status; };
 //  * the collision test looks only at the near-pair list of the current pose (or of a later attempt's pose once the
 //    list's distance budget is spent); the fp32 pose is written only for the attempt that passes.
 // status bit 1: retry bound hit (the pose in dst is meaningless), bit 2: recorded stream exhausted.
+template <int MODE>
 __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotView &s, SmSlotCtl *c, int src, int dst, uint64_t pos0) {
     const int lane = threadIdx.x & 31;
     const ChainArgs &a = A.c;
@@ -590,36 +703,7 @@ __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotVie
     Stream st; st.seed = a.seed; st.id = c->stream_id; st.rec = c->rec_ptr; st.rec_len = c->rec_len;
     ProposalResult R; R.pos = pos0; R.rej = 0; R.status = 0;
     int status = 0;
-    if (P.move_mode == 1) {
-        // EXTENSION: rigid-body move, draws tx,ty,tz,ax,ay,az,theta (no reference row); no collision test
-        const double tx = (st.draw(pos0, status) - 0.5) * P.rigid_translation;
-        const double ty = (st.draw(pos0 + 1, status) - 0.5) * P.rigid_translation;
-        const double tz = (st.draw(pos0 + 2, status) - 0.5) * P.rigid_translation;
-        double ax, ay, az, theta;
-        draw_axis_angle(st, pos0 + 3, P.rigid_angle, status, ax, ay, az, theta);
-        double gx = 0, gy = 0, gz = 0;
-        for (int i = 0; i < nl; ++i) { const double *p = s.xyz(src, i); gx += p[0]; gy += p[1]; gz += p[2]; }
-        if (nl > 0) { gx /= (double)nl; gy /= (double)nl; gz /= (double)nl; }
-        const double h = 0.5 * theta;
-        double sh, w; sincos(h, &sh, &w);
-        const double qx = sh * ax, qy = sh * ay, qz = sh * az;
-        for (int i = lane; i < nl; i += 32) {
-            const double *p = s.xyz(src, i);
-            const double vx = p[0] - gx, vy = p[1] - gy, vz = p[2] - gz;
-            const double c1x = qy * vz - qz * vy, c1y = qz * vx - qx * vz, c1z = qx * vy - qy * vx;
-            const double c2x = qy * c1z - qz * c1y, c2y = qz * c1x - qx * c1z, c2z = qx * c1y - qy * c1x;
-            double *o = s.xyz(dst, i);
-            o[0] = gx + (vx + 2.0 * (w * c1x + c2x)) + tx;
-            o[1] = gy + (vy + 2.0 * (w * c1y + c2y)) + ty;
-            o[2] = gz + (vz + 2.0 * (w * c1z + c2z)) + tz;
-        }
-        __syncwarp();
-        warp_write_lf(A, s, c, dst, nl);
-        if (A.cut) warp_build_unit_list(A, s, c, dst, nl);
-        R.pos = pos0 + 7;
-        R.status = __any_sync(0xffffffffu, status & 2) ? 2 : 0;
-        return R;
-    }
+    if (P.move_mode == 1) return sm_propose_rigid<MODE>(A, s, c, src, dst, pos0);   // EXTENSION, out of line
     const int dpa = (P.rotate ? 4 : 0) + 3 * nl;                         // draws per attempt
     const double pair_step = fabs(P.jitter_width) * 1.7320508075688774;   // max change of a pair distance per attempt
     const int k_max = pair_step > 0.0 ? (int)fmin((kNearMargin - 1e-6) / (pair_step * (1.0 + 1e-9)), 1.0e6) : 1000000;
@@ -637,6 +721,7 @@ __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotVie
     int from = src;
     for (;;) {
         ++k;
+        PROF_CNT(11, 1);
         const uint64_t apos = pos0 + (uint64_t)(k - 1) * (uint64_t)dpa;
         double ax = 0, ay = 0, az = 0, cos_t = 1, sin_t = 0;
         uint64_t jpos = apos;
@@ -658,6 +743,7 @@ __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotVie
         if (use_ubuf && nl > 0) {
             const int nb = (int)(((jpos + 3ull * (uint64_t)nl - 1) >> 1) - b_first) + 1;
             double2 *ub = reinterpret_cast<double2 *>(s.ubuf());
+            #pragma unroll 1
             for (int b = lane; b < nb; b += 32) {
                 const uint64_t blk = b_first + (uint64_t)b;
                 uint32_t o[4];
@@ -668,6 +754,7 @@ __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotVie
             __syncwarp();
         }
         const double *uu = s.ubuf() + (jpos - 2 * b_first);
+        #pragma unroll 1
         for (int i = lane; i < nl; i += 32) {
             const double *p = s.xyz(from, i);
             double x = p[0], y = p[1], z = p[2];
@@ -702,7 +789,7 @@ __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotVie
         ++R.rej;
         if (R.rej >= P.max_retries) { bail = true; break; }                // the reference would spin forever here
     }
-    if (A.cut && !bail) warp_build_unit_list(A, s, c, dst, nl);         // the cell-list query of the pose that will be evaluated
+    if (mode_cut<MODE>(A) && !bail) { PROF_T0(); warp_build_unit_list(A, s, c, dst, nl); PROF_ADD(6); }         // the cell-list query of the pose that will be evaluated
     R.pos = pos0 + (uint64_t)k * (uint64_t)dpa;
     R.status = (bail ? 1 : 0) | (__any_sync(0xffffffffu, status & 2) ? 2 : 0);
     return R;
@@ -710,20 +797,21 @@ __device__ __noinline__ ProposalResult sm_propose(const SmArgs &A, const SlotVie
 
 // Hand the slot out: pair-sum items of the trial pose (mode/stage) and, when `with_spec`, the speculative proposal of the
 // following step.  False when the receptor has no atoms (nothing to hand out: the caller goes on inline).
-__device__ __forceinline__ bool sm_publish(const SmArgs &A, const SmView &V, int slot_id, SmSlotCtl *c, int mode, int stage, bool with_spec) {
+template <int MODE>
+__device__ __noinline__ bool sm_publish(const SmArgs &A, const SmView &V, int slot_id, SmSlotCtl *c, int mode, int stage, bool with_spec) {
     // pair-sum items of this evaluation: the static cut of the receptor, or (cutoff extension, fp32 sums) runs of the
     // trial pose's unit list, 4*m units per item with m as small as the item-sum array allows
     int n_e = A.n_items, upi_e = A.upi;
-    if (A.gsum_bytes && mode == 0 && !A.cut) {          // per-group sums: items are scheduling granules only
+    if (A.gsum_bytes && mode == 0 && !mode_cut<MODE>(A)) {   // per-group sums: items are scheduling granules only
         const int live = ld_volatile(V.live());
         const int gpi = live >= 4 ? kGroupsPerItemBusy : live >= 2 ? 2 : 1;     // groups per item
         upi_e = 4 * gpi;
         n_e = (A.n_groups4 + gpi - 1) / gpi;
     }
-    if (A.cut) {
+    if (mode_cut<MODE>(A)) {
         const int ns = c->n_surv[c->i_trial];
         const int nu = ns >= 0 ? ns : A.c.rec.n_units_s;
-        upi_e = max(A.upi, 4 * ((nu + 4 * kSmMaxItems - 1) / (4 * kSmMaxItems)));
+        upi_e = 16 * max(1, (nu + 16 * kSmMaxItems - 1) / (16 * kSmMaxItems));  // runs of 16 units (two 8-atoms-per-lane calls; the second is prefetched), more only for huge lists
         n_e = (nu + upi_e - 1) / upi_e;
         if ((threadIdx.x & 31) == 0 && mode == 0) c->units_done += nu;
     }
@@ -746,9 +834,114 @@ __device__ __forceinline__ bool sm_publish(const SmArgs &A, const SmView &V, int
     return true;
 }
 
+// one out-of-line, rolled copy of the fp64 warp sum for the serial side (same butterfly, same bits as warp_sum)
+__device__ __noinline__ double cold_warp_sum(double v) {
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Cold path, out of line (the step loop's code should stay compact: see MODE above): load the chain at launch position
+// `load_pos` into the slot -- private copy of the start pose, counters, stream, fp32 pose, cell-list query.
+template <int MODE>
+__device__ __noinline__ void sm_load_chain(const SmArgs &A, const SlotView &s, SmSlotCtl *c, long long load_pos) {
+    const int lane = threadIdx.x & 31;
+    const ChainArgs &a = A.c;
+    const long long local = a.order ? (long long)a.order[load_pos] : load_pos;
+    const long long chain = a.chain_begin + local;
+    const long long lig = chain / a.replicas;
+    const long long off = a.offsets[lig];
+    const int nl = (int)(a.offsets[lig + 1] - off);
+    const double *src = a.lig_xyzq + (off - a.atom_base) * 4;           // private copy of the start pose
+    #pragma unroll 1
+    for (int i = lane; i < nl; i += 32) {
+        double *o = s.xyz(0, i);
+        o[0] = src[4 * i]; o[1] = src[4 * i + 1]; o[2] = src[4 * i + 2];
+        s.q(i) = src[4 * i + 3];
+    }
+    if (mode_lj_bytes<MODE>(A)) {                                       // LJ extension: the ligand's (sigma/2, sqrt eps)
+        const int lo = A.unit_list_bytes + A.gsum_bytes;
+        const double2 *lsrc = A.lig_lj + (off - a.atom_base);
+        float *lf4 = reinterpret_cast<float *>(s.ljf(lo));
+        #pragma unroll 1
+        for (int i = lane; i < nl + (nl & 1); i += 32) {
+            const double2 v = i < nl ? lsrc[i] : make_double2(0.0, 0.0);
+            if (i < nl) s.lj64(lo)[i] = v;
+            lf4[4 * (i >> 1) + (i & 1)] = (float)v.x;
+            lf4[4 * (i >> 1) + 2 + (i & 1)] = (float)v.y;
+        }
+    }
+    if (lane == 0) {
+        c->nl = nl; c->status = 0; c->rep = (int)(chain - lig * a.replicas); c->bailed = 0;
+        c->i_cur = 0; c->i_trial = 0; c->i_spec = 1; c->has_spec = 0;
+        c->local = local; c->step = 0; c->pos = 0; c->accepted = 0; c->downhill = 0; c->retries = 0;
+        c->cur_e = 0.0; c->start_e = 0.0; c->off = off; c->base_n = -1; c->list_cnt = 0; c->units_done = 0;
+        c->best_e = 0.0; c->best_is_cur = 1;
+        c->stream_id = a.chain_id_base + (uint64_t)chain;
+        c->rec_ptr = nullptr; c->rec_len = 0;
+        if (a.recorded) {
+            c->rec_ptr = a.recorded + (a.rec_offsets[chain] - a.rec_base);
+            c->rec_len = a.rec_offsets[chain + 1] - a.rec_offsets[chain];
+        }
+    }
+    __syncwarp();
+    warp_write_lf(A, s, c, 0, nl);
+    if (mode_cut<MODE>(A)) {
+        if (lane == 0) c->qsum = ligand_charge_sum_f32(s.lf(0), nl);
+        __syncwarp();
+        warp_build_unit_list(A, s, c, 0, nl);
+    }
+}
+
+// Cold path, out of line: the chain's results -- final pose, fused CalculateRMSD, best-ever pose, counters.
+__device__ __noinline__ void sm_store_chain(const SmArgs &A, const SlotView &s, SmSlotCtl *c, double e) {
+    const int lane = threadIdx.x & 31;
+    const ChainArgs &a = A.c;
+    const int nl = c->nl;
+    const double final_energy = e;
+    const long long out_atom = (long long)a.replicas * c->off + (long long)c->rep * nl - a.out_base;
+    double *dst = a.out_xyzq + out_atom * 4;
+    const int cu = c->i_cur;
+    // fused CalculateRMSD (validateResults.go:50-65) of the final pose against the reference pose: same lane-strided
+    // partial sums and butterfly as rmsd_chains_kernel, so both give the same bits
+    const double4 *ref4 = a.out_rmsd ? reinterpret_cast<const double4 *>(a.ref_xyzq) + (c->off - a.atom_base) : nullptr;
+    double *bdst = (a.out_best_e && c->best_is_cur) ? a.out_best_xyzq + out_atom * 4 : nullptr;
+    double rsum = 0.0;
+    #pragma unroll 1
+    for (int i = lane; i < nl; i += 32) {
+        const double *p = s.xyz(cu, i);
+        dst[4 * i] = p[0]; dst[4 * i + 1] = p[1]; dst[4 * i + 2] = p[2]; dst[4 * i + 3] = s.q(i);
+        if (bdst) { bdst[4 * i] = p[0]; bdst[4 * i + 1] = p[1]; bdst[4 * i + 2] = p[2]; bdst[4 * i + 3] = s.q(i); }
+        if (ref4) {
+            const double4 r = ref4[i];
+            const double dx = p[0] - r.x, dy = p[1] - r.y, dz = p[2] - r.z;
+            rsum += dx * dx + dy * dy + dz * dz;                       // :58-62
+        }
+    }
+    if (ref4) {
+        rsum = cold_warp_sum(rsum);
+        if (lane == 0) a.out_rmsd[c->local] = sqrt(rsum / (double)nl);  // :64 (nl == 0 -> NaN)
+    }
+    if (lane == 0) {
+        if (a.out_best_e) a.out_best_e[c->local] = c->best_e;
+        ChainStats cs;
+        cs.accepted = c->accepted; cs.downhill = c->downhill; cs.retries = c->retries; cs.steps = c->step;
+        cs.draws = (long long)c->pos; cs.status = c->status;
+        cs.final_energy = final_energy; cs.start_energy = c->start_e; cs.chain_energy = c->cur_e;
+        reinterpret_cast<ChainStats *>(a.out_stats)[c->local] = cs;
+        if (A.out_units) A.out_units[c->local] = c->units_done;
+    }
+}
+
+// Cold path, out of line: the draw of AcceptMove's uphill branch (:147-148) when exp(-dE/T) is not exactly 0
+__device__ __noinline__ bool sm_accept_draw(const ChainArgs &a, const SmSlotCtl *c, double x, uint64_t pos, int &status) {
+    Stream st; st.seed = a.seed; st.id = c->stream_id; st.rec = c->rec_ptr; st.rec_len = c->rec_len;
+    return st.draw(pos, status) < exp(x);
+}
+
 // ------------------------------------------------------------------ serial phase (one warp)
 // `load_pos` >= 0: (re)start the slot with the chain at launch position load_pos; -1: everything handed out is complete.
-template <bool PRECISE>
+template <bool PRECISE, int MODE>
 __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, int slot_id, long long load_pos) {
     const int lane = threadIdx.x & 31;
     SmSlotCtl *c = V.ctl(slot_id);
@@ -763,14 +956,16 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
         stage = c->stage;
         spec_ready = c->has_spec != 0;
         const double *items = V.items(slot_id);
-        if (A.gsum_bytes && c->mode == 0 && !A.cut) {                       // (group, lane) order: independent of the item cut
+        if (A.gsum_bytes && c->mode == 0 && !mode_cut<MODE>(A)) {           // (group, lane) order: independent of the item cut
             const float *gs = s.gsum(A.unit_list_bytes);
-            for (int g = 0; g < A.n_groups4; ++g) e += (double)gs[g * 32 + lane];
+            #pragma unroll 8
+            for (int g = 0; g < A.n_groups4; ++g) e += (double)gs[g * 32 + lane];      // loads in flight together; the adds stay in g order
         } else {
             const int n_e = c->n_e;
+            #pragma unroll 1
             for (int it = lane; it < n_e; it += 32) e += items[it];         // fixed order: independent of who computed what
         }
-        e = warp_sum(e);
+        e = cold_warp_sum(e);
     }
     for (;;) {
         if (stage == ST_LOAD) {
@@ -784,58 +979,20 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 if (lane == 0) { st_volatile(&c->next_item, kSlotIdle); atomicSub(V.live(), 1); }
                 return;
             }
-            const long long local = a.order ? (long long)a.order[load_pos] : load_pos;
-            const long long chain = a.chain_begin + local;
-            const long long lig = chain / a.replicas;
-            const long long off = a.offsets[lig];
-            const int nl = (int)(a.offsets[lig + 1] - off);
-            const double *src = a.lig_xyzq + (off - a.atom_base) * 4;           // private copy of the start pose
-            for (int i = lane; i < nl; i += 32) {
-                double *o = s.xyz(0, i);
-                o[0] = src[4 * i]; o[1] = src[4 * i + 1]; o[2] = src[4 * i + 2];
-                s.q(i) = src[4 * i + 3];
-            }
-            if (A.lj_bytes) {                                                   // LJ extension: the ligand's (sigma/2, sqrt eps)
-                const int lo = A.unit_list_bytes + A.gsum_bytes;
-                const double2 *lsrc = A.lig_lj + (off - a.atom_base);
-                float *lf4 = reinterpret_cast<float *>(s.ljf(lo));
-                for (int i = lane; i < nl + (nl & 1); i += 32) {
-                    const double2 v = i < nl ? lsrc[i] : make_double2(0.0, 0.0);
-                    if (i < nl) s.lj64(lo)[i] = v;
-                    lf4[4 * (i >> 1) + (i & 1)] = (float)v.x;
-                    lf4[4 * (i >> 1) + 2 + (i & 1)] = (float)v.y;
-                }
-            }
-            if (lane == 0) {
-                c->nl = nl; c->status = 0; c->rep = (int)(chain - lig * a.replicas); c->bailed = 0;
-                c->i_cur = 0; c->i_trial = 0; c->i_spec = 1; c->has_spec = 0;
-                c->local = local; c->step = 0; c->pos = 0; c->accepted = 0; c->downhill = 0; c->retries = 0;
-                c->cur_e = 0.0; c->start_e = 0.0; c->off = off; c->base_n = -1; c->list_cnt = 0; c->units_done = 0;
-                c->best_e = 0.0; c->best_is_cur = 1;
-                c->stream_id = a.chain_id_base + (uint64_t)chain;
-                c->rec_ptr = nullptr; c->rec_len = 0;
-                if (a.recorded) {
-                    c->rec_ptr = a.recorded + (a.rec_offsets[chain] - a.rec_base);
-                    c->rec_len = a.rec_offsets[chain + 1] - a.rec_offsets[chain];
-                }
-            }
-            __syncwarp();
-            warp_write_lf(A, s, c, 0, nl);
-            if (A.cut) warp_build_unit_list(A, s, c, 0, nl);
+            sm_load_chain<MODE>(A, s, c, load_pos);
             load_pos = -1;
             spec_ready = false;
             stage = ST_START64;
-            if (sm_publish(A, V, slot_id, c, 1, ST_START64, false)) return;             // :118 in fp64
+            if (sm_publish<MODE>(A, V, slot_id, c, 1, ST_START64, false)) return;             // :118 in fp64
             e = 0.0;
         }
-        const int nl = c->nl;
         if (stage == ST_START64) {
             if (lane == 0) { c->start_e = e; c->cur_e = e; c->best_e = e; }
             __syncwarp();
             if (PRECISE) stage = ST_NEXT;
             else {
                 stage = ST_START32;                                             // the chain's own currentEnergy, fp32-summed
-                if (sm_publish(A, V, slot_id, c, 0, ST_START32, false)) return;
+                if (sm_publish<MODE>(A, V, slot_id, c, 0, ST_START32, false)) return;
                 e = 0.0;
             }
         }
@@ -857,10 +1014,7 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 // exp(x) is exactly +0 below -746 and no uniform is < 0: reject without evaluating either; the draw
                 // is still consumed (:148).  (With K = 9e9 this is nearly every uphill move)
                 if (x < -746.0 && !c->rec_ptr) acc = false;
-                else {
-                    Stream st; st.seed = a.seed; st.id = c->stream_id; st.rec = c->rec_ptr; st.rec_len = c->rec_len;
-                    acc = st.draw(pos, status) < exp(x);
-                }
+                else acc = sm_accept_draw(a, c, x, pos, status);
                 pos += 1;
             }
             __syncwarp();
@@ -877,6 +1031,7 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 const long long out_atom = (long long)a.replicas * c->off + (long long)c->rep * c->nl - a.out_base;
                 double *bdst = a.out_best_xyzq + out_atom * 4;
                 const int cu = c->i_cur;
+                #pragma unroll 1
                 for (int i = lane; i < c->nl; i += 32) {
                     const double *p = s.xyz(cu, i);
                     bdst[4 * i] = p[0]; bdst[4 * i + 1] = p[1]; bdst[4 * i + 2] = p[2]; bdst[4 * i + 3] = s.q(i);
@@ -907,7 +1062,7 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 // the trial pose of this step: the adopted speculation (after a reject) or a proposal made here
                 ProposalResult R;
                 if (spec_ready) { R.pos = c->spec_pos; R.rej = c->spec_rej; R.status = c->spec_status; }
-                else R = sm_propose(A, s, c, c->i_cur, c->i_trial, c->pos);
+                else { PROF_T0(); R = sm_propose<MODE>(A, s, c, c->i_cur, c->i_trial, c->pos); PROF_ADD(5); }
                 spec_ready = false;
                 __syncwarp();
                 if (lane == 0) {
@@ -918,7 +1073,7 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 if (R.status & 1) finish = true;                                // retry bound: the chain ends on its current pose
                 else {
                     stage = ST_STEP;
-                    if (sm_publish(A, V, slot_id, c, PRECISE ? 1 : 0, ST_STEP, c->step + 1 < a.steps)) return;   // :127
+                    if (sm_publish<MODE>(A, V, slot_id, c, PRECISE ? 1 : 0, ST_STEP, c->step + 1 < a.steps)) return;   // :127
                     e = 0.0;
                     continue;
                 }
@@ -929,43 +1084,12 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
             stage = ST_FINAL64;
             if (PRECISE) e = c->cur_e;
             else {
-                if (sm_publish(A, V, slot_id, c, 1, ST_FINAL64, false)) return;
+                if (sm_publish<MODE>(A, V, slot_id, c, 1, ST_FINAL64, false)) return;
                 e = 0.0;
             }
         }
         if (stage == ST_FINAL64) {
-            const double final_energy = e;
-            const long long out_atom = (long long)a.replicas * c->off + (long long)c->rep * nl - a.out_base;
-            double *dst = a.out_xyzq + out_atom * 4;
-            const int cu = c->i_cur;
-            // fused CalculateRMSD (validateResults.go:50-65) of the final pose against the reference pose: same lane-strided
-            // partial sums and butterfly as rmsd_chains_kernel, so both give the same bits
-            const double4 *ref4 = a.out_rmsd ? reinterpret_cast<const double4 *>(a.ref_xyzq) + (c->off - a.atom_base) : nullptr;
-            double *bdst = (a.out_best_e && c->best_is_cur) ? a.out_best_xyzq + out_atom * 4 : nullptr;
-            double rsum = 0.0;
-            for (int i = lane; i < nl; i += 32) {
-                const double *p = s.xyz(cu, i);
-                dst[4 * i] = p[0]; dst[4 * i + 1] = p[1]; dst[4 * i + 2] = p[2]; dst[4 * i + 3] = s.q(i);
-                if (bdst) { bdst[4 * i] = p[0]; bdst[4 * i + 1] = p[1]; bdst[4 * i + 2] = p[2]; bdst[4 * i + 3] = s.q(i); }
-                if (ref4) {
-                    const double4 r = ref4[i];
-                    const double dx = p[0] - r.x, dy = p[1] - r.y, dz = p[2] - r.z;
-                    rsum += dx * dx + dy * dy + dz * dz;                       // :58-62
-                }
-            }
-            if (ref4) {
-                rsum = warp_sum(rsum);
-                if (lane == 0) a.out_rmsd[c->local] = sqrt(rsum / (double)nl);  // :64 (nl == 0 -> NaN)
-            }
-            if (lane == 0) {
-                if (a.out_best_e) a.out_best_e[c->local] = c->best_e;
-                ChainStats cs;
-                cs.accepted = c->accepted; cs.downhill = c->downhill; cs.retries = c->retries; cs.steps = c->step;
-                cs.draws = (long long)c->pos; cs.status = c->status;
-                cs.final_energy = final_energy; cs.start_energy = c->start_e; cs.chain_energy = c->cur_e;
-                reinterpret_cast<ChainStats *>(a.out_stats)[c->local] = cs;
-                if (A.out_units) A.out_units[c->local] = c->units_done;
-            }
+            sm_store_chain(A, s, c, e);
             __syncwarp();
             stage = ST_LOAD;                                // load_pos == -1: pull from the queue
         }
@@ -973,26 +1097,31 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
 }
 
 // the speculative proposal of the step after the one being evaluated: assumes a reject (pose unchanged, one accept draw)
+template <int MODE>
 __device__ __forceinline__ void sm_spec_task(const SmArgs &A, const SmView &V, int slot_id) {
     SmSlotCtl *c = V.ctl(slot_id);
     const SlotView s = V.slot(slot_id);
-    const ProposalResult R = sm_propose(A, s, c, c->i_cur, c->i_spec, c->pos + 1);
+    const ProposalResult R = sm_propose<MODE>(A, s, c, c->i_cur, c->i_spec, c->pos + 1);
     __syncwarp();
     if ((threadIdx.x & 31) == 0) { c->spec_pos = R.pos; c->spec_rej = R.rej; c->spec_status = R.status; }
 }
 
-template <bool PRECISE>
+template <bool PRECISE, int MODE>
 __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_constant__ SmArgs A) {
     extern __shared__ __align__(16) unsigned char ddd_sm_smem[];
     SmView V;
     V.raw = ddd_sm_smem; V.slots = A.slots; V.cap = A.c.nl_cap; V.ulb = A.unit_list_bytes + A.gsum_bytes + A.lj_bytes;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = A.slots;
+#ifdef DDD_SM_PROF
+    if (threadIdx.x < 16) ddd_prof[threadIdx.x] = 0;
+    const long long prof_start = clock64();
+#endif
     if (threadIdx.x == 0) *V.live() = K;
     if (threadIdx.x < kSmMaxSlots) V.keys()[threadIdx.x] = kKeyNone;
     if (threadIdx.x < K) { V.ctl(threadIdx.x)->next_item = kSlotIdle; V.ctl(threadIdx.x)->n_total = 0; V.ctl(threadIdx.x)->step = 0; }
     __syncthreads();
-    for (int sl = warp; sl < K; sl += kSmWarps) sm_serial_phase<PRECISE>(A, V, sl, (long long)sl * gridDim.x + blockIdx.x);
+    for (int sl = warp; sl < K; sl += kSmWarps) sm_serial_phase<PRECISE, MODE>(A, V, sl, (long long)sl * gridDim.x + blockIdx.x);
 
     for (;;) {
         // the chain that is furthest behind goes first: chains of an SM advance in step and end together, and one that
@@ -1007,7 +1136,7 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
         }
         if (sid < 0) {
             if (ld_volatile(V.live()) == 0) break;
-            __nanosleep(DDD_SM_IDLE_NS);
+            { PROF_T0(); __nanosleep(DDD_SM_IDLE_NS); PROF_ADD(4); PROF_CNT(12, 1); }
             continue;
         }
         SmSlotCtl *c = V.ctl(sid);
@@ -1022,21 +1151,23 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
         if (it == n_total - 1 && lane == 0) { st_volatile(V.keys() + sid, kKeyNone); st_volatile(&c->next_item, kSlotIdle); }
         if (it >= n_total) continue;
         const int has_spec = c->has_spec;                   // the speculative proposal is handed out first: it is the long pole
-        if (has_spec && it == 0) sm_spec_task(A, V, sid);
+        if (has_spec && it == 0) { PROF_T0(); sm_spec_task<MODE>(A, V, sid); PROF_ADD(2); PROF_CNT(9, 1); }
         else {
+            PROF_T0();
             const int e_it = it - has_spec;
             const SlotView s = V.slot(sid);
             const int nl = c->nl, buf = c->i_trial;
-            if (c->mode == 0 && A.gsum_bytes && !A.cut) {
+            if (c->mode == 0 && A.gsum_bytes && !mode_cut<MODE>(A)) {
                 const int gpi = c->upi_e >> 2;
-                sm_item_f32_groups(A, s.lf(buf), s.ljf(A.unit_list_bytes + A.gsum_bytes), c->apart[buf], s.gsum(A.unit_list_bytes), nl,
+                sm_item_f32_groups<MODE>(A, s.lf(buf), s.ljf(A.unit_list_bytes + A.gsum_bytes), c->apart[buf], s.gsum(A.unit_list_bytes), nl,
                                    e_it * gpi, min((e_it + 1) * gpi, A.n_groups4));
             } else {
-                const double sum = c->mode ? sm_item_f64(A, s, c, buf, nl, e_it)
-                                 : A.cut ? sm_item_f32_cut(A, s, c, buf, nl, e_it)
-                                         : sm_item_f32(A, s.lf(buf), s.ljf(A.unit_list_bytes + A.gsum_bytes), c->lbox[buf], nl, e_it);
+                const double sum = c->mode ? sm_item_f64<MODE>(A, s, c, buf, nl, e_it)
+                                 : mode_cut<MODE>(A) ? sm_item_f32_cut<MODE>(A, s, c, buf, nl, e_it)
+                                                     : sm_item_f32<MODE>(A, s.lf(buf), s.ljf(A.unit_list_bytes + A.gsum_bytes), c->lbox[buf], nl, e_it);
                 if (lane == 0) V.items(sid)[e_it] = sum;
             }
+            PROF_ADD(c->mode ? 1 : 0); PROF_CNT(8, 1);
         }
         cta_fence();
         int d = 0;
@@ -1044,9 +1175,22 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
         d = __shfl_sync(0xffffffffu, d, 0);
         if (d == n_total - 1) {                         // this warp completed the hand-out: it runs the serial phase
             cta_fence();
-            sm_serial_phase<PRECISE>(A, V, sid, -1);
+            PROF_T0();
+            sm_serial_phase<PRECISE, MODE>(A, V, sid, -1);
+            PROF_ADD(3); PROF_CNT(10, 1);
         }
     }
+#ifdef DDD_SM_PROF
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x < 4) {
+        const double tot = (double)(clock64() - prof_start) * kSmWarps;
+        printf("PROF cta %d: warp-cycles %.3e | items32 %.1f%% items64 %.1f%% spec %.1f%% serial %.1f%% (inline propose %.1f%%) idle %.1f%% celllist %.1f%% | items %llu spec %llu serial %llu attempts %llu polls %llu | cyc/item %.0f cyc/spec %.0f cyc/serial %.0f\n",
+               blockIdx.x, tot, 100.0 * ddd_prof[0] / tot, 100.0 * ddd_prof[1] / tot, 100.0 * ddd_prof[2] / tot, 100.0 * ddd_prof[3] / tot, 100.0 * ddd_prof[5] / tot,
+               100.0 * ddd_prof[4] / tot, 100.0 * ddd_prof[6] / tot, ddd_prof[8], ddd_prof[9], ddd_prof[10], ddd_prof[11], ddd_prof[12],
+               (double)ddd_prof[0] / (double)(ddd_prof[8] ? ddd_prof[8] : 1), (double)ddd_prof[2] / (double)(ddd_prof[9] ? ddd_prof[9] : 1),
+               (double)ddd_prof[3] / (double)(ddd_prof[10] ? ddd_prof[10] : 1));
+    }
+#endif
 }
 
 }  // namespace ddd
