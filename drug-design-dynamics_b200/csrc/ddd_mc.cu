@@ -213,6 +213,7 @@ struct ScreenDev {
     double *d_arg_val = nullptr;           // argmin scratch
     long long *d_arg_idx = nullptr;
     bool fused_rmsd = false;               // the last run's epilogue filled d_rmsd
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around this screen's chain kernel: its own timing and its own completion
 };
 
 struct ddd_screen {
@@ -282,6 +283,8 @@ void free_screen_dev(ScreenDev &sd, bool live) {
                     sd.d_arg_val, sd.d_arg_idx};
     cudaSetDevice(sd.dev_id);
     for (void *b : bufs) { if (!b) continue; if (live) dev_free(b); else cudaFree(b); }
+    if (sd.ev0) cudaEventDestroy(sd.ev0);
+    if (sd.ev1) cudaEventDestroy(sd.ev1);
     sd = ScreenDev();
 }
 
@@ -338,6 +341,7 @@ int screen_create_impl(const ddd_receptor *r, const int64_t *offsets, const doub
         cudaError_t ce = cudaSetDevice(g_devs[di].id);
         if (ce != cudaSuccess) guard(fail(DDD_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(ce)));
         const int64_t n_local = d.c1 - d.c0;
+        if (!rc && (cudaEventCreate(&d.ev0) != cudaSuccess || cudaEventCreate(&d.ev1) != cudaSuccess)) guard(fail(DDD_ECUDA, "cudaEventCreate failed"));
         if (!rc) guard(dev_alloc(&d.d_offsets, (size_t)n_lig + 1));
         if (!rc) guard(dev_alloc(&d.d_lig, (size_t)d.n_atoms_in * 4));
         if (!rc) guard(dev_alloc(&d.d_out, (size_t)d.out_atoms * 4));
@@ -475,7 +479,7 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
             const size_t smem = sm_smem_bytes(d.nl_cap, A.slots, ulb);
             d.threads = kSmThreads; d.slots = A.slots;
             CUDA_TRY(cudaMemsetAsync(d.d_queue, 0, sizeof(int), dev.stream));
-            CUDA_TRY(cudaEventRecord(dev.ev0, dev.stream));
+            CUDA_TRY(cudaEventRecord(d.ev0, dev.stream));
             // one instantiation per (precision, extension): the default kernel carries no cutoff / Lennard-Jones code
 #define LAUNCH_SM(PR, MD)                                                                     \
             do { if (int rc = set_smem(mc_sm_kernel<PR, MD>, smem)) return rc;                 \
@@ -485,13 +489,13 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
             else { if (mode == MODE_LJ) LAUNCH_SM(false, MODE_LJ); else if (mode == MODE_CUT) LAUNCH_SM(false, MODE_CUT); else LAUNCH_SM(false, MODE_PLAIN); }
 #undef LAUNCH_SM
             CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaEventRecord(dev.ev1, dev.stream));
+            CUDA_TRY(cudaEventRecord(d.ev1, dev.stream));
             continue;
         }
         const int threads = s->threads_override > 0 ? s->threads_override : pick_chain_threads(n_local, dev.sm_count);
         const size_t smem = chain_smem_bytes(d.nl_cap, threads);
         d.threads = threads; d.slots = 0;
-        CUDA_TRY(cudaEventRecord(dev.ev0, dev.stream));
+        CUDA_TRY(cudaEventRecord(d.ev0, dev.stream));
 #define LAUNCH_CHAIN(T, PR)                                                                   \
         do { if (int rc = set_smem(mc_chain_kernel<T, PR>, smem)) return rc;                   \
              mc_chain_kernel<T, PR><<<(unsigned)n_local, T, smem, dev.stream>>>(a); } while (0)
@@ -504,27 +508,38 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
         }
 #undef LAUNCH_CHAIN
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaEventRecord(dev.ev1, dev.stream));
+        CUDA_TRY(cudaEventRecord(d.ev1, dev.stream));
     }
     s->launched = true;
     return DDD_OK;
 }
 
-int screen_sync_impl(ddd_screen *s) {
+// Waits for the screen's own chain kernels.  `lk` (nullable): the library lock of the calling entry point -- it is released
+// while this thread blocks on the device, so that other threads can stage and launch their own batches meanwhile (they
+// queue behind this kernel on the device's stream; a goroutine per ligand block no longer serialises on the host side).
+int screen_sync_impl(ddd_screen *s, std::unique_lock<std::recursive_mutex> *lk = nullptr) {
     if (int rc0 = check_screen(s)) return rc0;
     for (auto &d : s->devs) {
         const Dev &dev = g_devs[d.di];
         CUDA_TRY(cudaSetDevice(dev.id));
-        CUDA_TRY(cudaStreamSynchronize(dev.stream));
-        if (s->launched) CUDA_TRY(cudaEventElapsedTime(&d.last_ms, dev.ev0, dev.ev1));
+        if (s->launched && d.ev1) {
+            cudaEvent_t ev = d.ev1;
+            if (lk) lk->unlock();
+            const cudaError_t ce = cudaEventSynchronize(ev);
+            if (lk) lk->lock();
+            if (ce != cudaSuccess) return fail(DDD_ECUDA, "cudaEventSynchronize failed: %s", cudaGetErrorString(ce));
+            if (int rc0 = check_screen(s)) return rc0;                    // the library was shut down while we waited
+            CUDA_TRY(cudaEventElapsedTime(&d.last_ms, d.ev0, d.ev1));
+        } else CUDA_TRY(cudaStreamSynchronize(dev.stream));
     }
     return DDD_OK;
 }
 
-int screen_download_impl(ddd_screen *s, double *out_xyzq, ddd_chain_stats *out_stats, uint8_t *out_trace) {
+int screen_download_impl(ddd_screen *s, double *out_xyzq, ddd_chain_stats *out_stats, uint8_t *out_trace,
+                         std::unique_lock<std::recursive_mutex> *lk = nullptr) {
     if (int rc0 = check_screen(s)) return rc0;
     if (!s->launched) return fail(DDD_EINVAL, "screen has not been run");
-    if (int rc = screen_sync_impl(s)) return rc;
+    if (int rc = screen_sync_impl(s, lk)) return rc;
     for (auto &d : s->devs) {
         const Dev &dev = g_devs[d.di];
         CUDA_TRY(cudaSetDevice(dev.id));
@@ -1039,14 +1054,14 @@ int ddd_run_chains(const ddd_receptor *r, const int64_t *offsets, const double *
                    const ddd_params *p, uint64_t seed, uint64_t first_chain_id,
                    const double *recorded, const int64_t *recorded_offsets,
                    double *out_xyzq, ddd_chain_stats *out_stats, uint8_t *out_accept_trace) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    std::unique_lock<std::recursive_mutex> lk(g_mu);
     REQUIRE_INIT();
     if (int rc = check_params(p)) return rc;
     if (p->lj_scale != 0.0) return fail(DDD_EINVAL, "params.lj_scale: ligand LJ parameters travel with a screen (ddd_screen_create + ddd_screen_set_lj)");
     ddd_screen *s = nullptr;
     if (int rc = screen_create_impl(r, offsets, lig_xyzq, n_lig, replicas, first_chain_id, &s)) return rc;
     int rc = screen_run_impl(s, steps_per_chain, rotate, temperature, p, seed, recorded, recorded_offsets, out_accept_trace != nullptr);
-    if (!rc) rc = screen_download_impl(s, out_xyzq, out_stats, out_accept_trace);
+    if (!rc) rc = screen_download_impl(s, out_xyzq, out_stats, out_accept_trace, &lk);
     screen_destroy_impl(s);
     g_status_bits = 0; g_status_chains = 0;
     if (!rc && out_stats)
@@ -1058,7 +1073,7 @@ int ddd_minimize_batch(const ddd_receptor *r, const int64_t *offsets, const doub
                        int64_t iterations, int32_t rotate, double temperature, int32_t num_procs,
                        const ddd_params *p, uint64_t seed, uint64_t first_ligand_index,
                        double *out_xyzq, double *out_energy, ddd_chain_stats *out_chain_stats, int64_t *out_picked) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    std::unique_lock<std::recursive_mutex> lk(g_mu);
     REQUIRE_INIT();
     g_status_bits = 0; g_status_chains = 0;
     if (num_procs <= 0) return fail(DDD_EINVAL, "num_procs must be >= 1 (the reference divides iterations by it, metropolis.go:97)");
@@ -1084,7 +1099,7 @@ int ddd_minimize_batch(const ddd_receptor *r, const int64_t *offsets, const doub
     // per-ligand results (and the 72-byte chain records) come back
     if (!rc) rc = screen_pick_impl(s, temperature, seed, first_ligand_index);
     const double t2 = now();
-    if (!rc) rc = screen_download_impl(s, nullptr, stats.data(), nullptr);
+    if (!rc) rc = screen_download_impl(s, nullptr, stats.data(), nullptr, &lk);
     if (!rc) rc = screen_download_pick(s, out_xyzq, out_energy, out_picked, nullptr);
     const double t3 = now();
     const double kms = ddd_screen_last_kernel_ms(s);
@@ -1270,9 +1285,9 @@ int32_t ddd_screen_chain_slots(const ddd_screen *s) {
 }
 
 int ddd_screen_sync(ddd_screen *s) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    std::unique_lock<std::recursive_mutex> lk(g_mu);
     REQUIRE_INIT();
-    return screen_sync_impl(s);
+    return screen_sync_impl(s, &lk);
 }
 
 double ddd_screen_last_kernel_ms(const ddd_screen *s) {
@@ -1283,9 +1298,9 @@ double ddd_screen_last_kernel_ms(const ddd_screen *s) {
 }
 
 int ddd_screen_download(ddd_screen *s, double *out_xyzq, ddd_chain_stats *out_stats) {
-    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    std::unique_lock<std::recursive_mutex> lk(g_mu);
     REQUIRE_INIT();
-    return screen_download_impl(s, out_xyzq, out_stats, nullptr);
+    return screen_download_impl(s, out_xyzq, out_stats, nullptr, &lk);
 }
 
 // CompareRMSD (validateResults.go:40-45) for every chain of the screen, device-resident: CalculateRMSD(final pose of the

@@ -43,6 +43,7 @@ import (
 	"fmt"
 	"math/rand"
 	"os"
+	"runtime"
 	"sync"
 	"sync/atomic"
 	"unsafe"
@@ -101,8 +102,7 @@ func (r dddReceptor) close() { C.ddd_receptor_release(r.h) }
 
 // dddWarnIfTruncated: a chain that needed more than max_retries collision retries in ONE step stopped there; the reference
 // would still be retrying (metropolis.go:155, :173).  Say so instead of returning a truncated chain silently.
-// (cgo calls stay on one OS thread from entry to return, and the status is thread-local in the library: call this right
-// after the batch call, in the same goroutine, with the thread locked.)
+// (The status is thread-local in the library: the callers hold runtime.LockOSThread across the batch call and this one.)
 func dddWarnIfTruncated(where string) {
 	var n C.int64_t
 	if bits := C.ddd_last_chain_status(&n); bits&C.DDD_STATUS_RETRY_LIMIT != 0 {
@@ -184,6 +184,8 @@ func SimulateMultipleLigandsParallel(protein Molecule, ligands []Molecule, itera
 		rot = 1
 	}
 	if len(ligands) > 0 {
+		runtime.LockOSThread() // the chain status below is thread-local in the library: stay on this OS thread between the two calls
+		defer runtime.UnlockOSThread()
 		var ePtr *C.double = (*C.double)(unsafe.Pointer(&energy[0]))
 		dddCheck(C.ddd_minimize_batch(rec.h, &offsets[0], flatPtr(flat), C.int64_t(len(ligands)), C.int64_t(iterations), rot,
 			C.double(temperature), C.int32_t(numProcs), &p, C.uint64_t(dddNextSeed()), 0, flatPtr(out), ePtr, nil, nil))
@@ -219,6 +221,8 @@ func runOneChain(protein, ligand Molecule, iterations int, rotate bool, temperat
 	if rotate {
 		rot = 1
 	}
+	runtime.LockOSThread() // the chain status below is thread-local in the library
+	defer runtime.UnlockOSThread()
 	dddCheck(C.ddd_run_chains(rec.h, &offsets[0], atomsPtr(ligand), 1, 1, C.int64_t(iterations), rot, C.double(temperature),
 		&p, C.uint64_t(dddNextSeed()), 0, nil, nil, flatPtr(out), &st, nil))
 	dddWarnIfTruncated("SimulateEnergyMinimizationOneProc")

@@ -284,3 +284,31 @@ def test_in_process_multi_device_matches_one_device():
     env = dict(os.environ)
     res = subprocess.run([sys.executable, str(ROOT / "tools" / "multi_gpu_check.py")], capture_output=True, text=True, timeout=1200, env=env)
     assert res.returncode == 0 and "MULTI_GPU_CHECK OK" in res.stdout, res.stdout + res.stderr
+
+
+def test_concurrent_callers_get_the_serial_results(gpu, ddd):
+    # goroutines call the batch entry points from many OS threads (metropolis.go:43, :100): the library lock is released while
+    # a caller blocks on the device, so callers overlap their staging with each other's kernels -- and results must not change
+    import threading
+    prot = ddd.synth.make_receptor(1500, seed=2)
+    off, lig = ddd.synth.make_ligands([24] * 96, prot)
+    blocks = [(0, 32), (32, 64), (64, 96)]
+    with gpu.Receptor(prot) as rec:
+        def call(b):
+            lo, hi = b
+            o = off[lo:hi + 1] - off[lo]
+            return gpu.minimize_batch(rec, o, lig[off[lo]:off[hi]], 600, True, T, 3, gpu.default_params(), seed=7, first_ligand_index=lo)
+        serial = [call(b) for b in blocks]
+        results = [None] * len(blocks)
+        def worker(k):
+            results[k] = call(blocks[k])
+        for _ in range(3):
+            threads = [threading.Thread(target=worker, args=(k,)) for k in range(len(blocks))]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            for a, b in zip(serial, results):
+                assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        whole = gpu.minimize_batch(rec, off, lig, 600, True, T, 3, gpu.default_params(), seed=7)
+        assert np.array_equal(np.concatenate([r[0] for r in serial]), whole[0])
