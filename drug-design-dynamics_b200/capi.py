@@ -21,7 +21,7 @@ SYMBOLS = [
     "ddd_closest_atom_batch", "ddd_shift_closer_batch", "ddd_randomize_pose_batch",
     "ddd_screen_create", "ddd_screen_run", "ddd_screen_sync", "ddd_screen_last_kernel_ms",
     "ddd_screen_download", "ddd_screen_destroy", "ddd_screen_set_chain_threads", "ddd_screen_chain_threads",
-    "ddd_screen_set_chain_slots", "ddd_screen_chain_slots", "ddd_screen_rmsd", "ddd_screen_pair_units", "ddd_screen_set_lj", "ddd_receptor_set_lj",
+    "ddd_screen_set_chain_slots", "ddd_screen_chain_slots", "ddd_screen_set_segment_steps", "ddd_screen_segment_steps", "ddd_screen_rmsd", "ddd_screen_pair_units", "ddd_screen_set_lj", "ddd_receptor_set_lj",
     "ddd_shard_plan", "ddd_device_info",
     "ddd_chain_kernel_info",
     "ddd_receptor_acquire", "ddd_receptor_release", "ddd_last_chain_status",
@@ -112,6 +112,8 @@ def lib() -> C.CDLL:
         "ddd_screen_chain_threads": (i32, [vp]),
         "ddd_screen_set_chain_slots": (C.c_int, [vp, i32]),
         "ddd_screen_chain_slots": (i32, [vp]),
+        "ddd_screen_set_segment_steps": (C.c_int, [vp, i64]),
+        "ddd_screen_segment_steps": (i64, [vp]),
         "ddd_screen_rmsd": (C.c_int, [vp, vp, C.POINTER(dbl)]),
         "ddd_screen_pair_units": (C.c_int, [vp, vp]),
         "ddd_screen_set_lj": (C.c_int, [vp, vp, vp]),
@@ -390,6 +392,13 @@ class Screen:
 
     def chain_slots(self) -> int:
         return int(lib().ddd_screen_chain_slots(self._h))
+
+    def set_segment_steps(self, steps: int):
+        """chain segments of the SM-persistent engine: -1 automatic, 0 whole chains, > 0 steps per segment (power of two)"""
+        _check(lib().ddd_screen_set_segment_steps(self._h, steps))
+
+    def segment_steps(self) -> int:
+        return int(lib().ddd_screen_segment_steps(self._h))
 
     def sync(self):
         _check(lib().ddd_screen_sync(self._h))

@@ -197,7 +197,10 @@ struct ScreenDev {
     float last_ms = 0.f;
     int threads = 0;                       // CTA width used by the last launch
     int slots = 0;                         // chains resident per SM in the last launch (0: one-CTA-per-chain engine)
-    int *d_queue = nullptr;                // SM-persistent engine: dynamic chain counter
+    int *d_queue = nullptr;                // SM-persistent engine: [0] dynamic chain counter, [32] park counter (own 128-byte line)
+    int *d_ring = nullptr;                 // chain segments: one entry per park of the launch (SmArgs::ring)
+    size_t ring_cap = 0;
+    long long seg_steps = 0;               // segment length of the last launch (0: whole chains)
     double *d_rmsd = nullptr;              // per-chain RMSD (ddd_screen_rmsd)
     long long *d_units = nullptr;          // per-chain receptor units evaluated (cutoff extension)
     double2 *d_lig_lj = nullptr;           // LJ extension: (sigma/2, sqrt(eps)) of this device's slice of the ligand atoms
@@ -229,6 +232,7 @@ struct ddd_screen {
     bool launched = false;
     int threads_override = 0;              // > 0: one-CTA-per-chain engine with this CTA width
     int slots_override = 0;                // > 0: SM-persistent engine with this many chains per SM; both 0: automatic
+    int64_t segment_override = -1;         // ddd_screen_set_segment_steps: -1 automatic, 0 whole chains, > 0 steps per segment (rounded up to a power of two)
     bool last_cut = false;                 // the last run used the cutoff extension
     bool has_lj = false;                   // ddd_screen_set_lj was called
 };
@@ -278,7 +282,7 @@ void plan_shards(const int64_t *offsets, int64_t n_lig, int replicas, int n_shar
 // `live`: the screen belongs to the current initialisation (frees go to the device's pool on the library's stream);
 // otherwise it outlived a ddd_shutdown and its buffers are released with plain cudaFree on the device they live on
 void free_screen_dev(ScreenDev &sd, bool live) {
-    void *bufs[] = {sd.d_offsets, sd.d_lig, sd.d_order, sd.d_out, sd.d_stats, sd.d_trace, sd.d_rec, sd.d_rec_off, sd.d_queue, sd.d_rmsd,
+    void *bufs[] = {sd.d_offsets, sd.d_lig, sd.d_order, sd.d_out, sd.d_stats, sd.d_trace, sd.d_rec, sd.d_rec_off, sd.d_queue, sd.d_ring, sd.d_rmsd,
                     sd.d_units, sd.d_lig_lj, sd.d_ref, sd.d_best, sd.d_best_e, sd.d_min, sd.d_min_e, sd.d_picked, sd.d_min_rmsd,
                     sd.d_arg_val, sd.d_arg_idx};
     cudaSetDevice(sd.dev_id);
@@ -346,7 +350,7 @@ int screen_create_impl(const ddd_receptor *r, const int64_t *offsets, const doub
         if (!rc) guard(dev_alloc(&d.d_lig, (size_t)d.n_atoms_in * 4));
         if (!rc) guard(dev_alloc(&d.d_out, (size_t)d.out_atoms * 4));
         if (!rc) guard(dev_alloc(&d.d_stats, (size_t)n_local));
-        if (!rc) guard(dev_alloc(&d.d_queue, 1));
+        if (!rc) guard(dev_alloc(&d.d_queue, 64));
         if (!rc) {
             static_assert(sizeof(long long) == sizeof(int64_t), "");
             ce = cudaMemcpyAsync(d.d_offsets, s->offsets.data(), sizeof(int64_t) * ((size_t)n_lig + 1), cudaMemcpyHostToDevice, g_devs[di].stream);
@@ -476,9 +480,30 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
                 if (!d.d_units) { if (int rc = dev_alloc(&d.d_units, (size_t)n_local)) return rc; }
                 A.out_units = d.d_units;
             }
+            // chain segments (SmArgs::seg_steps): when a launch has more chains than slots the SMs would run dry up to one chain
+            // duration apart; cut into ~32 segments per chain they run dry one segment apart.  A launch whose chains are all
+            // resident at once has nothing to rebalance (a chain cannot run faster than its own serial path).
+            long long seg = 0;
+            if (s->segment_override > 0) seg = s->segment_override;
+            else if (s->segment_override < 0 && n_local > A.first_dynamic) seg = std::max<int64_t>(64, steps / 32);
+            if (seg > 0) { long long p2 = 1; while (p2 < seg) p2 <<= 1; seg = p2; }
+            if (seg >= steps || (double)n_local * (double)((steps + std::max<long long>(seg, 1) - 1) / std::max<long long>(seg, 1)) > 2.0e9) seg = 0;
+            const long long n_seg = seg > 0 ? (steps + seg - 1) / seg : 1;
+            A.seg_steps = seg; A.n_positions = n_local * n_seg; A.ring = nullptr; A.push_ctr = d.d_queue + 32;
+            d.seg_steps = seg;
+            if (seg > 0) {
+                const size_t need = (size_t)(n_local * (n_seg - 1));
+                if (need > d.ring_cap) {
+                    dev_free(d.d_ring); d.d_ring = nullptr; d.ring_cap = 0;
+                    if (int rc = dev_alloc(&d.d_ring, need)) return rc;
+                    d.ring_cap = need;
+                }
+                CUDA_TRY(cudaMemsetAsync(d.d_ring, 0, need * sizeof(int), dev.stream));
+                A.ring = d.d_ring;
+            }
             const size_t smem = sm_smem_bytes(d.nl_cap, A.slots, ulb);
             d.threads = kSmThreads; d.slots = A.slots;
-            CUDA_TRY(cudaMemsetAsync(d.d_queue, 0, sizeof(int), dev.stream));
+            CUDA_TRY(cudaMemsetAsync(d.d_queue, 0, 64 * sizeof(int), dev.stream));
             CUDA_TRY(cudaEventRecord(d.ev0, dev.stream));
             // one instantiation per (precision, extension): the default kernel carries no cutoff / Lennard-Jones code
 #define LAUNCH_SM(PR, MD)                                                                     \
@@ -1277,6 +1302,19 @@ int ddd_screen_set_chain_slots(ddd_screen *s, int32_t slots) {
     s->slots_override = slots;
     if (slots > 0) s->threads_override = 0;
     return DDD_OK;
+}
+
+int ddd_screen_set_segment_steps(ddd_screen *s, int64_t steps) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    if (int rc0 = check_screen(s)) return rc0;
+    if (steps < -1) return fail(DDD_EINVAL, "segment steps must be -1 (automatic), 0 (whole chains) or > 0");
+    s->segment_override = steps;
+    return DDD_OK;
+}
+
+int64_t ddd_screen_segment_steps(const ddd_screen *s) {
+    if (!s || s->devs.empty()) return 0;
+    return s->devs[0].seg_steps;
 }
 
 int32_t ddd_screen_chain_slots(const ddd_screen *s) {

@@ -49,9 +49,12 @@ constexpr int kGroupsPerItemBusy = 10;     // 128-atom groups per item while >= 
 #ifndef DDD_SM_IDLE_NS
 #define DDD_SM_IDLE_NS 100
 #endif
+#ifndef DDD_SM_WAIT_NS
+#define DDD_SM_WAIT_NS 500                 // between two looks at a ring entry that is not published yet
+#endif
 constexpr double kNearMargin = DDD_NEAR_MARGIN;         // a near-pair list holds every ligand pair closer than MINDISTANCE + this
 
-enum : int { ST_START64 = 0, ST_START32 = 1, ST_STEP = 2, ST_FINAL64 = 3, ST_NEXT = 4, ST_LOAD = 5 };
+enum : int { ST_START64 = 0, ST_START32 = 1, ST_STEP = 2, ST_FINAL64 = 3, ST_NEXT = 4, ST_LOAD = 5, ST_WAIT = 6 };
 
 struct __align__(16) SmSlotCtl {
     int next_item, done_items, n_total, mode;         // n_total = n_items + has_spec; mode: 0 = fp32 items, 1 = fp64 items
@@ -78,7 +81,7 @@ struct __align__(16) SmSlotCtl {
     double best_e;                                    // lowest chain energy seen (start pose included)
     float lbox[3][8];                                 // fp32 bounding box of pose buffer b: (min xyz, -, max xyz, -)
     unsigned apart[3][2];                             // bit g: receptor group g's box is apart from pose buffer b's box (clamp-free)
-    unsigned pad4, pad5;
+    long long wait_pos;                               // ST_WAIT: the queue position (a ring entry) this slot is waiting for
 };
 static_assert(sizeof(SmSlotCtl) == 352, "SmSlotCtl is laid out as twenty-two 16-byte words");
 constexpr int kSlotFixedBytes = (int)sizeof(SmSlotCtl) + kSmMaxItems * 8 + 2 * kNearCap * 4;      // + ubuf_draws(cap) * 8, see slot_fixed_bytes
@@ -88,6 +91,8 @@ constexpr int kAtomBytes = kAtomRecBytes + 3 * 16;    // + three pair-packed fp3
 
 constexpr int kCtaHeaderBytes = 16 + 4 * kSmMaxSlots;   // live-slot count, then one scheduling key per slot
 constexpr int kKeyNone = 0x7fffffff;                    // key of a slot that has nothing to hand out
+constexpr int kKeyWait = 0x7ffffffe;                    // key of a slot that waits for a parked chain: served when no pair-sum item is on offer
+constexpr long long kStatusBestIsCur = 1ll << 30;       // parked chain records only: SmSlotCtl::best_is_cur
 
 struct SmArgs {
     ChainArgs c;
@@ -105,6 +110,13 @@ struct SmArgs {
     int lj_bytes;            // LJ extension: per slot 24 B per ligand atom ((sigma/2, sqrt eps) fp64 + pair-packed fp32), else 0
     const double2 *lig_lj;   // LJ extension: (sigma/2, sqrt eps) of the ligand atoms of this launch (atom_base-relative)
     long long *out_units;    // nullable: per-chain count of receptor units evaluated (ddd_screen_pair_units)
+    // Chain SEGMENTS (seg_steps > 0): a chain leaves its slot every seg_steps steps -- pose, energies and counters parked in
+    // its own output records -- and re-enters the launch's queue behind every other chain; any SM resumes it.  The launch's
+    // work unit shrinks from a whole chain to a segment, so the SMs run out of work together (see sm_park_chain).
+    long long seg_steps;     // a power of two; 0: chains run to completion in the slot that loaded them
+    long long n_positions;   // queue positions of the launch: n_local fresh chains + one per park (ring entry)
+    int *ring;               // [n_positions - n_local], zero before the launch: entry e = local chain + 1 of the e-th park (-1: void)
+    int *push_ctr;           // zero before the launch: parks so far
 };
 
 constexpr int kMaxLaneSumGroups = 64;       // receptors up to 8 192 atoms keep per-group, per-lane fp32 sums
@@ -843,11 +855,13 @@ __device__ __noinline__ double cold_warp_sum(double v) {
 
 // Cold path, out of line (the step loop's code should stay compact: see MODE above): load the chain at launch position
 // `load_pos` into the slot -- private copy of the start pose, counters, stream, fp32 pose, cell-list query.
+// `resume_local` >= 0: the chain was parked by sm_park_chain (possibly on another SM): same load, then the parked pose and
+// counters replace the start pose (read with ld.cg: this SM's L1 may hold the records of an earlier park of the same chain).
 template <int MODE>
-__device__ __noinline__ void sm_load_chain(const SmArgs &A, const SlotView &s, SmSlotCtl *c, long long load_pos) {
+__device__ __noinline__ void sm_load_chain(const SmArgs &A, const SlotView &s, SmSlotCtl *c, long long load_pos, long long resume_local) {
     const int lane = threadIdx.x & 31;
     const ChainArgs &a = A.c;
-    const long long local = a.order ? (long long)a.order[load_pos] : load_pos;
+    const long long local = resume_local >= 0 ? resume_local : a.order ? (long long)a.order[load_pos] : load_pos;
     const long long chain = a.chain_begin + local;
     const long long lig = chain / a.replicas;
     const long long off = a.offsets[lig];
@@ -885,11 +899,78 @@ __device__ __noinline__ void sm_load_chain(const SmArgs &A, const SlotView &s, S
         }
     }
     __syncwarp();
+    if (resume_local >= 0) {
+        const long long out_atom = (long long)a.replicas * off + (long long)c->rep * nl - a.out_base;
+        const double *parked = a.out_xyzq + out_atom * 4;
+        #pragma unroll 1
+        for (int i = lane; i < nl; i += 32) {
+            double *o = s.xyz(0, i);
+            o[0] = __ldcg(parked + 4 * i); o[1] = __ldcg(parked + 4 * i + 1); o[2] = __ldcg(parked + 4 * i + 2);
+        }
+        if (lane == 0) {
+            const long long *st = reinterpret_cast<const long long *>(reinterpret_cast<const ChainStats *>(a.out_stats) + local);
+            const double *sd = reinterpret_cast<const double *>(st);
+            static_assert(sizeof(ChainStats) == 72, "six counters, three energies");
+            c->step = __ldcg(st); c->accepted = __ldcg(st + 1); c->downhill = __ldcg(st + 2); c->retries = __ldcg(st + 3);
+            c->pos = (unsigned long long)__ldcg(st + 4);
+            const long long status = __ldcg(st + 5);
+            c->status = (int)(status & ~kStatusBestIsCur); c->best_is_cur = (status & kStatusBestIsCur) ? 1 : 0;
+            c->best_e = __ldcg(sd + 6); c->start_e = __ldcg(sd + 7); c->cur_e = __ldcg(sd + 8);
+            if (A.out_units) c->units_done = __ldcg(A.out_units + local);
+        }
+        __syncwarp();
+    }
     warp_write_lf(A, s, c, 0, nl);
     if (mode_cut<MODE>(A)) {
         if (lane == 0) c->qsum = ligand_charge_sum_f32(s.lf(0), nl);
         __syncwarp();
         warp_build_unit_list(A, s, c, 0, nl);
+    }
+}
+
+// Cold path, out of line: end of a chain SEGMENT.  The chain's state between two steps is its current pose, two energies, the
+// stream position and a few counters (the near-pair list, the fp32 pose and the speculation are functions of those): it is
+// parked in the chain's own output records (final pose, ddd_chain_stats), and the chain's index goes to the tail of the
+// launch's ring.  Whichever slot draws that queue position -- on any SM -- resumes the chain exactly where it stopped, so
+// results do not change.  Why: a launch lasts as long as its slowest SM; with whole chains as the work unit the SMs run
+// dry up to one chain duration apart (config 3 on 8 GPUs: 3.5 waves of chains per SM, 8 % lost), with segments one segment apart.
+__device__ __noinline__ void sm_park_chain(const SmArgs &A, const SlotView &s, SmSlotCtl *c) {
+    const int lane = threadIdx.x & 31;
+    const ChainArgs &a = A.c;
+    const int nl = c->nl;
+    const long long out_atom = (long long)a.replicas * c->off + (long long)c->rep * nl - a.out_base;
+    double *dst = a.out_xyzq + out_atom * 4;
+    const int cu = c->i_cur;
+    #pragma unroll 1
+    for (int i = lane; i < nl; i += 32) {
+        const double *p = s.xyz(cu, i);
+        __stcg(dst + 4 * i, p[0]); __stcg(dst + 4 * i + 1, p[1]); __stcg(dst + 4 * i + 2, p[2]);
+    }
+    if (lane == 0) {
+        long long *st = reinterpret_cast<long long *>(reinterpret_cast<ChainStats *>(a.out_stats) + c->local);
+        double *sd = reinterpret_cast<double *>(st);
+        __stcg(st, c->step); __stcg(st + 1, c->accepted); __stcg(st + 2, c->downhill); __stcg(st + 3, c->retries);
+        __stcg(st + 4, (long long)c->pos);
+        __stcg(st + 5, (long long)c->status | (c->best_is_cur ? kStatusBestIsCur : 0ll));
+        __stcg(sd + 6, c->best_e); __stcg(sd + 7, c->start_e); __stcg(sd + 8, c->cur_e);
+        if (A.out_units) __stcg(A.out_units + c->local, c->units_done);
+    }
+    __threadfence();                                    // every lane's stores are visible device-wide before the ring entry is
+    __syncwarp();
+    if (lane == 0) {
+        const int e = atomicAdd(A.push_ctr, 1);
+        atomicExch(A.ring + e, (int)c->local + 1);
+    }
+}
+
+// A chain that stops early (retry bound) will not park again: its remaining ring entries are published void, so that the
+// slots that draw those queue positions move on instead of waiting for ever.
+__device__ __noinline__ void sm_void_parks(const SmArgs &A, long long step) {
+    if ((threadIdx.x & 31) != 0) return;
+    const long long n_seg = (A.c.steps + A.seg_steps - 1) / A.seg_steps;
+    for (long long k = step / A.seg_steps; k < n_seg - 1; ++k) {
+        const int e = atomicAdd(A.push_ctr, 1);
+        atomicExch(A.ring + e, -1);
     }
 }
 
@@ -975,16 +1056,38 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                 t = __shfl_sync(0xffffffffu, t, 0);
                 load_pos = A.first_dynamic + (long long)t;
             }
-            if (load_pos >= A.n_local) {                                        // nothing left: the slot dies
+            if (load_pos >= A.n_positions) {                                    // nothing left: the slot dies
                 if (lane == 0) { st_volatile(&c->next_item, kSlotIdle); atomicSub(V.live(), 1); }
                 return;
             }
-            sm_load_chain<MODE>(A, s, c, load_pos);
+            long long resume_local = -1;
+            if (load_pos >= A.n_local) {                                        // a ring entry: the chain some slot parked (sm_park_chain)
+                int v = 0;
+                if (lane == 0) v = ld_volatile(A.ring + (load_pos - A.n_local));
+                v = __shfl_sync(0xffffffffu, v, 0);
+                if (v == 0) {                                                   // not parked yet: the slot waits; idle warps look again
+                    __nanosleep(DDD_SM_WAIT_NS);
+                    if (lane == 0) {
+                        c->wait_pos = load_pos; c->mode = 2; c->stage = ST_WAIT; c->has_spec = 0; c->n_e = 0; c->done_items = 0; c->n_total = 1;
+                    }
+                    cta_fence();
+                    __syncwarp();
+                    if (lane == 0) { st_volatile(&c->next_item, 0); st_volatile(V.keys() + slot_id, kKeyWait); }
+                    return;
+                }
+                if (v < 0) { load_pos = -1; continue; }                         // void entry (its chain stopped early)
+                __threadfence();
+                resume_local = v - 1;
+            }
+            sm_load_chain<MODE>(A, s, c, load_pos, resume_local);
             load_pos = -1;
             spec_ready = false;
-            stage = ST_START64;
-            if (sm_publish<MODE>(A, V, slot_id, c, 1, ST_START64, false)) return;             // :118 in fp64
-            e = 0.0;
+            if (resume_local >= 0) stage = ST_NEXT;
+            else {
+                stage = ST_START64;
+                if (sm_publish<MODE>(A, V, slot_id, c, 1, ST_START64, false)) return;             // :118 in fp64
+                e = 0.0;
+            }
         }
         if (stage == ST_START64) {
             if (lane == 0) { c->start_e = e; c->cur_e = e; c->best_e = e; }
@@ -1050,6 +1153,12 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
             __syncwarp();
             if (acc) spec_ready = false;                                        // the speculation assumed a reject
             stage = ST_NEXT;
+            if (A.seg_steps > 0 && c->step < a.steps && (c->step & (A.seg_steps - 1)) == 0) {   // end of a segment: back into the queue
+                sm_park_chain(A, s, c);
+                __syncwarp();
+                stage = ST_LOAD;
+                continue;
+            }
         }
         if (stage == ST_NEXT) {
             bool finish = c->step >= a.steps || c->bailed;
@@ -1070,10 +1179,13 @@ __device__ __noinline__ void sm_serial_phase(const SmArgs &A, const SmView &V, i
                     if (R.status & 1) c->bailed = 1;
                 }
                 __syncwarp();
-                if (R.status & 1) finish = true;                                // retry bound: the chain ends on its current pose
+                if (R.status & 1) {                                             // retry bound: the chain ends on its current pose
+                    finish = true;
+                    if (A.seg_steps > 0) sm_void_parks(A, c->step);
+                }
                 else {
                     stage = ST_STEP;
-                    if (sm_publish<MODE>(A, V, slot_id, c, PRECISE ? 1 : 0, ST_STEP, c->step + 1 < a.steps)) return;   // :127
+                    if (sm_publish<MODE>(A, V, slot_id, c, PRECISE ? 1 : 0, ST_STEP, c->step + 1 < a.steps && !(A.seg_steps > 0 && ((c->step + 1) & (A.seg_steps - 1)) == 0))) return;   // :127
                     e = 0.0;
                     continue;
                 }
@@ -1150,6 +1262,10 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
         // never an index that the next hand-out (with a larger n_total) would take for one of its own pieces
         if (it == n_total - 1 && lane == 0) { st_volatile(V.keys() + sid, kKeyNone); st_volatile(&c->next_item, kSlotIdle); }
         if (it >= n_total) continue;
+        if (c->mode == 2) {                                 // the slot waits for a parked chain: look at its ring entry again
+            sm_serial_phase<PRECISE, MODE>(A, V, sid, c->wait_pos);
+            continue;
+        }
         const int has_spec = c->has_spec;                   // the speculative proposal is handed out first: it is the long pole
         if (has_spec && it == 0) { PROF_T0(); sm_spec_task<MODE>(A, V, sid); PROF_ADD(2); PROF_CNT(9, 1); }
         else {

@@ -200,6 +200,14 @@ int    ddd_screen_set_chain_threads(ddd_screen *s, int32_t threads);
 int32_t ddd_screen_chain_threads(const ddd_screen *s);   /* CTA width used by the last run (1024: SM-persistent) */
 int    ddd_screen_set_chain_slots(ddd_screen *s, int32_t slots);
 int32_t ddd_screen_chain_slots(const ddd_screen *s);     /* chains per SM of the last run (0: one CTA per chain) */
+/* Chain segments of the SM-persistent engine: every `steps` steps (rounded up to a power of two) a chain leaves its slot --
+ * pose, energies, stream position and counters parked in its own output records -- and queues behind the launch's other
+ * chains; any SM resumes it.  The SMs then run out of work one segment apart instead of one chain apart (a launch lasts as
+ * long as its slowest SM).  -1 (default): automatic, ~32 segments per chain when the launch has more chains than slots;
+ * 0: whole chains.  Results never depend on it (the parked state is exact).  No reference counterpart: goroutines are
+ * scheduled by the Go runtime (metropolis.go:43, :100). */
+int    ddd_screen_set_segment_steps(ddd_screen *s, int64_t steps);
+int64_t ddd_screen_segment_steps(const ddd_screen *s);   /* segment length of the last run (0: whole chains) */
 int    ddd_screen_run(ddd_screen *s, int64_t steps_per_chain, int32_t rotate, double temperature,
                       const ddd_params *p, uint64_t seed);
 int    ddd_screen_sync(ddd_screen *s);

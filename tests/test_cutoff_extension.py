@@ -130,6 +130,11 @@ def test_cell_list_sums_equal_the_brute_force_sums(gpu, orc, ddd):
             units = scr.pair_units()
             scr.run(60, True, T, prm, seed=2)
             poses2, stats2 = scr.download()
+            scr.set_segment_steps(16)                                                       # parked and resumed three times: same bits, same counters
+            scr.run(60, True, T, prm, seed=2)
+            poses3, stats3 = scr.download()
+            assert scr.segment_steps() == 16 and np.array_equal(poses, poses3) and np.array_equal(stats, stats3)
+            assert np.array_equal(units, scr.pair_units())
             scr.close()
             e64, ab = gpu.energy_batch(rec, off, poses, gpu.default_params(precision=gpu.PRECISION_F64, cutoff=rc), with_abs=True)
             # fp32 rounding scales with the UNSHIFTED terms K|q q|/d (each 1/d is rounded before 1/rc is subtracted)

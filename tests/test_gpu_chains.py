@@ -92,6 +92,65 @@ def test_engines_agree_and_queue_refills(gpu, ddd):
     assert abs(s32["accepted"].sum() - s_sm["accepted"].sum()) <= 0.03 * s_sm["accepted"].sum()
 
 
+@pytest.mark.parametrize("seg,slots,rotate", [(16, 0, True), (32, 1, False), (64, 3, True), (16, 16, True)])
+def test_chain_segments_replay_the_oracle(gpu, orc, synth_small, seg, slots, rotate):
+    # chain segments (ddd_screen_set_segment_steps): every `seg` steps a chain is parked in its output records and resumed by
+    # whichever slot draws its queue position -- the parked state is exact, so the fp64 replay still matches the oracle step
+    # for step.  Forced on a launch with as many slots as chains (or more): the spare slots wait on the ring.
+    prot, off, lig = synth_small
+    with gpu.Receptor(prot) as rec:
+        scr = gpu.Screen(rec, off, lig, 3)
+        scr.set_chain_slots(slots)
+        scr.set_segment_steps(seg)
+        scr.run(150, rotate, T, _p64(gpu), seed=9)
+        poses, stats = scr.download()
+        assert scr.segment_steps() == seg
+        scr.close()
+    for c in range(3 * (len(off) - 1)):
+        li, r = divmod(c, 3)
+        pose_o, st_o = orc.chain(prot, lig[off[li]:off[li + 1]], 150, rotate, T, orc.philox_stream(9, c))
+        for k in ("steps", "accepted", "downhill", "retries", "draws", "status"):
+            assert stats[c][k] == st_o[k], (c, k)
+        assert np.allclose(gpu.chain_pose(off, 3, poses, li, r), pose_o, rtol=0, atol=1e-9)
+        assert stats[c]["final_energy"] == pytest.approx(st_o["final_energy"], rel=1e-11)
+        assert stats[c]["start_energy"] == pytest.approx(st_o["start_energy"], rel=1e-12)
+
+
+def test_chain_segments_do_not_change_a_bit(gpu, ddd):
+    # more chains than slots (the case segments exist for), mixed ligand sizes, production precision, best-ever tracker and
+    # fused RMSD on: whole chains == segments of 8 / 16 steps == the automatic choice, bit for bit; chains that stop at the
+    # retry bound void their remaining queue positions (nothing waits for them)
+    prot = ddd.synth.make_receptor(700, seed=5)
+    sizes = [3 + (7 * i) % 30 for i in range(500)]
+    off, lig = ddd.synth.make_ligands(sizes, prot)
+    bad = [3, 77, 401]                                        # impossible ligands: two atoms 0.01 A apart (metropolis.go:155 spins)
+    for b in bad:
+        lig[off[b] + 1, :3] = lig[off[b], :3] + np.array([0.01, 0.0, 0.0])
+    prm = gpu.default_params(max_retries=40)
+    res = {}
+    with gpu.Receptor(prot) as rec:
+        scr = gpu.Screen(rec, off, lig, 2)
+        scr.set_chain_slots(2)
+        scr.set_track_best(True)
+        for seg in (0, 8, 16, -1):
+            scr.set_segment_steps(seg)
+            scr.run(70 if seg >= 0 else 2100, True, T, prm, seed=12)
+            res[seg] = (scr.download(), scr.download_best(), scr.fused_rmsd(), scr.segment_steps())
+        scr.set_segment_steps(0)
+        scr.run(2100, True, T, prm, seed=12)
+        whole_long = (scr.download(), scr.download_best(), scr.fused_rmsd(), scr.segment_steps())
+        scr.close()
+    assert res[0][3] == 0 and res[8][3] == 8 and res[16][3] == 16 and res[-1][3] == 128 and whole_long[3] == 0
+    for seg, ref in ((8, res[0]), (16, res[0]), (-1, whole_long)):
+        (p, st), (bp, be), rm, _ = res[seg]
+        (p0, st0), (bp0, be0), rm0, _ = ref
+        assert np.array_equal(p, p0) and np.array_equal(st, st0), seg
+        assert np.array_equal(bp, bp0) and np.array_equal(be, be0) and np.array_equal(rm, rm0, equal_nan=True), seg
+    st0 = res[0][0][1]
+    stopped = np.nonzero(st0["status"] & gpu.STATUS_RETRY_LIMIT)[0]
+    assert set(stopped // 2) >= set(bad) and np.all(st0["steps"][[2 * b for b in bad]] == 0)
+
+
 def test_replay_golden_chains_on_shipped_data(gpu, sample):
     g = json.loads((GOLDEN / "oracle_golden.json").read_text())["chains"]
     with gpu.Receptor(sample["223l_protein"]) as rec:
