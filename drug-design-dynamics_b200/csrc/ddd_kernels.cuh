@@ -902,48 +902,68 @@ __device__ __forceinline__ double warp_rmsd_partial(const double4 *__restrict__ 
     return acc;
 }
 
-// One warp per (simulated, reference) pair; lane-strided atoms, coalesced; memory-bound.
+// One warp per (simulated, reference) pair at a time; lane-strided atoms, coalesced; HBM-bound.  PERSISTENT: the grid is sized to
+// the resident warps of the device and every warp walks the pairs with the grid's warp count as its stride, fetching the NEXT
+// pair's offsets before it sums the current one -- a 20..80-atom pair is one or two memory round trips, so the dependent
+// offsets -> atoms latency and the CTA turnover of a one-pair-per-warp launch cost as much as the traffic itself.
 __global__ void __launch_bounds__(256) rmsd_batch_kernel(const long long *__restrict__ offsets, long long atom_base,
                                                          const double *__restrict__ sim,
                                                          const double *__restrict__ ref, int stride,
                                                          long long n_pairs, double *__restrict__ out) {
-    const long long pair = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    long long pair = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (pair >= n_pairs) return;
     const int lane = threadIdx.x & 31;
-    const long long off = offsets[pair] - atom_base;
-    const int n = (int)(offsets[pair + 1] - offsets[pair]);
-    double acc = 0.0;
-    if (stride == 4) {
-        acc = warp_rmsd_partial(reinterpret_cast<const double4 *>(sim) + off, reinterpret_cast<const double4 *>(ref) + off, n);
-    } else {
-        const double *sp = sim + off * 3, *rp = ref + off * 3;
-        for (int i = lane; i < n; i += 32) {
-            const double dx = sp[3 * i] - rp[3 * i], dy = sp[3 * i + 1] - rp[3 * i + 1], dz = sp[3 * i + 2] - rp[3 * i + 2];
-            acc += dx * dx + dy * dy + dz * dz;
+    long long o0 = offsets[pair], o1 = offsets[pair + 1];
+    for (;;) {
+        const long long next = pair + n_warps;
+        long long n0 = 0, n1 = 0;
+        if (next < n_pairs) { n0 = offsets[next]; n1 = offsets[next + 1]; }
+        const long long off = o0 - atom_base;
+        const int n = (int)(o1 - o0);
+        double acc = 0.0;
+        if (stride == 4) {
+            acc = warp_rmsd_partial(reinterpret_cast<const double4 *>(sim) + off, reinterpret_cast<const double4 *>(ref) + off, n);
+        } else {
+            const double *sp = sim + off * 3, *rp = ref + off * 3;
+            for (int i = lane; i < n; i += 32) {
+                const double dx = sp[3 * i] - rp[3 * i], dy = sp[3 * i + 1] - rp[3 * i + 1], dz = sp[3 * i + 2] - rp[3 * i + 2];
+                acc += dx * dx + dy * dy + dz * dz;
+            }
         }
+        acc = warp_sum(acc);
+        if (lane == 0) out[pair] = sqrt(acc / (double)n);                     // :64 (n == 0 -> NaN)
+        if (next >= n_pairs) break;
+        pair = next; o0 = n0; o1 = n1;
     }
-    acc = warp_sum(acc);
-    if (lane == 0) out[pair] = sqrt(acc / (double)n);                         // :64 (n == 0 -> NaN)
 }
 
 // CalculateRMSD (validateResults.go:50-65) of every chain of a resident screen: final pose (chain-major output) against
-// the ligand's start pose, without leaving the device.  One warp per chain, 32-byte atoms (Go layout) read as double4.
+// the ligand's start pose, without leaving the device.  One warp per chain at a time (persistent, like rmsd_batch_kernel),
+// 32-byte atoms (Go layout) read as double4.
 __global__ void __launch_bounds__(256) rmsd_chains_kernel(const long long *__restrict__ offsets, const double *__restrict__ start_xyzq,
                                                           long long atom_base, const double *__restrict__ final_xyzq, long long out_base,
                                                           long long chain_begin, long long n_local, int replicas, double *__restrict__ out) {
-    const long long local = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    long long local = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (local >= n_local) return;
     const int lane = threadIdx.x & 31;
-    const long long chain = chain_begin + local;
-    const long long lig = chain / replicas;
-    const int rep = (int)(chain - lig * replicas);
-    const long long off = offsets[lig];
-    const int n = (int)(offsets[lig + 1] - off);
-    const double4 *r4 = reinterpret_cast<const double4 *>(start_xyzq) + (off - atom_base);
-    const double4 *s4 = reinterpret_cast<const double4 *>(final_xyzq) + ((long long)replicas * off + (long long)rep * n - out_base);
-    double acc = warp_rmsd_partial(s4, r4, n);
-    acc = warp_sum(acc);
-    if (lane == 0) out[local] = sqrt(acc / (double)n);                    // :64 (n == 0 -> NaN)
+    long long lig = (chain_begin + local) / replicas;
+    long long o0 = offsets[lig], o1 = offsets[lig + 1];
+    for (;;) {
+        const long long next = local + n_warps;
+        long long nlig = 0, n0 = 0, n1 = 0;
+        if (next < n_local) { nlig = (chain_begin + next) / replicas; n0 = offsets[nlig]; n1 = offsets[nlig + 1]; }
+        const int rep = (int)(chain_begin + local - lig * replicas);
+        const int n = (int)(o1 - o0);
+        const double4 *r4 = reinterpret_cast<const double4 *>(start_xyzq) + (o0 - atom_base);
+        const double4 *s4 = reinterpret_cast<const double4 *>(final_xyzq) + ((long long)replicas * o0 + (long long)rep * n - out_base);
+        double acc = warp_rmsd_partial(s4, r4, n);
+        acc = warp_sum(acc);
+        if (lane == 0) out[local] = sqrt(acc / (double)n);                // :64 (n == 0 -> NaN)
+        if (next >= n_local) break;
+        local = next; lig = nlig; o0 = n0; o1 = n1;
+    }
 }
 
 // ------------------------------------------------------------------ replica pick (metropolis.go:102-109) on device

@@ -292,6 +292,22 @@ void free_screen_dev(ScreenDev &sd, bool live) {
     sd = ScreenDev();
 }
 
+// grid of the persistent RMSD kernels: every resident warp of the device (256-thread CTAs), or one warp per pair when there are fewer
+unsigned rmsd_grid(const Dev &dev, int64_t n_pairs) {
+    static int per_sm = 0;                                                   // same kernel image on every device
+    if (per_sm == 0) {
+        int a = 0, b = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, rmsd_batch_kernel, 256, 0) != cudaSuccess) a = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, rmsd_chains_kernel, 256, 0) != cudaSuccess) b = 4;
+        per_sm = std::max(1, std::min(a, b));
+    }
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n_pairs + 7) / 8, (int64_t)dev.sm_count * per_sm));
+}
+
+// Morton-sorted receptor arrays: the units rounded up to whole groups of 8 (padding atoms: q = 0, parked far away), then one
+// more group of padding only -- its first unit is the FILLER that pads a pose's unit list to a multiple of 8 (ddd_sm_chain.cuh)
+int64_t sorted_pad_atoms(int64_t n_units_s) { return ((n_units_s + 7) / 8 * 8 + 8) * 32; }
+
 int check_receptor(const ddd_receptor *r) {
     if (!r) return fail(DDD_EINVAL, "receptor is NULL");
     if (r->epoch != g_epoch) return fail(DDD_EINVAL, "receptor handle is stale: it was created before the last ddd_shutdown / ddd_init");
@@ -443,7 +459,7 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
         if (lj && !fits_sm_engine) return fail(DDD_ELIMIT, "params.lj_scale: the ligand does not fit one SM's shared memory");
         if (cut && (s->threads_override > 0 || !fits_sm_engine))
             return fail(DDD_EINVAL, "params.cutoff needs the SM-persistent engine (chain_threads 0 and a ligand that fits one SM's shared memory)");
-        if (cut && s->rec->n_units_s > 32767) return fail(DDD_ELIMIT, "params.cutoff supports receptors up to 1048544 atoms");
+        if (cut && s->rec->n_units_s > 32752) return fail(DDD_ELIMIT, "params.cutoff supports receptors up to 1048064 atoms");
         if (s->track_best && n_local > 0 && (s->threads_override > 0 || !fits_sm_engine))
             return fail(DDD_EINVAL, "best-ever tracking needs the SM-persistent engine (chain_threads 0 and a ligand that fits one SM's shared memory)");
         if (s->threads_override <= 0 && n_local > 0 && fits_sm_engine) {
@@ -482,14 +498,19 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
             }
             // chain segments (SmArgs::seg_steps): when a launch has more chains than slots the SMs would run dry up to one chain
             // duration apart; cut into ~32 segments per chain they run dry one segment apart.  A launch whose chains are all
-            // resident at once has nothing to rebalance (a chain cannot run faster than its own serial path).
+            // resident at once has nothing to rebalance (a chain cannot run faster than its own serial path) -- unless the
+            // chains differ in cost per step: with the cutoff extension a ligand buried in the receptor has several times the
+            // units in reach of one at its surface (measured on config 4: busiest SM 1.34 x the lightest), and segments rotate
+            // the chains through the SMs.
             long long seg = 0;
             if (s->segment_override > 0) seg = s->segment_override;
-            else if (s->segment_override < 0 && n_local > A.first_dynamic) seg = std::max<int64_t>(64, steps / 32);
+            else if (s->segment_override < 0 && (n_local > A.first_dynamic || (cut && n_local > grid))) seg = std::max<int64_t>(64, steps / 32);
             if (seg > 0) { long long p2 = 1; while (p2 < seg) p2 <<= 1; seg = p2; }
             if (seg >= steps || (double)n_local * (double)((steps + std::max<long long>(seg, 1) - 1) / std::max<long long>(seg, 1)) > 2.0e9) seg = 0;
             const long long n_seg = seg > 0 ? (steps + seg - 1) / seg : 1;
             A.seg_steps = seg; A.n_positions = n_local * n_seg; A.ring = nullptr; A.push_ctr = d.d_queue + 32;
+            A.n_seg = (int)n_seg; A.seg_shift = 0;
+            while ((1ll << A.seg_shift) < seg) ++A.seg_shift;
             d.seg_steps = seg;
             if (seg > 0) {
                 const size_t need = (size_t)(n_local * (n_seg - 1));
@@ -501,7 +522,17 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
                 CUDA_TRY(cudaMemsetAsync(d.d_ring, 0, need * sizeof(int), dev.stream));
                 A.ring = d.d_ring;
             }
-            const size_t smem = sm_smem_bytes(d.nl_cap, A.slots, ulb);
+            size_t smem = sm_smem_bytes(d.nl_cap, A.slots, ulb);
+            A.box_off = 0; A.box_bytes = 0; A.gbox_count = 0;
+            if (cut) {                                                       // the cell list's box tables ride in shared memory when they fit
+                const int64_t n_groups = (s->rec->n_units_s + 3) / 4;
+                const int64_t g_entries = 2 * ((n_groups + 1) / 2 * 2), u_entries = 2 * s->rec->n_units_s;
+                const size_t off = (smem + 15) & ~(size_t)15, bytes = (size_t)(g_entries + u_entries) * sizeof(float4);
+                if (s->rec->n_units_s > 0 && off + bytes <= dev.max_smem) {
+                    A.box_off = (int)off; A.box_bytes = (int)bytes; A.gbox_count = (int)g_entries;
+                    smem = off + bytes;
+                }
+            }
             d.threads = kSmThreads; d.slots = A.slots;
             CUDA_TRY(cudaMemsetAsync(d.d_queue, 0, 64 * sizeof(int), dev.stream));
             CUDA_TRY(cudaEventRecord(d.ev0, dev.stream));
@@ -825,7 +856,7 @@ int ddd_receptor_create(const double *xyzq, int64_t n_atoms, ddd_receptor **out)
         }
         std::sort(key.begin(), key.end());
         r->n_units_s = (n_atoms + 31) / 32;
-        const int64_t n_pad_s = (r->n_units_s + 7) / 8 * 8 * 32;            // whole groups of 8 units may be read
+        const int64_t n_pad_s = sorted_pad_atoms(r->n_units_s);             // whole groups of 8 units may be read, + the filler unit
         h32s.assign((size_t)std::max<int64_t>(n_pad_s, 1), make_float4(kPadCoord, kPadCoord, kPadCoord, 0.f));
         hbox.assign((size_t)std::max<int64_t>(2 * r->n_units_s, 1), make_float4(0, 0, 0, 0));
         h64s.resize((size_t)std::max<int64_t>(n_atoms, 1));
@@ -971,7 +1002,7 @@ int ddd_receptor_set_lj(ddd_receptor *r, const double *sigma, const double *epsi
     if ((sigma == nullptr) != (epsilon == nullptr)) return fail(DDD_EINVAL, "sigma and epsilon must be given together");
     if (!sigma) { r->has_lj = false; return DDD_OK; }
     const int64_t n = r->n;
-    const size_t n_pad = (size_t)((r->n_units_s + 7) / 8 * 8 * 32);
+    const size_t n_pad = (size_t)sorted_pad_atoms(r->n_units_s);
     std::vector<double2> a((size_t)std::max<int64_t>(n, 1)), as((size_t)std::max<int64_t>(n, 1));
     std::vector<float2> fs(std::max<size_t>(n_pad, 1), make_float2(0.f, 0.f));          // padding atoms: epsilon = 0
     for (int64_t i = 0; i < n; ++i) {
@@ -1174,7 +1205,7 @@ int ddd_rmsd_batch(const int64_t *offsets, const double *sim, const double *ref,
             CUDA_TRY(cudaMemcpyAsync(d_s, sim + a0 * atom_stride, sizeof(double) * (size_t)(na * atom_stride), cudaMemcpyHostToDevice, dev.stream));
             CUDA_TRY(cudaMemcpyAsync(d_r, ref + a0 * atom_stride, sizeof(double) * (size_t)(na * atom_stride), cudaMemcpyHostToDevice, dev.stream));
         }
-        rmsd_batch_kernel<<<(unsigned)((np_blk + 7) / 8), 256, 0, dev.stream>>>(d_off, a0, d_s, d_r, atom_stride, np_blk, d_o);
+        rmsd_batch_kernel<<<rmsd_grid(dev, np_blk), 256, 0, dev.stream>>>(d_off, a0, d_s, d_r, atom_stride, np_blk, d_o);
         CUDA_TRY(cudaGetLastError());
         later.push_back([=]() -> int {
             CUDA_TRY(cudaSetDevice(dev.id));
@@ -1355,7 +1386,7 @@ int ddd_screen_rmsd(ddd_screen *s, double *out_rmsd, double *out_kernel_ms) {
         const int64_t n_local = d.c1 - d.c0;
         if (!d.d_rmsd) { if (int rc = dev_alloc(&d.d_rmsd, (size_t)n_local)) return rc; }
         CUDA_TRY(cudaEventRecord(dev.ev0, dev.stream));
-        rmsd_chains_kernel<<<(unsigned)((n_local + 7) / 8), 256, 0, dev.stream>>>(d.d_offsets, d.d_lig, d.atom_base, d.d_out, d.out_base,
+        rmsd_chains_kernel<<<rmsd_grid(dev, n_local), 256, 0, dev.stream>>>(d.d_offsets, d.d_lig, d.atom_base, d.d_out, d.out_base,
                                                                                d.c0, n_local, s->replicas, d.d_rmsd);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(dev.ev1, dev.stream));

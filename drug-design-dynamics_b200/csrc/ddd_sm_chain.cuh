@@ -117,6 +117,10 @@ struct SmArgs {
     long long n_positions;   // queue positions of the launch: n_local fresh chains + one per park (ring entry)
     int *ring;               // [n_positions - n_local], zero before the launch: entry e = local chain + 1 of the e-th park (-1: void)
     int *push_ctr;           // zero before the launch: parks so far
+    int n_seg, seg_shift;    // segments per chain; seg_steps == 1 << seg_shift
+    // cutoff extension: the cell list's box tables (group boxes, then unit boxes) staged in shared memory behind the slots when
+    // they fit -- every proposal that passes its collision test scans them, one warp chasing loads (0: they stay in global memory)
+    int box_off, box_bytes, gbox_count;      // byte offset in the CTA's dynamic shared memory; total bytes; float4 entries of the group table
 };
 
 constexpr int kMaxLaneSumGroups = 64;       // receptors up to 8 192 atoms keep per-group, per-lane fp32 sums
@@ -290,12 +294,17 @@ __device__ __noinline__ double sm_item_f32(const SmArgs &A, const float4 *lf, co
 // is (unit id | kUnitApart): the flag says the unit's box is farther than the clamp distance from the pose's box, so the
 // clamp-free loop applies (same bits).  Eight units (8 receptor atoms per lane) go through the loop together.
 constexpr unsigned kUnitApart = 0x8000u;
+// n_surv[buf] of a listed pose: (units really within reach) << 16 | (list length: the same rounded up to a multiple of 8 with
+// the receptor's FILLER unit -- 32 padding atoms, q = 0 -- so that the fp32 sums only ever run the 8-atoms-per-lane loop);
+// -1: list overflow, the sums run over every unit (the sorted receptor is padded to whole groups of 8 as well)
+__device__ __forceinline__ int surv_len(const SmArgs &A, int ns) { return ns >= 0 ? (ns & 0xffff) : ((A.c.rec.n_units_s + 7) & ~7); }
+__device__ __forceinline__ int surv_real(const SmArgs &A, int ns) { return ns >= 0 ? (ns >> 16) : A.c.rec.n_units_s; }
 template <int MODE>
 __device__ __forceinline__ double sm_item_f32_cut(const SmArgs &A, const SlotView &s, const SmSlotCtl *c, int buf, int nl, int it) {
     const ulonglong2 *lf2 = reinterpret_cast<const ulonglong2 *>(s.lf(buf));
     const int n_pairs = (nl + 1) >> 1;
     const int ns = c->n_surv[buf];
-    const int nu = ns >= 0 ? ns : A.c.rec.n_units_s;
+    const int nu = surv_len(A, ns);
     const unsigned short *ul = s.units(buf);
     const int upi = c->upi_e;
     int j = it * upi;
@@ -340,18 +349,7 @@ __device__ __forceinline__ double sm_item_f32_cut(const SmArgs &A, const SlotVie
         else hi = warp_units_sum_f32<8, true, true>(rec, ub, lf2, n_pairs, rmax, rci, &lo, rc_q);
         acc += (double)lo + (double)hi;
     }
-    if (j + 4 <= j1) {
-        int ub[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) ub[a] = 32 * (ns >= 0 ? (int)(ul[j + a] & ~kUnitApart) : j + a);
-        acc += (double)warp_units_sum_f32<4, true, true>(rec, ub, lf2, n_pairs, rmax, rci, nullptr, rc_q);
-        j += 4;
-    }
-    for (; j < j1; ++j) {
-        int ub[1] = {32 * (ns >= 0 ? (int)(ul[j] & ~kUnitApart) : j)};
-        acc += (double)warp_units_sum_f32<1, true, true>(rec, ub, lf2, n_pairs, rmax, rci, nullptr, rc_q);
-    }
-    return warp_sum(acc);
+    return warp_sum(acc);                               // lists and items are whole groups of 8 units: no remainder
 }
 
 // LJ extension, one pair in fp64, in the CPU restatement's expression order: pj / lj = (sigma/2, sqrt eps)
@@ -372,7 +370,7 @@ __device__ __noinline__ double sm_item_f64(const SmArgs &A, const SlotView &s, c
     double e = 0.0;
     if (mode_cut<MODE>(A)) {                                                          // the pose's cell-list units, exact per-pair test
         const int ns = c->n_surv[buf];
-        const int nu = ns >= 0 ? ns : A.c.rec.n_units_s;
+        const int nu = surv_len(A, ns);
         const unsigned short *ul = s.units(buf);
         const int j1 = min((it + 1) * c->upi_e, nu);
         for (int j = it * c->upi_e; j < j1; ++j) {
@@ -537,6 +535,10 @@ __device__ __noinline__ void warp_build_unit_list(const SmArgs &A, const SlotVie
     unsigned short *ul = s.units(buf);
     const int n_units = A.c.rec.n_units_s;
     const float gap_apart = A.c.prm.apart_gap;
+    extern __shared__ __align__(16) unsigned char ddd_sm_smem[];
+    const bool staged = A.box_bytes != 0;
+    const float4 *gbox = staged ? reinterpret_cast<const float4 *>(ddd_sm_smem + A.box_off) : A.c.rec.gbox;
+    const float4 *ubox = staged ? reinterpret_cast<const float4 *>(ddd_sm_smem + A.box_off) + A.gbox_count : A.c.rec.ubox;
     bool apart_out = false;                                               // side result of the last test: the boxes are farther apart than the clamp margin
     auto within = [&](const float4 bmin, const float4 bmax) {
         const float gx = fmaxf(0.f, fmaxf(bmin.x - hi[0], lo[0] - bmax.x));
@@ -552,13 +554,15 @@ __device__ __noinline__ void warp_build_unit_list(const SmArgs &A, const SlotVie
     const int n_groups = (n_units + 3) >> 2;
     int n_g = 0;
     // the query is one warp chasing global loads: pull every group box towards L1 first (one round trip instead of one per step)
+    if (!staged) {
 #pragma unroll 1
-    for (int b = lane; b < n_groups; b += 32) asm volatile("prefetch.global.L1 [%0];" :: "l"(A.c.rec.gbox + 2 * b));
+        for (int b = lane; b < n_groups; b += 32) asm volatile("prefetch.global.L1 [%0];" :: "l"(A.c.rec.gbox + 2 * b));
+    }
 #pragma unroll 1
     for (int b = 0; b < n_groups; b += 32) {
         const int g = b + lane;
         const int gc = min(g, n_groups - 1);
-        const bool keep = g < n_groups && nl > 0 && within(__ldg(A.c.rec.gbox + 2 * gc), __ldg(A.c.rec.gbox + 2 * gc + 1));
+        const bool keep = g < n_groups && nl > 0 && within(gbox[2 * gc], gbox[2 * gc + 1]);
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         if (keep) {
             const int idx = n_g + __popc(m & ((1u << lane) - 1));
@@ -571,17 +575,19 @@ __device__ __noinline__ void warp_build_unit_list(const SmArgs &A, const SlotVie
     int count = 0;
     if (n_g > kGroupCap) count = kUnitCap + 1;                            // more than 1024 units in reach: overflow
     else {
+        if (!staged) {
 #pragma unroll 1
-        for (int e = lane; e < 4 * n_g; e += 32) {
-            const int u = min(4 * (int)grp[e >> 2] + (e & 3), n_units - 1);
-            asm volatile("prefetch.global.L1 [%0];" :: "l"(A.c.rec.ubox + 2 * u));
+            for (int e = lane; e < 4 * n_g; e += 32) {
+                const int u = min(4 * (int)grp[e >> 2] + (e & 3), n_units - 1);
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(A.c.rec.ubox + 2 * u));
+            }
         }
 #pragma unroll 1
         for (int b = 0; b < 4 * n_g; b += 32) {
             const int e = b + lane;
             const int u = e < 4 * n_g ? 4 * (int)grp[e >> 2] + (e & 3) : n_units;
             const int uc = min(u, n_units - 1);
-            const float4 bmin = __ldg(A.c.rec.ubox + 2 * uc), bmax = __ldg(A.c.rec.ubox + 2 * uc + 1);
+            const float4 bmin = ubox[2 * uc], bmax = ubox[2 * uc + 1];
             const bool keep = within(bmin, bmax) && u < n_units;
             const bool apart = apart_out;
             const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -593,7 +599,11 @@ __device__ __noinline__ void warp_build_unit_list(const SmArgs &A, const SlotVie
         }
     }
     __syncwarp();
-    if (lane == 0) c->n_surv[buf] = count <= kUnitCap ? count : -1;
+    if (count <= kUnitCap) {                                                // filler entries up to the next multiple of 8 (kUnitCap is one)
+        const int padded = (count + 7) & ~7;
+        if (count + lane < padded) ul[count + lane] = (unsigned short)((unsigned)((n_units + 7) & ~7) | kUnitApart);
+        if (lane == 0) c->n_surv[buf] = count << 16 | padded;
+    } else if (lane == 0) c->n_surv[buf] = -1;
     __syncwarp();
 }
 
@@ -822,10 +832,10 @@ __device__ __noinline__ bool sm_publish(const SmArgs &A, const SmView &V, int sl
     }
     if (mode_cut<MODE>(A)) {
         const int ns = c->n_surv[c->i_trial];
-        const int nu = ns >= 0 ? ns : A.c.rec.n_units_s;
+        const int nu = surv_len(A, ns);
         upi_e = 16 * max(1, (nu + 16 * kSmMaxItems - 1) / (16 * kSmMaxItems));  // runs of 16 units (two 8-atoms-per-lane calls; the second is prefetched), more only for huge lists
         n_e = (nu + upi_e - 1) / upi_e;
-        if ((threadIdx.x & 31) == 0 && mode == 0) c->units_done += nu;
+        if ((threadIdx.x & 31) == 0 && mode == 0) c->units_done += surv_real(A, ns);
     }
     if (n_e == 0 && (!with_spec || A.n_items == 0)) {
         if ((threadIdx.x & 31) == 0) { c->mode = mode; c->stage = stage; c->has_spec = 0; c->n_e = 0; }
@@ -967,8 +977,8 @@ __device__ __noinline__ void sm_park_chain(const SmArgs &A, const SlotView &s, S
 // slots that draw those queue positions move on instead of waiting for ever.
 __device__ __noinline__ void sm_void_parks(const SmArgs &A, long long step) {
     if ((threadIdx.x & 31) != 0) return;
-    const long long n_seg = (A.c.steps + A.seg_steps - 1) / A.seg_steps;
-    for (long long k = step / A.seg_steps; k < n_seg - 1; ++k) {
+    #pragma unroll 1
+    for (long long k = step >> A.seg_shift; k < A.n_seg - 1; ++k) {
         const int e = atomicAdd(A.push_ctr, 1);
         atomicExch(A.ring + e, -1);
     }
@@ -1229,6 +1239,12 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
     if (threadIdx.x < 16) ddd_prof[threadIdx.x] = 0;
     const long long prof_start = clock64();
 #endif
+    if (MODE != MODE_PLAIN && A.box_bytes) {              // cutoff extension: the box tables of the cell list, staged once per CTA
+        float4 *dst = reinterpret_cast<float4 *>(ddd_sm_smem + A.box_off);
+        const int n_u = A.box_bytes / 16 - A.gbox_count;
+        for (int i = threadIdx.x; i < A.gbox_count; i += kSmThreads) dst[i] = __ldg(A.c.rec.gbox + i);
+        for (int i = threadIdx.x; i < n_u; i += kSmThreads) dst[A.gbox_count + i] = __ldg(A.c.rec.ubox + i);
+    }
     if (threadIdx.x == 0) *V.live() = K;
     if (threadIdx.x < kSmMaxSlots) V.keys()[threadIdx.x] = kKeyNone;
     if (threadIdx.x < K) { V.ctl(threadIdx.x)->next_item = kSlotIdle; V.ctl(threadIdx.x)->n_total = 0; V.ctl(threadIdx.x)->step = 0; }
