@@ -329,7 +329,7 @@ def run_ours(args, capi, torch, dist, peaks, peaks_src, go, prot, off, lig, firs
     # a chain that needs more than max_retries (1024) collision retries in ONE step stops there (the reference would spin,
     # metropolis.go:173): counted below, and only the steps really executed enter the metric
     assert my_steps >= 0.99 * n_lig * replicas * args.chain_steps, "too many chains stopped early"
-    width, slots = scr.chain_threads(), scr.chain_slots()
+    width, slots, seg_steps = scr.chain_threads(), scr.chain_slots(), scr.segment_steps()
     scr.close()
     dev_s = max_over_ranks(kernel_ms * 1e-3)          # max over ranks of the device time of K steps
     wall_s = max_over_ranks(wall)
@@ -409,7 +409,7 @@ def run_ours(args, capi, torch, dist, peaks, peaks_src, go, prot, off, lig, firs
            if visited_pairs is not None else {}),
         "config": config_dict(args, desc, n_lig, replicas, world,
                               pair_precision="fp32 terms, fp64 accumulation", chain_cta_threads=width, chains_per_sm=slots,
-                              chains_stopped_at_retry_bound=n_bailed_all,
+                              chains_stopped_at_retry_bound=n_bailed_all, chain_segment_steps=seg_steps,
                               engine="SM-persistent (one CTA per SM, speculative proposals)" if slots else "one CTA per chain",
                               l2=f"receptor ({NP * 16 // 1024} KB fp32) and poses are L1/L2-resident by design; the kernel is FP32/MUFU-bound, HBM traffic ~0, "
                                  "so no L2 flush applies"),

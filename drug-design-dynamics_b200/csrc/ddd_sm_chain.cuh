@@ -49,6 +49,9 @@ constexpr int kGroupsPerItemBusy = 10;     // 128-atom groups per item while >= 
 #ifndef DDD_SM_IDLE_NS
 #define DDD_SM_IDLE_NS 100
 #endif
+#ifndef DDD_CUT_UPI
+#define DDD_CUT_UPI 16                     // cutoff extension: receptor units per pair-sum item (a multiple of 8)
+#endif
 #ifndef DDD_SM_WAIT_NS
 #define DDD_SM_WAIT_NS 500                 // between two looks at a ring entry that is not published yet
 #endif
@@ -290,10 +293,8 @@ __device__ __noinline__ double sm_item_f32(const SmArgs &A, const float4 *lf, co
 }
 
 // cutoff extension: item `it` covers entries [it*upi, (it+1)*upi) of the pose's unit list (or of all units after a list
-// overflow); the units are whatever the Morton order put within reach, so each call gathers its own bases.  A list entry
-// is (unit id | kUnitApart): the flag says the unit's box is farther than the clamp distance from the pose's box, so the
-// clamp-free loop applies (same bits).  Eight units (8 receptor atoms per lane) go through the loop together.
-constexpr unsigned kUnitApart = 0x8000u;
+// overflow); the units are whatever the Morton order put within reach, so each call gathers its own bases.  Eight units
+// (8 receptor atoms per lane) go through the loop together.
 // n_surv[buf] of a listed pose: (units really within reach) << 16 | (list length: the same rounded up to a multiple of 8 with
 // the receptor's FILLER unit -- 32 padding atoms, q = 0 -- so that the fp32 sums only ever run the 8-atoms-per-lane loop);
 // -1: list overflow, the sums run over every unit (the sorted receptor is padded to whole groups of 8 as well)
@@ -317,11 +318,11 @@ __device__ __forceinline__ double sm_item_f32_cut(const SmArgs &A, const SlotVie
         for (; j + 4 <= j1; j += 4) {
             int ub[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) ub[a] = 32 * (ns >= 0 ? (int)(ul[j + a] & ~kUnitApart) : j + a);
+            for (int a = 0; a < 4; ++a) ub[a] = 32 * (ns >= 0 ? (int)(ul[j + a]) : j + a);
             acc += (double)warp_units_sum_lj_f32<4, true>(rec, A.c.rec.lj32s, ub, lf2, ljp, n_pairs, rmax, rci, A.c.prm.lj_c32, A.c.prm.lj_cap32);
         }
         for (; j < j1; ++j) {
-            int ub[1] = {32 * (ns >= 0 ? (int)(ul[j] & ~kUnitApart) : j)};
+            int ub[1] = {32 * (ns >= 0 ? (int)(ul[j]) : j)};
             acc += (double)warp_units_sum_lj_f32<1, true>(rec, A.c.rec.lj32s, ub, lf2, ljp, n_pairs, rmax, rci, A.c.prm.lj_c32, A.c.prm.lj_cap32);
         }
         return warp_sum(acc);
@@ -332,21 +333,19 @@ __device__ __forceinline__ double sm_item_f32_cut(const SmArgs &A, const SlotVie
     const float rc_q = rci * c->qsum;                   // (1/cutoff) * sum_l q_l: the constant part of the shifted terms
     for (; j + 8 <= j1; j += 8) {
         int ub[8];
-        unsigned ap = kUnitApart;
 #pragma unroll
-        for (int a = 0; a < 8; ++a) {
-            const unsigned e = ns >= 0 ? (unsigned)ul[j + a] : (unsigned)(j + a);
-            ub[a] = 32 * (int)(e & ~kUnitApart);
-            ap &= e;
-        }
+        for (int a = 0; a < 8; ++a) ub[a] = 32 * (ns >= 0 ? (int)ul[j + a] : j + a);
         if (j + 16 <= j1) {
 #pragma unroll
             for (int a = 0; a < 8; ++a)
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(rec + 32 * (ns >= 0 ? (int)(ul[j + 8 + a] & ~kUnitApart) : j + 8 + a) + lane));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(rec + 32 * (ns >= 0 ? (int)ul[j + 8 + a] : j + 8 + a) + lane));
         }
-        float lo, hi;
-        if (ap) hi = warp_units_sum_f32<8, true, false>(rec, ub, lf2, n_pairs, rmax, rci, &lo, rc_q);
-        else hi = warp_units_sum_f32<8, true, true>(rec, ub, lf2, n_pairs, rmax, rci, &lo, rc_q);
+        // ONE loop variant, the clamped one: with ~60 units per evaluation this kernel is bound by instruction fetch on its
+        // serial side (ncu: half of those warps' stall samples are no_instruction; the step's hot code is ~45 KB against a
+        // 32 KB instruction cache), and a second copy of the loop without the clamp's two FMNMX cost more there than it saved
+        // here (measured on config 4: 314 -> 307 ms)
+        float lo;
+        const float hi = warp_units_sum_f32<8, true, true>(rec, ub, lf2, n_pairs, rmax, rci, &lo, rc_q);
         acc += (double)lo + (double)hi;
     }
     return warp_sum(acc);                               // lists and items are whole groups of 8 units: no remainder
@@ -374,7 +373,7 @@ __device__ __noinline__ double sm_item_f64(const SmArgs &A, const SlotView &s, c
         const unsigned short *ul = s.units(buf);
         const int j1 = min((it + 1) * c->upi_e, nu);
         for (int j = it * c->upi_e; j < j1; ++j) {
-            const int p = 32 * (ns >= 0 ? (int)(ul[j] & ~kUnitApart) : j) + (int)(threadIdx.x & 31);
+            const int p = 32 * (ns >= 0 ? (int)(ul[j]) : j) + (int)(threadIdx.x & 31);
             if (p >= A.c.rec.n) continue;
             const Atom64 P = A.c.rec.f64s[p];
             const double2 PJ = lj ? A.c.rec.lj64s[p] : make_double2(0.0, 0.0);
@@ -534,17 +533,14 @@ __device__ __noinline__ void warp_build_unit_list(const SmArgs &A, const SlotVie
     const float rc2 = rc * rc * 1.0001f + 1e-3f;                      // conservative: fp32 boxes, fp32 pose
     unsigned short *ul = s.units(buf);
     const int n_units = A.c.rec.n_units_s;
-    const float gap_apart = A.c.prm.apart_gap;
     extern __shared__ __align__(16) unsigned char ddd_sm_smem[];
     const bool staged = A.box_bytes != 0;
     const float4 *gbox = staged ? reinterpret_cast<const float4 *>(ddd_sm_smem + A.box_off) : A.c.rec.gbox;
     const float4 *ubox = staged ? reinterpret_cast<const float4 *>(ddd_sm_smem + A.box_off) + A.gbox_count : A.c.rec.ubox;
-    bool apart_out = false;                                               // side result of the last test: the boxes are farther apart than the clamp margin
     auto within = [&](const float4 bmin, const float4 bmax) {
         const float gx = fmaxf(0.f, fmaxf(bmin.x - hi[0], lo[0] - bmax.x));
         const float gy = fmaxf(0.f, fmaxf(bmin.y - hi[1], lo[1] - bmax.y));
         const float gz = fmaxf(0.f, fmaxf(bmin.z - hi[2], lo[2] - bmax.z));
-        apart_out = fmaxf(gx, fmaxf(gy, gz)) > gap_apart;                 // == boxes_apart(bmin, bmax, lbox, gap)
         return gx * gx + gy * gy + gz * gz < rc2;
     };
     // level 1: the boxes of the groups of 4 units; the survivors' ids are staged in the (idle) dynamic near-pair list.
@@ -589,11 +585,10 @@ __device__ __noinline__ void warp_build_unit_list(const SmArgs &A, const SlotVie
             const int uc = min(u, n_units - 1);
             const float4 bmin = ubox[2 * uc], bmax = ubox[2 * uc + 1];
             const bool keep = within(bmin, bmax) && u < n_units;
-            const bool apart = apart_out;
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             if (keep) {
                 const int idx = count + __popc(m & ((1u << lane) - 1));
-                if (idx < kUnitCap) ul[idx] = (unsigned short)((unsigned)u | (apart ? kUnitApart : 0u));
+                if (idx < kUnitCap) ul[idx] = (unsigned short)u;
             }
             count += __popc(m);
         }
@@ -601,7 +596,7 @@ __device__ __noinline__ void warp_build_unit_list(const SmArgs &A, const SlotVie
     __syncwarp();
     if (count <= kUnitCap) {                                                // filler entries up to the next multiple of 8 (kUnitCap is one)
         const int padded = (count + 7) & ~7;
-        if (count + lane < padded) ul[count + lane] = (unsigned short)((unsigned)((n_units + 7) & ~7) | kUnitApart);
+        if (count + lane < padded) ul[count + lane] = (unsigned short)((n_units + 7) & ~7);
         if (lane == 0) c->n_surv[buf] = count << 16 | padded;
     } else if (lane == 0) c->n_surv[buf] = -1;
     __syncwarp();
@@ -833,7 +828,7 @@ __device__ __noinline__ bool sm_publish(const SmArgs &A, const SmView &V, int sl
     if (mode_cut<MODE>(A)) {
         const int ns = c->n_surv[c->i_trial];
         const int nu = surv_len(A, ns);
-        upi_e = 16 * max(1, (nu + 16 * kSmMaxItems - 1) / (16 * kSmMaxItems));  // runs of 16 units (two 8-atoms-per-lane calls; the second is prefetched), more only for huge lists
+        upi_e = DDD_CUT_UPI * max(1, (nu + DDD_CUT_UPI * kSmMaxItems - 1) / (DDD_CUT_UPI * kSmMaxItems));  // runs of 16 units (two 8-atoms-per-lane calls; the second is prefetched), more only for huge lists
         n_e = (nu + upi_e - 1) / upi_e;
         if ((threadIdx.x & 31) == 0 && mode == 0) c->units_done += surv_real(A, ns);
     }
@@ -1250,18 +1245,17 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
     if (threadIdx.x < K) { V.ctl(threadIdx.x)->next_item = kSlotIdle; V.ctl(threadIdx.x)->n_total = 0; V.ctl(threadIdx.x)->step = 0; }
     __syncthreads();
     for (int sl = warp; sl < K; sl += kSmWarps) sm_serial_phase<PRECISE, MODE>(A, V, sl, (long long)sl * gridDim.x + blockIdx.x);
+    const unsigned keys_s = (unsigned)__cvta_generic_to_shared(V.keys());
 
     for (;;) {
         // the chain that is furthest behind goes first: chains of an SM advance in step and end together, and one that
         // loses time in collision retries gets its pair sums served ahead of the others
-        int sid = -1, best = kKeyNone;
-#pragma unroll
-        for (int t = 0; t < kSmMaxSlots; ++t) {             // all K keys in flight at once
-            if (t < K) {
-                const int key = ld_volatile(V.keys() + t);
-                if (key < best) { best = key; sid = t; }
-            }
-        }
+        // (one key per lane, one shared-memory load and a warp-wide minimum: the 16-way unrolled scan this replaces was 75
+        // instructions on every look -- 5 % of all instructions executed with the cutoff extension, ncu)
+        int key = kKeyNone;
+        if (lane < K) asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(key) : "r"(keys_s + 4u * (unsigned)lane) : "memory");
+        const int best = __reduce_min_sync(0xffffffffu, key);
+        const int sid = best == kKeyNone ? -1 : __ffs(__ballot_sync(0xffffffffu, key == best)) - 1;     // ties: the lowest slot
         if (sid < 0) {
             if (ld_volatile(V.live()) == 0) break;
             { PROF_T0(); __nanosleep(DDD_SM_IDLE_NS); PROF_ADD(4); PROF_CNT(12, 1); }
