@@ -344,7 +344,9 @@ def test_f32_chains_match_oracle_statistics(gpu, orc, ddd):
                 assert stats[c]["draws"] == st_o["draws"] and stats[c]["retries"] == st_o["retries"]
         acc_o = np.array(acc_o)
         assert abs(stats["accepted"].mean() - acc_o.mean()) <= 0.02 * max(1.0, acc_o.mean())
-        assert len(same) >= 0.85 * 48                                # most chains never meet an fp32 near-tie
+        # measured on B200 (tools/f32_divergence.py, profiles/r02_f32_trace_divergence.json): 46 / 48 identical traces without
+        # rotation (the two others part at steps 50-99 and 200-249: an fp32 near-tie), 48 / 48 with it
+        assert len(same) >= 44
         # the chain's own fp32-summed energy agrees with the fp64 energy of the same pose (conditioning-aware)
         e, ab = gpu.energy_batch(gpu.Receptor(prot), off, poses, gpu.default_params(precision=gpu.PRECISION_F64), with_abs=True)
         assert np.all(np.abs(e - stats["final_energy"]) <= 1e-13 * ab)          # same fp64 terms, different summation order
