@@ -251,7 +251,7 @@ int pick_chain_threads(int64_t n_chains, int sm_count) {
 
 // Chains resident per SM in the SM-persistent engine.  A launch whose chains all fit (<= grid * kSlotsAuto) is
 // dealt statically, ceil(n/grid) per SM; beyond that slots refill from the launch's queue as chains finish.
-constexpr int kSlotsAuto = 8;
+constexpr int kSlotsAuto = 10;    // measured on a config 3 shard (4096 chains): 6 / 8 / 10 / 12 / 14 chains per SM -> 56.7 / 57.1 / 57.4 / 57.4 / 57.3 % of FP32 peak
 int pick_chain_slots(int64_t n_chains, int grid) {
     const int64_t per_sm = (n_chains + grid - 1) / std::max(grid, 1);
     return (int)std::max<int64_t>(1, std::min<int64_t>(kSlotsAuto, per_sm));
@@ -330,6 +330,9 @@ int screen_create_impl(const ddd_receptor *r, const int64_t *offsets, const doub
     ddd_screen *s = new ddd_screen();
     s->epoch = g_epoch;
     s->rec = r; s->n_lig = n_lig; s->replicas = replicas; s->n_chains = n_lig * replicas; s->chain_id_base = first_chain_id;
+    // testing knob: the default segment length of every screen this process creates, the one-shot entry points included
+    // (ddd_screen_set_segment_steps overrides it); results never depend on it
+    if (const char *e = std::getenv("DDD_SEGMENT_STEPS")) { const long long v = std::atoll(e); if (v >= -1) s->segment_override = v; }
     s->offsets.assign(offsets ? offsets : nullptr, offsets ? offsets + n_lig + 1 : nullptr);
     if (s->offsets.empty()) s->offsets.push_back(0);
     std::vector<int64_t> begin;

@@ -205,7 +205,8 @@ int32_t ddd_screen_chain_slots(const ddd_screen *s);     /* chains per SM of the
  * chains; any SM resumes it.  The SMs then run out of work one segment apart instead of one chain apart (a launch lasts as
  * long as its slowest SM).  -1 (default): automatic, ~32 segments per chain when the launch has more chains than slots;
  * 0: whole chains.  Results never depend on it (the parked state is exact).  No reference counterpart: goroutines are
- * scheduled by the Go runtime (metropolis.go:43, :100). */
+ * scheduled by the Go runtime (metropolis.go:43, :100).  The environment variable DDD_SEGMENT_STEPS sets the default of
+ * every screen created afterwards, the one-shot entry points' internal screens included (a testing knob). */
 int    ddd_screen_set_segment_steps(ddd_screen *s, int64_t steps);
 int64_t ddd_screen_segment_steps(const ddd_screen *s);   /* segment length of the last run (0: whole chains) */
 int    ddd_screen_run(ddd_screen *s, int64_t steps_per_chain, int32_t rotate, double temperature,

@@ -223,6 +223,34 @@ def test_accept_branch_with_intermediate_probability(gpu, orc, synth_small, temp
     assert uphill_acc > 200 and rejected > 200          # both outcomes of the draw < exp(x) comparison really occur
 
 
+def test_segments_keep_recorded_streams_traces_and_uphill_accepts(gpu, orc, synth_small, monkeypatch):
+    # DDD_SEGMENT_STEPS forces chain segments on the one-shot entry points too: a chain parked every 16 steps must resume at the
+    # same position of a RECORDED stream, keep writing its accept trace, and take the same draw < exp(x) decisions (T = 3e8)
+    monkeypatch.setenv("DDD_SEGMENT_STEPS", "16")
+    prot, off, lig = synth_small
+    sel = [0, 2, 4]
+    ligs = [lig[off[i]:off[i + 1]] for i in sel]
+    o2, l2 = gpu.pack_ligands(ligs)
+    rng = np.random.default_rng(42)
+    streams = [rng.random(90 * (4 + 3 * len(l) + 1) * 2) for l in ligs]
+    roff = np.concatenate([[0], np.cumsum([len(s) for s in streams])]).astype(np.int64)
+    with gpu.Receptor(prot) as rec:
+        for temperature in (T, 3.0e8):
+            poses, stats, trace = gpu.run_chains(rec, o2, l2, 1, 90, True, temperature, _p64(gpu), seed=0, recorded=np.concatenate(streams),
+                                                 recorded_offsets=roff, want_trace=True)
+            for c, l in enumerate(ligs):
+                pose_o, st_o, tr_o, _ = orc.chain(prot, l, 90, True, temperature, orc.recorded_stream(streams[c]), want_trace=True)
+                assert np.array_equal(trace[c], tr_o) and stats[c]["status"] == 0
+                for k in ("steps", "accepted", "downhill", "retries", "draws"):
+                    assert stats[c][k] == st_o[k], (c, k)
+                assert np.allclose(gpu.chain_pose(o2, 1, poses, c, 0), pose_o, rtol=0, atol=1e-9)
+        # and the replica pick on top of segmented chains (minimize_batch) still equals the unsegmented call
+        a = gpu.minimize_batch(rec, off, lig, 240, True, T, 3, gpu.default_params(), seed=21)
+        monkeypatch.setenv("DDD_SEGMENT_STEPS", "0")
+        b = gpu.minimize_batch(rec, off, lig, 240, True, T, 3, gpu.default_params(), seed=21)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
 def test_accept_branch_intermediate_probability_recorded_stream_and_f32(gpu, orc, synth_small):
     prot, off, lig = synth_small
     sel = [2, 4, 7]
