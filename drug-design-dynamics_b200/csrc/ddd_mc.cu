@@ -251,7 +251,7 @@ int pick_chain_threads(int64_t n_chains, int sm_count) {
 
 // Chains resident per SM in the SM-persistent engine.  A launch whose chains all fit (<= grid * kSlotsAuto) is
 // dealt statically, ceil(n/grid) per SM; beyond that slots refill from the launch's queue as chains finish.
-constexpr int kSlotsAuto = 10;    // measured on a config 3 shard (4096 chains): 6 / 8 / 10 / 12 / 14 chains per SM -> 56.7 / 57.1 / 57.4 / 57.4 / 57.3 % of FP32 peak
+constexpr int kSlotsAuto = 8;     // same-box A/B on config 3 in full (32 768 chains): 8 -> 18 244 ms, 10 -> 18 293 ms; on a 4096-chain shard 6 / 10 / 12 / 14 give 2 327 / 2 299 / 2 301 / 2 303 ms against 2 314
 int pick_chain_slots(int64_t n_chains, int grid) {
     const int64_t per_sm = (n_chains + grid - 1) / std::max(grid, 1);
     return (int)std::max<int64_t>(1, std::min<int64_t>(kSlotsAuto, per_sm));

@@ -15,7 +15,8 @@ prot = synth.make_receptor(5000)
 off, lig = synth.make_ligands([40] * (4096 // n), prot)
 rec = capi.Receptor(prot)
 scr = capi.Screen(rec, off, lig, 8)
-import os
+import os, signal
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 if os.environ.get('SLOTS'): scr.set_chain_slots(int(os.environ['SLOTS']))
 prm = capi.default_params()
 scr.run(500, 1, 310.15, prm, seed=1); scr.sync()
