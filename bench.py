@@ -100,6 +100,14 @@ def workload(config, rank, world, n_override):
     if config == 5:
         total = n_override or 100000
         lo, hi = rank * total // world, (rank + 1) * total // world
+        if world > 1:
+            # ligands of 20..80 atoms: the ranks' blocks are the library's own cost-balanced contiguous shards (ddd_shard_plan:
+            # balanced by sum(nL + 1)), as a multi-device ddd_init would cut them -- an equal COUNT is up to 0.8 % off balance
+            import ddd_loader
+            m = ddd_loader.load()
+            sizes = m.synth.sweep_sizes(total)
+            plan = m.capi.shard_plan(np.concatenate([[0], np.cumsum(sizes)]), 1, world)
+            lo, hi = int(plan[rank]), int(plan[rank + 1])
         return lo, hi - lo, 1, f"virtual-screen sweep: synthetic {NP}-atom receptor x {total} ligands of 20..80 atoms, 1 chain each, sharded; batched RMSD resident"
     total = n_override or 4096
     lo, hi = rank * total // world, (rank + 1) * total // world
@@ -185,6 +193,9 @@ class StdoutToStderr:
         sys.stdout.flush()
         os.dup2(self.saved, 1)
         os.close(self.saved)
+
+
+T_START = time.perf_counter()
 
 
 def main():
@@ -349,7 +360,9 @@ def run_ours(args, capi, torch, dist, peaks, peaks_src, go, prot, off, lig, firs
     pin_lig.numpy()[:] = lig
     h_lig = pin_lig.numpy()
     launch_s = max_over_ranks(kernel_ms * 1e-3 / max(1, args.steps))
-    n_e2e = args.e2e_calls or int(max(1, min(args.steps, 60.0 // max(launch_s, 1e-3))))
+    # ~60 s of e2e calls, less when the device-resident steps already used most of the driver's per-run limit (870 s)
+    e2e_budget = max(0.0, min(60.0, 780.0 - (time.perf_counter() - T_START) - 30.0))
+    n_e2e = args.e2e_calls or int(max(1, min(args.steps, e2e_budget // max(launch_s, 1e-3))))
     iters = args.chain_steps * replicas               # SimulateEnergyMinimizationParallel runs iterations/numProcs per replica (:97)
     call = lambda seed: capi.minimize_batch(rec, off, h_lig, iters, True, TEMPERATURE, replicas, prm, seed=seed, first_ligand_index=first)   # noqa: E731
     if launch_s < 5.0:
