@@ -529,7 +529,8 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
             A.box_off = 0; A.box_bytes = 0; A.gbox_count = 0;
             if (cut) {                                                       // the cell list's box tables ride in shared memory when they fit
                 const int64_t n_groups = (s->rec->n_units_s + 3) / 4;
-                const int64_t g_entries = 2 * ((n_groups + 1) / 2 * 2), u_entries = 2 * s->rec->n_units_s;
+                const int64_t n_super = (n_groups + 7) / 8;
+                const int64_t g_entries = 2 * ((n_groups + 1) / 2 * 2) + std::max<int64_t>(2 * n_super, 2), u_entries = 2 * s->rec->n_units_s;   // group + super-group boxes
                 const size_t off = (smem + 15) & ~(size_t)15, bytes = (size_t)(g_entries + u_entries) * sizeof(float4);
                 if (s->rec->n_units_s > 0 && off + bytes <= dev.max_smem) {
                     A.box_off = (int)off; A.box_bytes = (int)bytes; A.gbox_count = (int)g_entries;
@@ -890,6 +891,19 @@ int ddd_receptor_create(const double *xyzq, int64_t n_atoms, ddd_receptor **out)
                 hi.x = std::max(hi.x, b.x); hi.y = std::max(hi.y, b.y); hi.z = std::max(hi.z, b.z);
             }
             hgbox[(size_t)(2 * g)] = lo; hgbox[(size_t)(2 * g + 1)] = hi;
+        }
+        // behind them, the boxes of the super-groups of 8 groups (32 units): the top level of the cell-list query
+        const int64_t n_super = (n_groups + 7) / 8;
+        const size_t g_pad = hgbox.size();
+        hgbox.resize(g_pad + (size_t)std::max<int64_t>(2 * n_super, 2), make_float4(kPadCoord, kPadCoord, kPadCoord, 0.f));
+        for (int64_t sg = 0; sg < n_super; ++sg) {
+            float4 lo = make_float4(3e38f, 3e38f, 3e38f, 0.f), hi = make_float4(-3e38f, -3e38f, -3e38f, 0.f);
+            for (int64_t g = 8 * sg; g < std::min<int64_t>(8 * sg + 8, n_groups); ++g) {
+                const float4 a = hgbox[(size_t)(2 * g)], b = hgbox[(size_t)(2 * g + 1)];
+                lo.x = std::min(lo.x, a.x); lo.y = std::min(lo.y, a.y); lo.z = std::min(lo.z, a.z);
+                hi.x = std::max(hi.x, b.x); hi.y = std::max(hi.y, b.y); hi.z = std::max(hi.z, b.z);
+            }
+            hgbox[g_pad + (size_t)(2 * sg)] = lo; hgbox[g_pad + (size_t)(2 * sg + 1)] = hi;
         }
     }
     r->f32.assign(g_devs.size(), nullptr);

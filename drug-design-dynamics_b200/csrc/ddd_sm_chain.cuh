@@ -521,79 +521,70 @@ __device__ __noinline__ void warp_write_lf(const SmArgs &A, const SlotView &s, S
     __syncwarp();
 }
 
-// Cutoff extension, the cell-list query of one pose: the ligand's fp32 bounding box against the box of every receptor
-// unit (32 Morton-ordered atoms); a unit whose box is farther than the cutoff from the ligand's box cannot hold a pair
-// inside the cutoff and is dropped.  Two levels: first the boxes of the groups of 4 units, then the unit boxes of the
-// surviving groups.  The survivors' ids go to the pose buffer's list in ascending order (deterministic); more than
-// kUnitCap survivors: -1, the sums then run over every unit.  One warp, 32 boxes per step.
+// Cutoff extension, the cell-list query of one pose: the ligand's fp32 bounding box against the boxes of the receptor's units
+// (32 Morton-ordered atoms); a unit whose box is farther than the cutoff from the ligand's box cannot hold a pair inside the
+// cutoff and is dropped.  Three levels of boxes -- super-groups of 32 units, groups of 4, units -- each filtered by the same
+// rolled loop (warp_filter_boxes): this query runs once per step on one warp that shares its scheduler with three pair-loop
+// warps, so what it costs is the number of instructions it executes (two levels: 1 100 per step for 1 563 units, ncu).  The
+// survivors' ids go to the pose buffer's list in ascending order (deterministic), padded to a multiple of 8 with the filler
+// unit; more than kUnitCap survivors: -1, the sums then run over every unit.
+//
+// One level: candidate e of [0, n_in << fan_shift) is box (in[e >> fan_shift] << fan_shift) + (e & (fan - 1)) -- every child of
+// every survivor of the level above -- or simply box e when `in` is null (the top level).  Kept when it exists (< n_box) and
+// lies within the cutoff of the pose's box; kept ids are appended to out[0 .. cap) in ascending order.  Returns how many were
+// kept (may exceed cap: the caller treats that as an overflow).  One warp, 32 boxes per trip.
+__device__ __noinline__ int warp_filter_boxes(const float4 *box, int n_box, const unsigned short *in, int n_in, int fan_shift,
+                                              unsigned short *out, int cap, float lox, float loy, float loz, float hix, float hiy, float hiz, float rc2) {
+    const int lane = threadIdx.x & 31;
+    const int n_cand = in ? (n_in << fan_shift) : n_box;
+    int count = 0;
+#pragma unroll 1
+    for (int b = 0; b < n_cand; b += 32) {
+        const int e = min(b + lane, n_cand - 1);
+        const int id = in ? ((int)in[e >> fan_shift] << fan_shift) + (e & ((1 << fan_shift) - 1)) : e;
+        const int idc = min(id, n_box - 1);
+        const float4 bmin = box[2 * idc], bmax = box[2 * idc + 1];
+        const float gx = fmaxf(0.f, fmaxf(bmin.x - hix, lox - bmax.x));
+        const float gy = fmaxf(0.f, fmaxf(bmin.y - hiy, loy - bmax.y));
+        const float gz = fmaxf(0.f, fmaxf(bmin.z - hiz, loz - bmax.z));
+        const bool keep = b + lane < n_cand && id < n_box && gx * gx + gy * gy + gz * gz < rc2;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int idx = count + __popc(m & ((1u << lane) - 1));
+            if (idx < cap) out[idx] = (unsigned short)id;
+        }
+        count += __popc(m);
+    }
+    __syncwarp();
+    return count;
+}
+
 __device__ __noinline__ void warp_build_unit_list(const SmArgs &A, const SlotView &s, SmSlotCtl *c, int buf, int nl) {
     const int lane = threadIdx.x & 31;
-    const float lo[3] = {c->lbox[buf][0], c->lbox[buf][1], c->lbox[buf][2]}, hi[3] = {c->lbox[buf][4], c->lbox[buf][5], c->lbox[buf][6]};
+    const float lox = c->lbox[buf][0], loy = c->lbox[buf][1], loz = c->lbox[buf][2], hix = c->lbox[buf][4], hiy = c->lbox[buf][5], hiz = c->lbox[buf][6];
     const float rc = (float)A.c.prm.cutoff;
     const float rc2 = rc * rc * 1.0001f + 1e-3f;                      // conservative: fp32 boxes, fp32 pose
     unsigned short *ul = s.units(buf);
     const int n_units = A.c.rec.n_units_s;
+    const int n_groups = (n_units + 3) >> 2, n_super = (n_groups + 7) >> 3;
     extern __shared__ __align__(16) unsigned char ddd_sm_smem[];
-    const bool staged = A.box_bytes != 0;
-    const float4 *gbox = staged ? reinterpret_cast<const float4 *>(ddd_sm_smem + A.box_off) : A.c.rec.gbox;
-    const float4 *ubox = staged ? reinterpret_cast<const float4 *>(ddd_sm_smem + A.box_off) + A.gbox_count : A.c.rec.ubox;
-    auto within = [&](const float4 bmin, const float4 bmax) {
-        const float gx = fmaxf(0.f, fmaxf(bmin.x - hi[0], lo[0] - bmax.x));
-        const float gy = fmaxf(0.f, fmaxf(bmin.y - hi[1], lo[1] - bmax.y));
-        const float gz = fmaxf(0.f, fmaxf(bmin.z - hi[2], lo[2] - bmax.z));
-        return gx * gx + gy * gy + gz * gz < rc2;
-    };
-    // level 1: the boxes of the groups of 4 units; the survivors' ids are staged in the (idle) dynamic near-pair list.
-    // Rolled loops on purpose: the body is fetched once and then runs out of the instruction cache (see the note above).
-    unsigned short *grp = reinterpret_cast<unsigned short *>(s.dyn_list());
-    constexpr int kGroupCap = kNearCap * 2;                               // ushort entries in that list
-    const int n_groups = (n_units + 3) >> 2;
-    int n_g = 0;
-    // the query is one warp chasing global loads: pull every group box towards L1 first (one round trip instead of one per step)
-    if (!staged) {
-#pragma unroll 1
-        for (int b = lane; b < n_groups; b += 32) asm volatile("prefetch.global.L1 [%0];" :: "l"(A.c.rec.gbox + 2 * b));
-    }
-#pragma unroll 1
-    for (int b = 0; b < n_groups; b += 32) {
-        const int g = b + lane;
-        const int gc = min(g, n_groups - 1);
-        const bool keep = g < n_groups && nl > 0 && within(gbox[2 * gc], gbox[2 * gc + 1]);
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            const int idx = n_g + __popc(m & ((1u << lane) - 1));
-            if (idx < kGroupCap) grp[idx] = (unsigned short)g;
-        }
-        n_g += __popc(m);
-    }
-    __syncwarp();
-    // level 2: the 4 unit boxes of every surviving group, 8 groups per step; ascending ids are preserved
+    // group boxes (padded to an even count), then super-group boxes, then unit boxes: staged behind the slots when they fit
+    const float4 *gbox = A.box_bytes ? reinterpret_cast<const float4 *>(ddd_sm_smem + A.box_off) : A.c.rec.gbox;
+    const float4 *sbox = gbox + 2 * ((n_groups + 1) & ~1);
+    const float4 *ubox = A.box_bytes ? gbox + A.gbox_count : A.c.rec.ubox;
+    // the survivors of the two upper levels are staged in the (idle) dynamic near-pair list
+    unsigned short *sup = reinterpret_cast<unsigned short *>(s.dyn_list());
+    constexpr int kSuperCap = 64, kGroupCap = kNearCap * 2 - kSuperCap;   // ushort entries; more survivors than that are > kUnitCap units anyway
+    unsigned short *grp = sup + kSuperCap;
     int count = 0;
-    if (n_g > kGroupCap) count = kUnitCap + 1;                            // more than 1024 units in reach: overflow
-    else {
-        if (!staged) {
-#pragma unroll 1
-            for (int e = lane; e < 4 * n_g; e += 32) {
-                const int u = min(4 * (int)grp[e >> 2] + (e & 3), n_units - 1);
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(A.c.rec.ubox + 2 * u));
-            }
-        }
-#pragma unroll 1
-        for (int b = 0; b < 4 * n_g; b += 32) {
-            const int e = b + lane;
-            const int u = e < 4 * n_g ? 4 * (int)grp[e >> 2] + (e & 3) : n_units;
-            const int uc = min(u, n_units - 1);
-            const float4 bmin = ubox[2 * uc], bmax = ubox[2 * uc + 1];
-            const bool keep = within(bmin, bmax) && u < n_units;
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (keep) {
-                const int idx = count + __popc(m & ((1u << lane) - 1));
-                if (idx < kUnitCap) ul[idx] = (unsigned short)u;
-            }
-            count += __popc(m);
+    if (nl > 0 && n_units > 0) {
+        const int n_s = warp_filter_boxes(sbox, n_super, nullptr, 0, 0, sup, kSuperCap, lox, loy, loz, hix, hiy, hiz, rc2);
+        count = kUnitCap + 1;
+        if (n_s <= kSuperCap) {
+            const int n_g = warp_filter_boxes(gbox, n_groups, sup, n_s, 3, grp, kGroupCap, lox, loy, loz, hix, hiy, hiz, rc2);
+            if (n_g <= kGroupCap) count = warp_filter_boxes(ubox, n_units, grp, n_g, 2, ul, kUnitCap, lox, loy, loz, hix, hiy, hiz, rc2);
         }
     }
-    __syncwarp();
     if (count <= kUnitCap) {                                                // filler entries up to the next multiple of 8 (kUnitCap is one)
         const int padded = (count + 7) & ~7;
         if (count + lane < padded) ul[count + lane] = (unsigned short)((n_units + 7) & ~7);
