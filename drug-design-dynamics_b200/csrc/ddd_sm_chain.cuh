@@ -158,10 +158,11 @@ struct SlotView {
 struct SmView {
     unsigned char *raw;
     int slots, cap, ulb;
+    int stride;              // bytes per slot: slot_fixed_bytes(cap) + cap * kAtomBytes + ulb (computed once, not at every use)
     __device__ __forceinline__ int *live() const { return reinterpret_cast<int *>(raw); }
     // scheduling key of a slot: the chain's step count while it has work to hand out, kKeyNone otherwise
     __device__ __forceinline__ int *keys() const { return reinterpret_cast<int *>(raw + 16); }
-    __device__ __forceinline__ unsigned char *block(int s) const { return raw + kCtaHeaderBytes + (size_t)s * (slot_fixed_bytes(cap) + cap * kAtomBytes + ulb); }   // ulb: all per-slot extras
+    __device__ __forceinline__ unsigned char *block(int s) const { return raw + kCtaHeaderBytes + s * stride; }   // ulb: all per-slot extras
     __device__ __forceinline__ SmSlotCtl *ctl(int s) const { return reinterpret_cast<SmSlotCtl *>(block(s)); }
     __device__ __forceinline__ double *items(int s) const { return reinterpret_cast<double *>(block(s) + sizeof(SmSlotCtl)); }
     __device__ __forceinline__ SlotView slot(int s) const {
@@ -327,19 +328,13 @@ __device__ __forceinline__ double sm_item_f32_cut(const SmArgs &A, const SlotVie
         }
         return warp_sum(acc);
     }
-    // the sorted receptor of a large complex lives in L2, not L1: the next call's atoms are prefetched into L1 while
-    // this call's pairs are summed
     const int lane = threadIdx.x & 31;
     const float rc_q = rci * c->qsum;                   // (1/cutoff) * sum_l q_l: the constant part of the shifted terms
     for (; j + 8 <= j1; j += 8) {
         int ub[8];
 #pragma unroll
         for (int a = 0; a < 8; ++a) ub[a] = 32 * (ns >= 0 ? (int)ul[j + a] : j + a);
-        if (j + 16 <= j1) {
-#pragma unroll
-            for (int a = 0; a < 8; ++a)
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(rec + 32 * (ns >= 0 ? (int)ul[j + 8 + a] : j + 8 + a) + lane));
-        }
+        // (no L1 prefetch of the next call's atoms: measured, same box, 314 -> 310 ms without it -- 32 more instructions per call)
         // ONE loop variant, the clamped one: with ~60 units per evaluation this kernel is bound by instruction fetch on its
         // serial side (ncu: half of those warps' stall samples are no_instruction; the step's hot code is ~45 KB against a
         // 32 KB instruction cache), and a second copy of the loop without the clamp's two FMNMX cost more there than it saved
@@ -819,7 +814,7 @@ __device__ __noinline__ bool sm_publish(const SmArgs &A, const SmView &V, int sl
     if (mode_cut<MODE>(A)) {
         const int ns = c->n_surv[c->i_trial];
         const int nu = surv_len(A, ns);
-        upi_e = DDD_CUT_UPI * max(1, (nu + DDD_CUT_UPI * kSmMaxItems - 1) / (DDD_CUT_UPI * kSmMaxItems));  // runs of 16 units (two 8-atoms-per-lane calls; the second is prefetched), more only for huge lists
+        upi_e = DDD_CUT_UPI * max(1, (nu + DDD_CUT_UPI * kSmMaxItems - 1) / (DDD_CUT_UPI * kSmMaxItems));  // runs of 16 units (two 8-atoms-per-lane calls), more only for huge lists
         n_e = (nu + upi_e - 1) / upi_e;
         if ((threadIdx.x & 31) == 0 && mode == 0) c->units_done += surv_real(A, ns);
     }
@@ -1219,6 +1214,7 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
     extern __shared__ __align__(16) unsigned char ddd_sm_smem[];
     SmView V;
     V.raw = ddd_sm_smem; V.slots = A.slots; V.cap = A.c.nl_cap; V.ulb = A.unit_list_bytes + A.gsum_bytes + A.lj_bytes;
+    V.stride = slot_fixed_bytes(V.cap) + V.cap * kAtomBytes + V.ulb;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = A.slots;
 #ifdef DDD_SM_PROF
