@@ -328,7 +328,6 @@ __device__ __forceinline__ double sm_item_f32_cut(const SmArgs &A, const SlotVie
         }
         return warp_sum(acc);
     }
-    const int lane = threadIdx.x & 31;
     const float rc_q = rci * c->qsum;                   // (1/cutoff) * sum_l q_l: the constant part of the shifted terms
     for (; j + 8 <= j1; j += 8) {
         int ub[8];
