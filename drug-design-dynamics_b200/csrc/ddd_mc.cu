@@ -781,7 +781,7 @@ int ddd_num_devices(void) {
 
 const char *ddd_last_error(void) { return g_err.c_str(); }
 
-const char *ddd_version(void) { return "ddd_mc 0.3 (sm_100a; SM-persistent chain engine: 16 warps per SM, speculative proposals, per-group pair sums; resident randomise/shift/pick/RMSD/argmin pipeline)"; }
+const char *ddd_version(void) { return "ddd_mc 0.4 (sm_100a; SM-persistent chain engine: 16 warps per SM, speculative proposals, per-group pair sums, chain segments; resident randomise/shift/pick/RMSD/argmin pipeline)"; }
 
 void ddd_params_default(ddd_params *p) {
     if (!p) return;
