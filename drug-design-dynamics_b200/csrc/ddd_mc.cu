@@ -466,7 +466,7 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
         if (s->track_best && n_local > 0 && (s->threads_override > 0 || !fits_sm_engine))
             return fail(DDD_EINVAL, "best-ever tracking needs the SM-persistent engine (chain_threads 0 and a ligand that fits one SM's shared memory)");
         if (s->threads_override <= 0 && n_local > 0 && fits_sm_engine) {
-            // SM-persistent engine: one 32-warp CTA per SM, K resident chains each (ddd_sm_chain.cuh)
+            // SM-persistent engine: one 16-warp CTA per SM, K resident chains each (ddd_sm_chain.cuh)
             // its epilogue also leaves CalculateRMSD(final pose, reference pose) of every chain in d_rmsd (CompareRMSD :40-45)
             if (!d.d_rmsd) { if (int rc = dev_alloc(&d.d_rmsd, (size_t)n_local)) return rc; }
             a.ref_xyzq = d.d_ref ? d.d_ref : d.d_lig; a.out_rmsd = d.d_rmsd; d.fused_rmsd = true;

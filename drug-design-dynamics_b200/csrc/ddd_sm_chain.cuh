@@ -1,6 +1,6 @@
 // ddd_sm_chain.cuh -- SM-persistent engine of the Metropolis chain kernel (sm_100a).
 //
-// One CTA of 32 warps owns one SM and keeps up to K chains ("slots") of
+// One CTA of 16 warps (512 threads, 128 registers) owns one SM and keeps up to K chains ("slots") of
 // SimulateEnergyMinimizationOneProc (reference metropolisMethod/metropolis.go:116-136) resident in
 // shared memory.  A chain alternates between
 //   * an ENERGY phase: CalculateEnergy (:247-262) cut into work items (runs of receptor warp tiles)
@@ -9,9 +9,12 @@
 //     AcceptMove (:141-149), the next proposal (:154-208) with its collision retries (:229-242).
 // There is no CTA-wide barrier inside the step loop: a chain that is proposing (latency-bound fp64 +
 // Philox work of one warp) overlaps with the pair sums of the other chains, and when chains finish the
-// remaining ones inherit all 32 warps -- the SM stays busy until its last chain ends, which the
+// remaining ones inherit all 16 warps -- the SM stays busy until its last chain ends, which the
 // one-CTA-per-chain engine (ddd_kernels.cuh) cannot do when a launch has only ~7 chains per SM.
-// Chains beyond grid*K are pulled from a global counter as slots free up.
+// Chains beyond grid*K are pulled from a global counter as slots free up; when a launch has more chains than slots (or
+// chains of unequal cost per step) a chain is cut into SEGMENTS: every few hundred steps it is parked in its own output
+// records and queues behind the launch's other chains, so that any SM resumes it and all SMs run dry together
+// (sm_park_chain / sm_load_chain).
 //
 // SPECULATIVE PROPOSALS.  At T = 310 K with K = 9e9 nearly every step is rejected, and after a reject the
 // next proposal is fully determined: it starts from the unchanged current pose and from stream position pos + 1 (the

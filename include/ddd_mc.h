@@ -191,7 +191,7 @@ int ddd_randomize_pose_batch(const int64_t *offsets, double *lig_xyzq_inout, int
  * of the chain kernel on its launch stream; download copies final poses + stats to the host. */
 int    ddd_screen_create(const ddd_receptor *r, const int64_t *offsets, const double *lig_xyzq,
                          int64_t n_lig, int32_t replicas, uint64_t first_chain_id, ddd_screen **out);
-/* Engine of the chain kernel for subsequent runs.  Default (both 0): the SM-persistent engine -- one 32-warp
+/* Engine of the chain kernel for subsequent runs.  Default (both 0): the SM-persistent engine -- one 16-warp
  * CTA per SM keeps `slots` chains resident and every warp takes pair-sum work items of any of them -- with the
  * chains per SM chosen from the chain count.  set_chain_slots(k > 0) fixes k (1..16; clipped to what fits in
  * shared memory).  set_chain_threads(32|64|128|256) selects the one-CTA-per-chain engine with that CTA width;

@@ -44,7 +44,7 @@ def test_replay_matches_oracle_every_cta_width(gpu, orc, synth_small, rotate, wi
 @pytest.mark.parametrize("rotate", [False, True])
 @pytest.mark.parametrize("slots", [0, 1, 3, 16])
 def test_replay_matches_oracle_sm_persistent_engine(gpu, orc, synth_small, rotate, slots):
-    # the default engine: one 32-warp CTA per SM, `slots` resident chains, warps take pair-sum items of any chain
+    # the default engine: one 16-warp CTA per SM, `slots` resident chains, warps take pair-sum items of any chain
     prot, off, lig = synth_small
     with gpu.Receptor(prot) as rec:
         scr = gpu.Screen(rec, off, lig, 3)
