@@ -197,7 +197,7 @@ int    ddd_screen_create(const ddd_receptor *r, const int64_t *offsets, const do
  * shared memory).  set_chain_threads(32|64|128|256) selects the one-CTA-per-chain engine with that CTA width;
  * set_chain_threads(0) returns to the default.  Results do not depend on the engine in F64 precision. */
 int    ddd_screen_set_chain_threads(ddd_screen *s, int32_t threads);
-int32_t ddd_screen_chain_threads(const ddd_screen *s);   /* CTA width used by the last run (1024: SM-persistent) */
+int32_t ddd_screen_chain_threads(const ddd_screen *s);   /* CTA width used by the last run (512: SM-persistent engine) */
 int    ddd_screen_set_chain_slots(ddd_screen *s, int32_t slots);
 int32_t ddd_screen_chain_slots(const ddd_screen *s);     /* chains per SM of the last run (0: one CTA per chain) */
 /* Chain segments of the SM-persistent engine: every `steps` steps (rounded up to a power of two) a chain leaves its slot --
