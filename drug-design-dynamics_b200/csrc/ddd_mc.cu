@@ -554,7 +554,7 @@ int screen_run_impl(ddd_screen *s, int64_t steps, int32_t rotate, double tempera
         }
         const int threads = s->threads_override > 0 ? s->threads_override : pick_chain_threads(n_local, dev.sm_count);
         const size_t smem = chain_smem_bytes(d.nl_cap, threads);
-        d.threads = threads; d.slots = 0;
+        d.threads = threads; d.slots = 0; d.seg_steps = 0;
         CUDA_TRY(cudaEventRecord(d.ev0, dev.stream));
 #define LAUNCH_CHAIN(T, PR)                                                                   \
         do { if (int rc = set_smem(mc_chain_kernel<T, PR>, smem)) return rc;                   \
