@@ -41,6 +41,25 @@ def test_shard_plan_edge_cases(capi):
         capi.shard_plan(np.array([0, 3, 2]), 1, 2)                                  # not monotone
 
 
+def test_bench_rank_blocks_cover_the_workload_and_balance_config5(ddd):
+    # bench.py's per-rank ligand blocks: contiguous, disjoint, complete for every config and world size; config 5 (20..80-atom
+    # ligands) follows the library's own cost-balanced shard plan instead of an equal count
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("ddd_bench", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for config, total in ((3, 4096), (5, 100000), (5, 1003)):
+        for world in (1, 2, 4, 8):
+            blocks = [bench.workload(config, r, world, total if config == 5 else 0)[:2] for r in range(world)]
+            assert blocks[0][0] == 0 and sum(n for _, n in blocks) == total
+            assert all(blocks[r][0] + blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
+    sizes = ddd.synth.sweep_sizes(100000)
+    work = [int(sizes[lo:lo + n].sum() + n) for lo, n in (bench.workload(5, r, 8, 0)[:2] for r in range(8))]
+    assert max(work) <= 1.001 * np.mean(work)                                     # an equal count is 0.8 % off
+    assert bench.workload(2, 3, 8, 0)[:3] == (3 * 1024, 1024, 1)                   # config 2 / 4: weak scaling, 1024 ligands per rank
+
+
 def test_pack_unpack_roundtrip(capi):
     ligs = [np.random.default_rng(i).normal(size=(n, 4)) for i, n in enumerate([3, 0, 7, 1])]
     off, x = capi.pack_ligands(ligs)
