@@ -16,7 +16,9 @@ import "unsafe"
 
 // CalculateRMSD: validateResults.go:50-65.  Same panic as the reference when `reference` is shorter.
 func CalculateRMSD(simulated, reference Molecule) float64 {
-	_ = reference.atoms[:len(simulated.atoms)] // index out of range panic, as in the reference's loop
+	if n := len(simulated.atoms); n > 0 {
+		_ = reference.atoms[n-1] // index out of range panic when `reference` is shorter, as in the reference's loop (:56); a slice expression would only check the capacity
+	}
 	out := CalculateRMSDBatch([]Molecule{simulated}, []Molecule{reference})
 	return out[0]
 }
