@@ -52,6 +52,9 @@ constexpr int kGroupsPerItemBusy = 10;     // 128-atom groups per item while >= 
 #ifndef DDD_SM_IDLE_NS
 #define DDD_SM_IDLE_NS 100
 #endif
+#ifndef DDD_SM_IDLE_MAX_NS
+#define DDD_SM_IDLE_MAX_NS 400             // idle polling backs off from DDD_SM_IDLE_NS to this (measured: caps of 100 / 400 / 800 / 1600 ns -> lone worst chain 530 / 518 / 513 / 514 ms, lone chain without retries 129 / 130 / 133 / 143 ms)
+#endif
 #ifndef DDD_CUT_UPI
 #define DDD_CUT_UPI 16                     // cutoff extension: receptor units per pair-sum item (a multiple of 8)
 #endif
@@ -1235,6 +1238,7 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
     __syncthreads();
     for (int sl = warp; sl < K; sl += kSmWarps) sm_serial_phase<PRECISE, MODE>(A, V, sl, (long long)sl * gridDim.x + blockIdx.x);
     const unsigned keys_s = (unsigned)__cvta_generic_to_shared(V.keys());
+    int idle_n = 0;                                         // consecutive looks that found nothing
 
     for (;;) {
         // the chain that is furthest behind goes first: chains of an SM advance in step and end together, and one that
@@ -1247,9 +1251,14 @@ __global__ void __launch_bounds__(kSmThreads, 1) mc_sm_kernel(const __grid_const
         const int sid = best == kKeyNone ? -1 : __ffs(__ballot_sync(0xffffffffu, key == best)) - 1;     // ties: the lowest slot
         if (sid < 0) {
             if (ld_volatile(V.live()) == 0) break;
-            { PROF_T0(); __nanosleep(DDD_SM_IDLE_NS); PROF_ADD(4); PROF_CNT(12, 1); }
+            // back off while nothing turns up: a warp that polls every 100 ns issues ~0.2 instructions per cycle, and three of
+            // them share a scheduler with the one warp that works through a chain's collision retries at the end of a launch
+            // (ncu on a lone chain: 680 polls per attempt, 14 000 poll instructions against the attempt's 600)
+            { PROF_T0(); __nanosleep(min(DDD_SM_IDLE_NS << idle_n, DDD_SM_IDLE_MAX_NS)); PROF_ADD(4); PROF_CNT(12, 1); }
+            if (idle_n < 5) ++idle_n;
             continue;
         }
+        idle_n = 0;
         SmSlotCtl *c = V.ctl(sid);
         int it = 0;
         if (lane == 0) it = atomicAdd(&c->next_item, 1);
